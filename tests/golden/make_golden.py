@@ -1,0 +1,180 @@
+"""Generate golden fixtures from the REFERENCE itself (build container only).
+
+Run:  python tests/golden/make_golden.py          (needs /root/reference)
+
+The reference holds no golden vectors for the GNN head, so
+the oracle is pinned against outputs of the reference's own ``methods/gnn.py``
+and ``methods/gnnnet.py`` / ``gnnnet_copy.py`` imported from /root/reference and
+run on CPU in float32 and float64.  /root/reference does not travel to the GPU
+box, so the outputs are committed as small ``.npz`` files next to this script.
+
+Fixtures
+--------
+gnn_tiny.npz       GNN_nl(13, 16, 3), B=3, N=7: full state_dict, input, output
+                   and every gradient, float64 (truth) + float32 output.
+gnn_5w5s.npz       GNN_nl(133, 96, 5), B=16, N=30 (config C1 head shape): input,
+                   seeded state_dict (stored in full), fp64 output and every gradient.
+head_5w5s.npz      GnnNet head on features (fc -> graphs -> gnn -> select):
+                   scores + loss for n_query 16 and the finetune.py is_feature path (15).
+head_50c.npz       gnnnet_copy (compressed 50-shot, N=130) scores on features
+                   (parameters: those of head_5w5s.npz).
+sampler.npz        EpisodicBatchSampler / generate_perm class draws, support_label,
+                   query labels.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _import_reference():
+    sys.path.insert(0, REF)
+    # gnnnet.py:40,69 hard-code .cuda(); identity shim for the CPU container
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    nn.Module.cuda = lambda self, *a, **k: self
+    from methods import gnn as ref_gnn
+    from methods import gnnnet as ref_gnnnet
+    from methods import gnnnet_copy as ref_gnnnet_copy
+    import backbone as ref_backbone
+    return ref_gnn, ref_gnnnet, ref_gnnnet_copy, ref_backbone
+
+
+def _perturb_bn(module, gen):
+    """Move BN affine terms off (1,0) so gamma/beta wiring is exercised."""
+    with torch.no_grad():
+        for name, prm in module.named_parameters():
+            if ".bn" in "." + name and name.endswith("weight") and prm.dim() == 1:
+                prm.add_(0.25 * torch.randn(prm.shape, generator=gen, dtype=prm.dtype))
+            elif ".bn" in "." + name and name.endswith("bias"):
+                prm.add_(0.2 * torch.randn(prm.shape, generator=gen, dtype=prm.dtype))
+
+
+def _run_gnn(ref_gnn, fin, nf, n_way, bsz, n, seed):
+    """fp64 (truth) and fp32 runs of the reference GNN_nl on float32-representable
+    parameters / inputs, so that everything stored is self-consistent."""
+    torch.manual_seed(seed)
+    net32 = ref_gnn.GNN_nl(fin, nf, n_way)
+    gen = torch.Generator().manual_seed(seed + 1)
+    _perturb_bn(net32, gen)
+    x = torch.randn(bsz, n, fin, generator=gen)
+    proj = torch.randn(bsz, n, n_way, generator=gen)
+    net = ref_gnn.GNN_nl(fin, nf, n_way).double()
+    net.load_state_dict({k: v.double() for k, v in net32.state_dict().items()})
+    x64 = x.double().requires_grad_(True)
+    out64 = net(x64)
+    (out64 * proj.double()).sum().backward()
+    rec = {"x": x.numpy(), "proj": proj.numpy(), "out64": out64.detach().numpy(),
+           "dx64": x64.grad.numpy()}
+    for k, v in net32.state_dict().items():
+        rec["p." + k] = v.numpy()
+    for k, v in net.named_parameters():
+        rec["g." + k] = v.grad.numpy()
+    x32 = x.clone().requires_grad_(True)
+    out32 = net32(x32)
+    (out32 * proj).sum().backward()
+    rec["out32"] = out32.detach().numpy()
+    rec["dx32"] = x32.grad.numpy()
+    # the reference's own fp32 error vs fp64, the yardstick for the fp32-path tolerance
+    for k, v in net32.named_parameters():
+        g64 = rec["g." + k]
+        den = np.linalg.norm(g64)
+        rec["e32." + k] = np.float64(np.linalg.norm(v.grad.numpy() - g64) / den if den > 0 else 0.0)
+    return rec
+
+
+def main():
+    ref_gnn, ref_gnnnet, ref_gnnnet_copy, ref_backbone = _import_reference()
+    torch.set_num_threads(8)
+
+    rec = _run_gnn(ref_gnn, 13, 16, 3, 3, 7, seed=1234)
+    np.savez_compressed(os.path.join(HERE, "gnn_tiny.npz"), **rec)
+
+    rec = _run_gnn(ref_gnn, 133, 96, 5, 16, 30, seed=77)
+    for k in list(rec):
+        if k.startswith("g."):
+            rec[k] = rec[k].astype(np.float32)      # halve the file; 1e-7 rel is ample
+    np.savez_compressed(os.path.join(HERE, "gnn_5w5s.npz"), **rec)
+
+    # ---- GnnNet head on features -------------------------------------------------
+    torch.manual_seed(5)
+    np.random.seed(10)
+    m = ref_gnnnet.GnnNet(ref_backbone.ResNet10, n_way=5, n_support=5)
+    gen = torch.Generator().manual_seed(6)
+    _perturb_bn(m.gnn, gen)
+    head = {}
+    for k, v in m.state_dict().items():
+        if k.startswith("fc.") or k.startswith("gnn."):
+            head["p." + k] = v.numpy()
+    head["support_label"] = m.support_label.numpy()
+    feat15 = torch.randn(5, 5 + 15, 512, generator=gen)
+    m.n_query = 15
+    s15 = m.set_forward(feat15, is_feature=True)           # finetune.py:316 path
+    head["feat15"] = feat15.numpy()
+    head["scores15"] = s15.detach().numpy()
+    # training shape (n_query 16): drive fc + forward_gnn directly on features
+    feat16 = torch.randn(5, 5 + 16, 512, generator=gen)
+    m.n_query = 16
+    z = m.fc(feat16.view(-1, 512)).view(5, -1, 128)
+    z_stack = [torch.cat([z[:, :5], z[:, 5 + i:5 + i + 1]], dim=1).view(1, -1, 128) for i in range(16)]
+    s16 = m.forward_gnn(z_stack)
+    y = torch.from_numpy(np.repeat(range(5), 16))
+    loss16 = m.loss_fn(s16, y)
+    head["feat16"] = feat16.numpy()
+    head["scores16"] = s16.detach().numpy()
+    head["loss16"] = np.float64(loss16.item())
+    head["y16"] = y.numpy()
+    np.savez_compressed(os.path.join(HERE, "head_5w5s.npz"), **head)
+
+    # ---- compressed 50-shot ------------------------------------------------------
+    torch.manual_seed(9)
+    mc = ref_gnnnet_copy.GnnNet(ref_backbone.ResNet10, n_way=5, n_support=50)
+    # same fc/gnn parameters as head_5w5s.npz (identical architecture) -- not stored twice
+    sd = mc.state_dict()
+    for k, v in m.state_dict().items():
+        if k.startswith("fc.") or k.startswith("gnn."):
+            sd[k] = v.clone()
+    mc.load_state_dict(sd)
+    c = {}
+    c["support_label"] = mc.support_label.numpy()
+    c["n_support_eff"] = np.int64(mc.n_support)
+    feat = torch.randn(5, 50 + 15, 512, generator=gen)
+    mc.n_query = 15
+    with torch.no_grad():
+        sc = mc.set_forward(feat, is_feature=True)
+    c["feat"] = feat.numpy()
+    c["scores"] = sc.numpy()
+    np.savez_compressed(os.path.join(HERE, "head_50c.npz"), **c)
+
+    # ---- sampling / label indexing ------------------------------------------------
+    s = {}
+    sys.path.insert(0, REF)
+    from datasets import miniImageNet_few_shot as mini
+    torch.manual_seed(10)
+    smp = mini.EpisodicBatchSampler(64, 5, 100)
+    s["mini_train"] = torch.stack(list(iter(smp))).numpy()
+    for name, n_cls, seed in (("CropDisease", 38, 10), ("EuroSAT", 10, 7), ("ISIC", 7, 10), ("Chest", 7, 11)):
+        # datasets/<name>_few_shot.py: SetDataset2 re-seeds everything to `seed`, then
+        # EpisodicBatchSampler2.generate_perm draws 600 class permutations
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        from datasets import CropDisease_few_shot as crop
+        smp2 = crop.EpisodicBatchSampler2(n_cls, 5, 600)
+        s["perm_" + name] = torch.stack(smp2.generate_perm()).numpy()
+    for n_way, n_sup in ((5, 5), (5, 20), (5, 25)):
+        mm = ref_gnnnet.GnnNet(ref_backbone.ResNet10, n_way=n_way, n_support=n_sup)
+        s[f"support_label_{n_way}_{n_sup}"] = mm.support_label.numpy()
+    s["y_query_5_16"] = np.repeat(range(5), 16)
+    s["y_query_5_15"] = np.repeat(range(5), 15)
+    np.savez_compressed(os.path.join(HERE, "sampler.npz"), **s)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+/*
+ * mft_gnn.h -- C ABI of the B200-native GNN few-shot head (libmft_gnn.so).
+ *
+ * The reference (johncai117/Meta-Fine-Tuning) has no FFI layer: its boundary for
+ * this path is the Python nn.Module surface of methods/gnn.py.  The host side of
+ * this repo (meta-fine-tuning_b200/gnn.py) mirrors that surface and binds the
+ * entry points below through ctypes; each entry point names the reference
+ * function it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (allocated by
+ *    PyTorch), contiguous float32 unless stated, and must stay alive until the
+ *    stream has executed the call;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *    entry point synchronises the device or allocates device memory;
+ *  - return value 0 = success; non-zero = failure, message via mft_last_error()
+ *    (thread-local).  There is no CPU fallback: on a device that is not
+ *    sm_100 the compute entry points fail with MFT_ERR_DEVICE;
+ *  - `precision`: MFT_PREC_FP32 = CUDA-core fp32 path; MFT_PREC_TF32 = tcgen05
+ *    kind::tf32 tensor-core path for the edge-MLP GEMMs (fp32 accumulate in
+ *    TMEM, fp32 statistics / softmax / Gconv).
+ *
+ * Node features live in a strided matrix x[(b*N + n) * ldx + f] so that the
+ * dense concatenation of GNN_nl (gnn.py:161) is a column range of one buffer.
+ */
+#ifndef MFT_GNN_H
+#define MFT_GNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFT_PREC_FP32 0
+#define MFT_PREC_TF32 1
+
+#define MFT_OK            0
+#define MFT_ERR_ARG       1
+#define MFT_ERR_DEVICE    2
+#define MFT_ERR_CUDA      3
+#define MFT_ERR_UNSUPPORTED 4
+
+#define MFT_MAX_LAYERS 3   /* Wcompute/Gconv pairs in one GNN_nl (num_layers 2 + last) */
+
+/* Parameters of one Wcompute (gnn.py:60-76): conv2d_k.weight is [C_k, C_{k-1}]
+ * row-major (the [out,in,1,1] tensor as stored), C = {F, 2nf, 2nf, nf, nf}.
+ * conv2d_{1..4}.bias is not read: batch-statistic BatchNorm cancels it exactly. */
+typedef struct {
+    const float* conv_w[4];
+    const float* bn_g[4];
+    const float* bn_b[4];
+    const float* last_w;   /* conv2d_last.weight [nf] */
+    const float* last_b;   /* conv2d_last.bias   [1]  */
+} mft_wcompute_params;
+
+/* Gradient destinations for one Wcompute; the library overwrites them. */
+typedef struct {
+    float* conv_w[4];
+    float* conv_b[4];      /* analytically zero -> written as 0 */
+    float* bn_g[4];
+    float* bn_b[4];
+    float* last_w;
+    float* last_b;         /* analytically zero -> written as 0 */
+} mft_wcompute_grads;
+
+/* Parameters of one Gconv (gnn.py:32-41): fc.weight [n_out, 2F], fc.bias [n_out],
+ * bn.weight/bias [n_out] or NULL when bn_bool is False. */
+typedef struct {
+    const float* fc_w;
+    const float* fc_b;
+    const float* bn_g;
+    const float* bn_b;
+} mft_gconv_params;
+
+typedef struct {
+    float* fc_w;
+    float* fc_b;
+    float* bn_g;
+    float* bn_b;
+} mft_gconv_grads;
+
+/* Whole GNN_nl (gnn.py:134-152): layer_w0, layer_l0, layer_w1, layer_l1,
+ * w_comp_last, layer_last. */
+typedef struct {
+    mft_wcompute_params w[MFT_MAX_LAYERS];
+    mft_gconv_params    l[MFT_MAX_LAYERS];
+} mft_gnn_params;
+
+typedef struct {
+    mft_wcompute_grads w[MFT_MAX_LAYERS];
+    mft_gconv_grads    l[MFT_MAX_LAYERS];
+} mft_gnn_grads;
+
+/* ---- library / device -------------------------------------------------- */
+
+/* Message of the last failure on this thread ("" if none). */
+const char* mft_last_error(void);
+/* ABI version of this header. */
+int mft_version(void);
+/* 0 when `device` is an sm_100 part this library can run on. */
+int mft_device_check(int device);
+/* 1 when the tcgen05 TF32 path supports this Wcompute shape, else 0. */
+int mft_tf32_supported(int F, int nf);
+
+/* ---- Wcompute: replaces Wcompute.forward (gnn.py:78-132) ------------------ */
+
+/* Bytes of the activation tape kept from forward to backward / of scratch. */
+size_t mft_wcompute_saved_bytes(int B, int N, int F, int nf);
+size_t mft_wcompute_workspace_bytes(int B, int N, int F, int nf);
+
+/* x [B*N, ldx] (first F columns used) -> adj [B,N,N]: adj[b,i,:] =
+ * softmax_j(edge_mlp(|x_i - x_j|) - 1e8*[i==j]).  The reference's output
+ * [B,N,N,2] is stack(identity, adj); the identity half is built by the host. */
+int mft_wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf,
+                     const mft_wcompute_params* p, float* adj,
+                     void* saved, void* workspace, int precision, void* stream);
+
+/* Backward: d_adj [B,N,N] -> dx (ACCUMULATED into dx[(b*N+n)*ldx + f], f < F)
+ * and parameter gradients (overwritten). */
+int mft_wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf,
+                     const mft_wcompute_params* p, const float* adj, const float* d_adj,
+                     float* dx, const mft_wcompute_grads* g,
+                     void* saved, void* workspace, int precision, void* stream);
+
+/* ---- Gconv: replaces gmul + Gconv.forward (gnn.py:16-28, 43-56) ------------- */
+
+size_t mft_gconv_saved_bytes(int B, int N, int F, int n_out);
+size_t mft_gconv_workspace_bytes(int B, int N, int F, int n_out);
+
+/* out[(b*N+n)*ldo + c] = act(BN1d(x Wa^T + adj (x Wb^T) + b)), c < n_out.
+ * bn: p->bn_g != NULL; lrelu != 0 applies the LeakyReLU of gnn.py:160. */
+int mft_gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out,
+                  const mft_gconv_params* p, int lrelu, float* out, int ldo,
+                  void* saved, void* workspace, void* stream);
+
+/* d_out [B*N, ldo] -> dx (ACCUMULATED, ldx), d_adj [B,N,N] (overwritten),
+ * parameter gradients (overwritten). */
+int mft_gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out,
+                  const mft_gconv_params* p, int lrelu, const float* d_out, int ldo,
+                  float* dx, float* d_adj, const mft_gconv_grads* g,
+                  void* saved, void* workspace, void* stream);
+
+/* ---- GNN_nl: replaces GNN_nl.forward (gnn.py:154-166) in one call ---------- */
+
+size_t mft_gnn_saved_bytes(int B, int N, int F0, int nf, int n_way);
+size_t mft_gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way);
+
+/* x [B,N,F0] contiguous -> out [B,N,n_way] contiguous. */
+int mft_gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way,
+                const mft_gnn_params* p, float* out,
+                void* saved, void* workspace, int precision, void* stream);
+
+/* d_out [B,N,n_way] -> dx [B,N,F0] (overwritten) + every parameter gradient. */
+int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way,
+                const mft_gnn_params* p, float* dx, const mft_gnn_grads* g,
+                void* saved, void* workspace, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFT_GNN_H */

@@ -1,0 +1,147 @@
+// extern "C" surface of libmft_gnn.so (declared in include/mft_gnn.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "wcompute.cuh"
+
+namespace mft {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_code = 0;
+
+void set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    g_code = code;
+}
+int last_code() { return g_code; }
+
+size_t gnn_saved_bytes(int B, int N, int F0, int nf, int n_way);
+size_t gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way);
+int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
+            void* saved, void* workspace, int precision, cudaStream_t st);
+int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* dx,
+            const mft_gnn_grads* g, void* saved, void* workspace, int precision, cudaStream_t st);
+bool umma_shape_supported(int F, int nf);
+
+// The kernels are compiled for sm_100a only; refuse anything else up front instead of
+// failing with "no kernel image" somewhere in the middle of a call.
+static int require_sm100() {
+    static int cached[64] = {0};   // 0 unknown, 1 ok, 2 bad
+    int dev = 0;
+    MFT_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return MFT_OK;
+    if (cached[dev] == 0) {
+        int major = 0;
+        MFT_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        cached[dev] = (major == 10) ? 1 : 2;
+    }
+    if (cached[dev] != 1) {
+        set_error(MFT_ERR_DEVICE, "device %d is not an sm_100 (Blackwell B200) part; libmft_gnn has no other path", dev);
+        return MFT_ERR_DEVICE;
+    }
+    return MFT_OK;
+}
+
+}  // namespace mft
+
+using namespace mft;
+
+#define MFT_ENTER()                         \
+    do {                                    \
+        int _rc = require_sm100();          \
+        if (_rc != MFT_OK) return _rc;      \
+    } while (0)
+
+extern "C" {
+
+const char* mft_last_error(void) { return g_err; }
+int mft_version(void) { return 1; }
+
+int mft_device_check(int device) {
+    int major = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e != cudaSuccess) {
+        set_error(MFT_ERR_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+        return MFT_ERR_CUDA;
+    }
+    if (major != 10) {
+        set_error(MFT_ERR_DEVICE, "device %d has compute capability major %d, need 10 (sm_100)", device, major);
+        return MFT_ERR_DEVICE;
+    }
+    return MFT_OK;
+}
+
+int mft_tf32_supported(int F, int nf) { return umma_shape_supported(F, nf) ? 1 : 0; }
+
+size_t mft_wcompute_saved_bytes(int B, int N, int F, int nf) {
+    return wc_layout(B, N, F, nf, nullptr, nullptr).saved_bytes;
+}
+size_t mft_wcompute_workspace_bytes(int B, int N, int F, int nf) {
+    return wc_layout(B, N, F, nf, nullptr, nullptr).workspace_bytes;
+}
+
+int mft_wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
+                     float* adj, void* saved, void* workspace, int precision, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(x && p && adj && saved && workspace, "mft_wcompute_fwd: null pointer");
+    return wcompute_fwd(x, ldx, B, N, F, nf, p, adj, saved, workspace, precision, (cudaStream_t)stream);
+}
+
+int mft_wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
+                     const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* g, void* saved,
+                     void* workspace, int precision, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(x && p && adj && d_adj && dx && g && saved && workspace, "mft_wcompute_bwd: null pointer");
+    return wcompute_bwd(x, ldx, B, N, F, nf, p, adj, d_adj, dx, g, saved, workspace, precision,
+                        (cudaStream_t)stream);
+}
+
+size_t mft_gconv_saved_bytes(int B, int N, int F, int n_out) {
+    return gc_layout(B, N, F, n_out, nullptr, nullptr).saved_bytes;
+}
+size_t mft_gconv_workspace_bytes(int B, int N, int F, int n_out) {
+    return gc_layout(B, N, F, n_out, nullptr, nullptr).workspace_bytes;
+}
+
+int mft_gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out,
+                  const mft_gconv_params* p, int lrelu, float* out, int ldo, void* saved, void* workspace,
+                  void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(adj && x && p && out && saved && workspace, "mft_gconv_fwd: null pointer");
+    return gconv_fwd(adj, x, ldx, B, N, F, n_out, p, lrelu, out, ldo, saved, workspace, (cudaStream_t)stream);
+}
+
+int mft_gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out,
+                  const mft_gconv_params* p, int lrelu, const float* d_out, int ldo, float* dx, float* d_adj,
+                  const mft_gconv_grads* g, void* saved, void* workspace, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(adj && x && p && d_out && dx && d_adj && g && saved && workspace, "mft_gconv_bwd: null pointer");
+    return gconv_bwd(adj, x, ldx, B, N, F, n_out, p, lrelu, d_out, ldo, dx, d_adj, g, saved, workspace,
+                     (cudaStream_t)stream);
+}
+
+size_t mft_gnn_saved_bytes(int B, int N, int F0, int nf, int n_way) { return gnn_saved_bytes(B, N, F0, nf, n_way); }
+size_t mft_gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way) {
+    return gnn_workspace_bytes(B, N, F0, nf, n_way);
+}
+
+int mft_gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
+                void* saved, void* workspace, int precision, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(x && p && out && saved && workspace, "mft_gnn_fwd: null pointer");
+    return gnn_fwd(x, B, N, F0, nf, n_way, p, out, saved, workspace, precision, (cudaStream_t)stream);
+}
+
+int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* dx,
+                const mft_gnn_grads* g, void* saved, void* workspace, int precision, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(d_out && p && dx && g && saved && workspace, "mft_gnn_bwd: null pointer");
+    return gnn_bwd(d_out, B, N, F0, nf, n_way, p, dx, g, saved, workspace, precision, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// Shared definitions of libmft_gnn: error plumbing, the unordered-pair row
+// geometry, batch-statistic helpers.  See DESIGN.md for the data layout.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "mft_gnn.h"
+
+namespace mft {
+
+constexpr float kBnEps = 1e-5f;     // reference gnn.py:65 (torch BatchNorm default)
+constexpr float kSlope = 0.01f;     // F.leaky_relu default, gnn.py:86
+constexpr float kDiagMask = 1e8f;   // gnn.py:106
+constexpr int kMaxC = 256;          // widest channel count a BN'd layer may have (2*nf)
+
+void set_error(int code, const char* fmt, ...);
+int last_code();
+
+#define MFT_CHECK_CUDA(expr)                                                          \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            mft::set_error(MFT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                \
+            return MFT_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+#define MFT_CHECK_LAUNCH()  MFT_CHECK_CUDA(cudaGetLastError())
+
+#define MFT_REQUIRE(cond, ...)                                                        \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            mft::set_error(MFT_ERR_ARG, __VA_ARGS__);                                  \
+            return MFT_ERR_ARG;                                                        \
+        }                                                                              \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Pair-row geometry.  One graph has N nodes; the edge MLP runs on the Rg =
+// N(N+1)/2 unordered pairs (i<=j) of each of the B graphs, row-major in i:
+//   r_local = i*N - i*(i-1)/2 + (j-i),   r = b*Rg + r_local.
+// Off-diagonal rows stand for the two ordered pairs (i,j),(j,i) of the
+// reference's dense [B,N,N] tensor and carry multiplicity 2 into the batch
+// statistics; `pairs` = B*N*N is the reference's BatchNorm population.
+// ---------------------------------------------------------------------------
+struct PairGeom {
+    int B, N, Rg, R;
+    double inv_pairs;
+    const int* tri;   // [Rg] packed (j << 16) | i, filled by tri_table_kernel
+};
+
+inline PairGeom make_geom(int B, int N, const int* tri) {
+    PairGeom g;
+    g.B = B;
+    g.N = N;
+    g.Rg = N * (N + 1) / 2;
+    g.R = B * g.Rg;
+    g.inv_pairs = 1.0 / ((double)B * (double)N * (double)N);
+    g.tri = tri;
+    return g;
+}
+
+__host__ __device__ inline int tri_start(int i, int N) { return i * N - (i * (i - 1)) / 2; }
+
+__device__ __forceinline__ void decode_local(int rl, int N, int& i, int& j) {
+    float fn = (float)(2 * N + 1);
+    int ii = (int)((fn - sqrtf(fn * fn - 8.0f * (float)rl)) * 0.5f);
+    ii = max(0, min(ii, N - 1));
+    while (tri_start(ii, N) > rl) --ii;
+    while (ii + 1 < N && tri_start(ii + 1, N) <= rl) ++ii;
+    i = ii;
+    j = ii + (rl - tri_start(ii, N));
+}
+
+struct PairRow {
+    int b, i, j;
+    float w;   // multiplicity: 1 diagonal, 2 off-diagonal, 0 past the end
+};
+
+__device__ __forceinline__ PairRow decode_row(int r, const PairGeom& g) {
+    PairRow p;
+    if (r >= g.R) {
+        p.b = 0; p.i = 0; p.j = 0; p.w = 0.f;
+        return p;
+    }
+    p.b = r / g.Rg;
+    int packed = __ldg(g.tri + (r - p.b * g.Rg));
+    p.i = packed & 0xffff;
+    p.j = packed >> 16;
+    p.w = (p.i == p.j) ? 1.f : 2.f;
+    return p;
+}
+
+__device__ __forceinline__ float lrelu(float y) { return y > 0.f ? y : y * kSlope; }
+__device__ __forceinline__ float dlrelu(float y) { return y > 0.f ? 1.f : kSlope; }
+
+// Batch statistics of one BN layer: sums[0..C) = sum w*h, sums[C..2C) = sum w*h^2,
+// accumulated across CTAs with fp64 atomics.  Each consumer CTA turns them into
+// mean / rstd itself (C <= 256 values, cheaper than another launch).
+__device__ __forceinline__ void bn_mean_rstd(const double* sums, int C, int c, double inv_count,
+                                             float& mean, float& rstd) {
+    double m = sums[c] * inv_count;
+    double v = sums[C + c] * inv_count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(v + (double)kBnEps));
+}
+
+// Per-channel constants staged in shared memory by every kernel that applies a BN.
+struct BnSmem {
+    float* mean;
+    float* rstd;
+    float* gamma;
+    float* beta;
+};
+
+__device__ __forceinline__ BnSmem bn_smem_at(float* base) {
+    BnSmem s;
+    s.mean = base;
+    s.rstd = base + kMaxC;
+    s.gamma = base + 2 * kMaxC;
+    s.beta = base + 3 * kMaxC;
+    return s;
+}
+
+__device__ __forceinline__ void bn_smem_fill(BnSmem s, const double* sums, const float* gamma,
+                                             const float* beta, int C, double inv_count) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float m, r;
+        bn_mean_rstd(sums, C, c, inv_count, m, r);
+        s.mean[c] = m;
+        s.rstd[c] = r;
+        s.gamma[c] = gamma ? gamma[c] : 1.f;
+        s.beta[c] = beta ? beta[c] : 0.f;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Bump carving of the caller-provided blobs (saved / workspace).
+struct Carver {
+    char* base;
+    size_t off;
+    explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~size_t(255);
+        T* r = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+    size_t used() const { return (off + 255) & ~size_t(255); }
+};
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace mft

@@ -1,0 +1,300 @@
+// Gconv (J=2 aggregation + Linear + BatchNorm1d) forward and backward.
+// Replaces gmul + Gconv.forward of the reference (methods/gnn.py:16-28, 43-56).
+// The identity operator of gmul is never multiplied out, and A (x Wb^T) is
+// evaluated as written there instead of (A x) Wb^T: same result, the N x N
+// product runs on n_out (48 or n_way) columns instead of F (133..229).
+#include "common.cuh"
+#include "simt_gemm.cuh"
+#include "wcompute.cuh"
+
+namespace mft {
+
+namespace {
+
+struct PlainOp {
+    const float* p;
+    int ld;
+    struct Ctx { const float* row; };
+    __device__ __forceinline__ void init(float*) const {}
+    __device__ __forceinline__ Ctx row(int r) const { return Ctx{p + (size_t)r * ld}; }
+    __device__ __forceinline__ float at(const Ctx& c, int k, const float*) const { return c.row[k]; }
+    __device__ __forceinline__ float at(int r, int k, const float*) const { return p[(size_t)r * ld + k]; }
+};
+
+struct EpiStore {
+    static constexpr int kStats = 0;
+    float* out;
+    int ld;
+    __device__ __forceinline__ void init(float*) const {}
+    __device__ __forceinline__ void tile(int r0, int c0, int M, int N, float (&acc)[8][6], float (&)[6],
+                                         float (&)[6], const float*) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int r = r0 + i;
+            if (r >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                int c = c0 + 32 * (j >> 1) + (j & 1);
+                if (c < N) out[(size_t)r * ld + c] = acc[i][j];
+            }
+        }
+    }
+    __device__ __forceinline__ void commit(int, float, float) const {}
+};
+
+constexpr int kGcRows = 4;    // rows (nodes) per CTA in the per-node kernels
+constexpr int kGcCols = 64;   // threads along the output channel
+
+// Y[b,i,c] = V[b,i,c] + sum_j adj[b,i,j] U[b,j,c] + bias[c]; optional batch statistics.
+__global__ void __launch_bounds__(kGcRows * kGcCols)
+gconv_combine_kernel(const float* __restrict__ adj, const float* __restrict__ UV, const float* __restrict__ bias,
+                     int rows, int N, int n_out, float* __restrict__ Y, int ldy, double* sums) {
+    __shared__ float red[2][kGcRows][kMaxC];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.x * kGcRows + ty;
+    const bool live = row < rows;
+    const int b = live ? row / N : 0;
+    const float* arow = adj + (size_t)(live ? row : 0) * N;
+    const float* Ub = UV + (size_t)b * N * 2 * n_out + n_out;
+    for (int c = tx; c < n_out; c += kGcCols) {
+        float y = 0.f;
+        if (live) {
+            y = UV[(size_t)row * 2 * n_out + c] + bias[c];
+            for (int j = 0; j < N; ++j) y = fmaf(arow[j], Ub[(size_t)j * 2 * n_out + c], y);
+            Y[(size_t)row * ldy + c] = y;
+        }
+        red[0][ty][c] = y;
+        red[1][ty][c] = y * y;
+    }
+    if (sums == nullptr) return;
+    __syncthreads();
+    if (ty == 0) {
+        for (int c = tx; c < n_out; c += kGcCols) {
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < kGcRows; ++q) { v0 += red[0][q][c]; v1 += red[1][q][c]; }
+            atomicAdd(sums + c, (double)v0);
+            atomicAdd(sums + n_out + c, (double)v1);
+        }
+    }
+}
+
+// out = act(BN1d(Y))
+__global__ void gconv_apply_kernel(const float* __restrict__ Y, int rows, int n_out, const double* sums,
+                                   const float* gamma, const float* beta, int lrelu_on, float* __restrict__ out,
+                                   int ldo) {
+    __shared__ float aux[4 * kMaxC];
+    bn_smem_fill(bn_smem_at(aux), sums, gamma, beta, n_out, 1.0 / (double)rows);
+    __syncthreads();
+    BnSmem s = bn_smem_at(aux);
+    int total = rows * n_out;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int r = idx / n_out, c = idx - r * n_out;
+        float hh = (Y[idx] - s.mean[c]) * s.rstd[c];
+        float z = fmaf(hh, s.gamma[c], s.beta[c]);
+        out[(size_t)r * ldo + c] = lrelu_on ? lrelu(z) : z;
+    }
+}
+
+// dz = d_out * lrelu'(z) -> dY buffer, with column sums of dz and dz*hhat
+__global__ void __launch_bounds__(kGcRows * kGcCols)
+gconv_dz_kernel(const float* __restrict__ d_out, int ldo, const float* __restrict__ Y, int rows, int n_out,
+                const double* fsums, const float* gamma, const float* beta, int has_bn, int lrelu_on,
+                float* __restrict__ dY, double* bsums) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float red[2][kGcRows][kMaxC];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int t = ty * kGcCols + tx;
+    if (has_bn) {
+        for (int c = t; c < n_out; c += kGcRows * kGcCols) {
+            float m, r;
+            bn_mean_rstd(fsums, n_out, c, 1.0 / (double)rows, m, r);
+            aux[c] = m; aux[kMaxC + c] = r; aux[2 * kMaxC + c] = gamma[c]; aux[3 * kMaxC + c] = beta[c];
+        }
+    }
+    __syncthreads();
+    BnSmem s = bn_smem_at(aux);
+    const int row = blockIdx.x * kGcRows + ty;
+    const bool live = row < rows;
+    for (int c = tx; c < n_out; c += kGcCols) {
+        float d = 0.f, dh = 0.f;
+        if (live) {
+            d = d_out[(size_t)row * ldo + c];
+            if (has_bn) {
+                float hh = (Y[(size_t)row * n_out + c] - s.mean[c]) * s.rstd[c];
+                float z = fmaf(hh, s.gamma[c], s.beta[c]);
+                if (lrelu_on) d *= dlrelu(z);
+                dh = d * hh;
+            }
+            dY[(size_t)row * n_out + c] = d;
+        }
+        red[0][ty][c] = d;
+        red[1][ty][c] = dh;
+    }
+    __syncthreads();
+    if (ty == 0) {
+        for (int c = tx; c < n_out; c += kGcCols) {
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < kGcRows; ++q) { v0 += red[0][q][c]; v1 += red[1][q][c]; }
+            atomicAdd(bsums + c, (double)v0);
+            atomicAdd(bsums + n_out + c, (double)v1);
+        }
+    }
+}
+
+// BatchNorm1d backward in place on dY, plus the small parameter gradients.
+__global__ void gconv_dy_kernel(float* __restrict__ dY, const float* __restrict__ Y, int rows, int n_out,
+                                const double* fsums, const float* gamma, const double* bsums) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float m1[kMaxC], m2[kMaxC];
+    bn_smem_fill(bn_smem_at(aux), fsums, gamma, nullptr, n_out, 1.0 / (double)rows);
+    for (int c = threadIdx.x; c < n_out; c += blockDim.x) {
+        m1[c] = (float)(bsums[c] / (double)rows);
+        m2[c] = (float)(bsums[n_out + c] / (double)rows);
+    }
+    __syncthreads();
+    BnSmem s = bn_smem_at(aux);
+    int total = rows * n_out;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int c = idx % n_out;
+        float hh = (Y[idx] - s.mean[c]) * s.rstd[c];
+        dY[idx] = s.gamma[c] * s.rstd[c] * (dY[idx] - m1[c] - hh * m2[c]);
+    }
+}
+
+__global__ void gconv_small_grads_kernel(const double* bsums, int n_out, int has_bn, float* fc_b, float* bn_g,
+                                         float* bn_b) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_out) return;
+    if (has_bn) {
+        if (bn_b) bn_b[c] = (float)bsums[c];
+        if (bn_g) bn_g[c] = (float)bsums[n_out + c];
+        if (fc_b) fc_b[c] = 0.f;                   // BatchNorm1d removes the mean: exactly zero
+    } else if (fc_b) {
+        fc_b[c] = (float)bsums[c];
+    }
+}
+
+// dx[r, f] += DU[r, f]   (the identity operator of gmul)
+__global__ void add_cols_kernel(float* __restrict__ dx, int ldx, const float* __restrict__ src, int lds, int rows,
+                                int F) {
+    int total = rows * F;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int r = idx / F, f = idx - r * F;
+        dx[(size_t)r * ldx + f] += src[(size_t)r * lds + f];
+    }
+}
+
+}  // namespace
+
+GcLayout gc_layout(int B, int N, int F, int n_out, void* saved, void* workspace) {
+    GcLayout L;
+    size_t rows = (size_t)B * N;
+    Carver sv(saved);
+    L.Y = sv.take<float>(rows * n_out);
+    L.fsums = sv.take<double>(2 * kMaxC);
+    L.saved_bytes = sv.used();
+    Carver ws(workspace);
+    L.UV = ws.take<float>(rows * 2 * n_out);
+    L.dY = ws.take<float>(rows * n_out);
+    L.AX = ws.take<float>(rows * F);
+    L.DU = ws.take<float>(rows * 2 * F);
+    L.bsums = ws.take<double>(2 * kMaxC);
+    L.workspace_bytes = ws.used();
+    return L;
+}
+
+int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
+              int lrelu_on, float* out, int ldo, void* saved, void* workspace, cudaStream_t st) {
+    MFT_REQUIRE(B > 0 && N > 0 && F > 0 && n_out > 0, "gconv_fwd: bad shape");
+    MFT_REQUIRE(n_out <= kMaxC, "gconv_fwd: n_out=%d exceeds %d", n_out, kMaxC);
+    MFT_REQUIRE(ldx >= F && ldo >= n_out, "gconv_fwd: bad leading dimensions");
+    GcLayout L = gc_layout(B, N, F, n_out, saved, workspace);
+    const int rows = B * N;
+    const bool has_bn = p->bn_g != nullptr;
+    MFT_REQUIRE(has_bn || !lrelu_on, "gconv_fwd: LeakyReLU without BatchNorm is not a reference configuration");
+
+    // UV = x [Wa; Wb]^T : fc.weight [n_out, 2F] viewed as [2 n_out, F]
+    PlainOp a{x, ldx};
+    WView wv{p->fc_w, 2 * F, 1, n_out, F};
+    EpiStore epi{L.UV, 2 * n_out};
+    MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, rows, 2 * n_out, F, st)));
+
+    dim3 blk(kGcCols, kGcRows);
+    if (has_bn) {
+        MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 2 * kMaxC, st));
+        gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, L.Y, n_out,
+                                                                   L.fsums);
+        MFT_CHECK_LAUNCH();
+        int total = rows * n_out;
+        gconv_apply_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.Y, rows, n_out, L.fsums, p->bn_g,
+                                                                           p->bn_b, lrelu_on, out, ldo);
+        MFT_CHECK_LAUNCH();
+    } else {
+        gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, out, ldo,
+                                                                   nullptr);
+        MFT_CHECK_LAUNCH();
+    }
+    return MFT_OK;
+}
+
+int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
+              int lrelu_on, const float* d_out, int ldo, float* dx, float* d_adj, const mft_gconv_grads* g,
+              void* saved, void* workspace, cudaStream_t st) {
+    MFT_REQUIRE(B > 0 && N > 0 && F > 0 && n_out > 0, "gconv_bwd: bad shape");
+    MFT_REQUIRE(n_out <= kMaxC, "gconv_bwd: n_out=%d exceeds %d", n_out, kMaxC);
+    GcLayout L = gc_layout(B, N, F, n_out, saved, workspace);
+    const int rows = B * N;
+    const int has_bn = p->bn_g != nullptr;
+
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 2 * kMaxC, st));
+    MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)n_out * 2 * F, st));
+    dim3 blk(kGcCols, kGcRows);
+    gconv_dz_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(d_out, ldo, L.Y, rows, n_out, L.fsums, p->bn_g, p->bn_b,
+                                                          has_bn, lrelu_on, L.dY, L.bsums);
+    MFT_CHECK_LAUNCH();
+    if (has_bn) {
+        int total = rows * n_out;
+        gconv_dy_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.dY, L.Y, rows, n_out, L.fsums, p->bn_g,
+                                                                        L.bsums);
+        MFT_CHECK_LAUNCH();
+    }
+    gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, st>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
+    MFT_CHECK_LAUNCH();
+
+    // AX = adj x   [B*N, F]
+    BView A{adj, (long)N * N, N, 1};
+    BView X{x, (long)N * ldx, ldx, 1};
+    MFT_CHECK_CUDA(launch_bgemm(A, X, L.AX, (long)N * F, F, B, N, F, N, 0.f, st));
+
+    // d fc.weight [n_out, 2F] = [dY^T x | dY^T AX]
+    PlainOp dy{L.dY, n_out};
+    PlainOp qx{x, ldx};
+    PlainOp qax{L.AX, F};
+    MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, st)));
+    MFT_CHECK_CUDA((launch_gemm_tn(dy, qax, g->fc_w + F, 2 * F, n_out, F, rows, st)));
+
+    // DU = dY W  [B*N, 2F]: first half feeds the identity operator, second half the adjacency
+    EpiStore epi{L.DU, 2 * F};
+    MFT_CHECK_CUDA((launch_gemm_rows<false>(dy, wview_nn(p->fc_w, 2 * F), epi, rows, 2 * F, n_out, st)));
+
+    // dx += DU1 + adj^T DU2
+    {
+        int total = rows * F;
+        add_cols_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(dx, ldx, L.DU, 2 * F, rows, F);
+        MFT_CHECK_LAUNCH();
+        BView At{adj, (long)N * N, 1, N};                       // (m=j, k=i) -> adj[b, i, j]
+        BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (k=i, n=f)
+        MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st));
+    }
+    // d_adj[b,i,j] = sum_f DU2[b,i,f] x[b,j,f]
+    {
+        BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (m=i, k=f)
+        BView Xt{x, (long)N * ldx, 1, ldx};                     // (k=f, n=j) -> x[b, j, f]
+        MFT_CHECK_CUDA(launch_bgemm(D2, Xt, d_adj, (long)N * N, N, B, N, N, F, 0.f, st));
+    }
+    return MFT_OK;
+}
+
+}  // namespace mft

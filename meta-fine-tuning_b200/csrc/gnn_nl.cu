@@ -1,0 +1,111 @@
+// GNN_nl forward / backward in one library call each.
+// Replaces GNN_nl.forward (methods/gnn.py:154-166): two (Wcompute, Gconv, LeakyReLU,
+// concat) blocks and the final (Wcompute, Gconv).  The dense concatenation is a
+// column range of one wide node buffer `xcat` [B*N, LDX]; layer l reads columns
+// [0, F0 + l*nf/2) and writes its 48 new features right behind them, so no copy
+// is ever made.  The backward mirrors it with `dxcat`.
+#include "common.cuh"
+#include "wcompute.cuh"
+
+namespace mft {
+
+struct GnnLayout {
+    int L;                 // Wcompute/Gconv pairs (num_layers + 1)
+    int F[MFT_MAX_LAYERS]; // input width of pair l
+    int nout[MFT_MAX_LAYERS];
+    int ldx;
+    float* xcat;           // saved
+    float* adj[MFT_MAX_LAYERS];
+    void* wc_saved[MFT_MAX_LAYERS];
+    void* gc_saved[MFT_MAX_LAYERS];
+    float* dxcat;          // workspace
+    float* d_adj;
+    void* sub_ws;          // shared by every Wcompute / Gconv call (stream-ordered)
+    size_t saved_bytes, workspace_bytes;
+};
+
+static GnnLayout gnn_layout(int B, int N, int F0, int nf, int n_way, void* saved, void* workspace) {
+    GnnLayout G;
+    G.L = MFT_MAX_LAYERS;
+    const int half = nf / 2;
+    for (int l = 0; l < G.L; ++l) {
+        G.F[l] = F0 + half * l;
+        G.nout[l] = (l == G.L - 1) ? n_way : half;
+    }
+    int ftot = G.F[G.L - 1];
+    G.ldx = (ftot + 3) & ~3;
+    size_t rows = (size_t)B * N;
+    Carver sv(saved);
+    G.xcat = sv.take<float>(rows * G.ldx);
+    size_t sub_ws = 0;
+    for (int l = 0; l < G.L; ++l) {
+        G.adj[l] = sv.take<float>((size_t)B * N * N);
+        WcLayout w = wc_layout(B, N, G.F[l], nf, nullptr, nullptr);
+        GcLayout c = gc_layout(B, N, G.F[l], G.nout[l], nullptr, nullptr);
+        G.wc_saved[l] = sv.take<char>(w.saved_bytes);
+        G.gc_saved[l] = sv.take<char>(c.saved_bytes);
+        sub_ws = sub_ws > w.workspace_bytes ? sub_ws : w.workspace_bytes;
+        sub_ws = sub_ws > c.workspace_bytes ? sub_ws : c.workspace_bytes;
+    }
+    G.saved_bytes = sv.used();
+    Carver ws(workspace);
+    G.dxcat = ws.take<float>(rows * G.ldx);
+    G.d_adj = ws.take<float>((size_t)B * N * N);
+    G.sub_ws = ws.take<char>(sub_ws);
+    G.workspace_bytes = ws.used();
+    return G;
+}
+
+size_t gnn_saved_bytes(int B, int N, int F0, int nf, int n_way) {
+    return gnn_layout(B, N, F0, nf, n_way, nullptr, nullptr).saved_bytes;
+}
+size_t gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way) {
+    return gnn_layout(B, N, F0, nf, n_way, nullptr, nullptr).workspace_bytes;
+}
+
+int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
+            void* saved, void* workspace, int precision, cudaStream_t st) {
+    MFT_REQUIRE(B > 0 && N > 0 && F0 > 0 && nf >= 2 && (nf % 2) == 0 && n_way > 0, "gnn_fwd: bad shape");
+    GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace);
+    const int rows = B * N;
+    MFT_CHECK_CUDA(cudaMemcpy2DAsync(G.xcat, sizeof(float) * G.ldx, x, sizeof(float) * F0, sizeof(float) * F0,
+                                     rows, cudaMemcpyDeviceToDevice, st));
+    for (int l = 0; l < G.L; ++l) {
+        int rc = wcompute_fwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.wc_saved[l], G.sub_ws,
+                              precision, st);
+        if (rc != MFT_OK) return rc;
+        const bool last = (l == G.L - 1);
+        float* dst = last ? out : G.xcat + G.F[l];
+        int ldo = last ? n_way : G.ldx;
+        rc = gconv_fwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, dst, ldo,
+                       G.gc_saved[l], G.sub_ws, st);
+        if (rc != MFT_OK) return rc;
+    }
+    return MFT_OK;
+}
+
+int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* dx,
+            const mft_gnn_grads* g, void* saved, void* workspace, int precision, cudaStream_t st) {
+    MFT_REQUIRE(B > 0 && N > 0 && F0 > 0 && nf >= 2 && (nf % 2) == 0 && n_way > 0, "gnn_bwd: bad shape");
+    GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace);
+    const int rows = B * N;
+    MFT_CHECK_CUDA(cudaMemsetAsync(G.dxcat, 0, sizeof(float) * (size_t)rows * G.ldx, st));
+    for (int l = G.L - 1; l >= 0; --l) {
+        const bool last = (l == G.L - 1);
+        // upstream of this Gconv: d_out for the last one, else the columns it produced in xcat
+        // (every later layer has already accumulated its dx there)
+        const float* up = last ? d_out : G.dxcat + G.F[l];
+        int ldu = last ? n_way : G.ldx;
+        int rc = gconv_bwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, up, ldu,
+                           G.dxcat, G.d_adj, &g->l[l], G.gc_saved[l], G.sub_ws, st);
+        if (rc != MFT_OK) return rc;
+        rc = wcompute_bwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.d_adj, G.dxcat, &g->w[l],
+                          G.wc_saved[l], G.sub_ws, precision, st);
+        if (rc != MFT_OK) return rc;
+    }
+    MFT_CHECK_CUDA(cudaMemcpy2DAsync(dx, sizeof(float) * F0, G.dxcat, sizeof(float) * G.ldx, sizeof(float) * F0,
+                                     rows, cudaMemcpyDeviceToDevice, st));
+    return MFT_OK;
+}
+
+}  // namespace mft

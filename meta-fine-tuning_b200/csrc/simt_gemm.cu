@@ -1,0 +1,54 @@
+// Non-template parts of the CUDA-core GEMM toolkit (see simt_gemm.cuh).
+#include "simt_gemm.cuh"
+
+namespace mft {
+
+constexpr int BG_T = 32;
+
+__global__ void __launch_bounds__(256)
+bgemm_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int M, int N, int K, float beta) {
+    __shared__ float As[BG_T][BG_T + 1];   // [m][k]
+    __shared__ float Bs[BG_T][BG_T + 1];   // [k][n]
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.y * BG_T, n0 = blockIdx.x * BG_T;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const float* Ab = A.p + (size_t)b * A.sb;
+    const float* Bb = Bm.p + (size_t)b * Bm.sb;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < K; k0 += BG_T) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int r = ty + 8 * q;
+            int m = m0 + r, k = k0 + tx;
+            As[r][tx] = (m < M && k < K) ? Ab[(size_t)m * A.s0 + (size_t)k * A.s1] : 0.f;
+            int kk = k0 + r, n = n0 + tx;
+            Bs[r][tx] = (kk < K && n < N) ? Bb[(size_t)kk * Bm.s0 + (size_t)n * Bm.s1] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BG_T; ++k) {
+            float bv = Bs[k][tx];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fmaf(As[ty + 8 * q][k], bv, acc[q]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int m = m0 + ty + 8 * q, n = n0 + tx;
+        if (m < M && n < N) {
+            float* c = C + (size_t)b * scb + (size_t)m * ldc + n;
+            *c = (beta == 0.f) ? acc[q] : fmaf(beta, *c, acc[q]);
+        }
+    }
+}
+
+cudaError_t launch_bgemm(BView A, BView Bm, float* C, long scb, int ldc, int batch, int M, int N, int K,
+                         float beta, cudaStream_t st) {
+    if (batch <= 0 || M <= 0 || N <= 0) return cudaSuccess;
+    dim3 grid(cdiv(N, BG_T), cdiv(M, BG_T), batch);
+    bgemm_kernel<<<grid, 256, 0, st>>>(A, Bm, C, scb, ldc, M, N, K, beta);
+    return cudaGetLastError();
+}
+
+}  // namespace mft

@@ -1,0 +1,535 @@
+// Wcompute (edge MLP + adjacency softmax) forward and backward.
+// Replaces Wcompute.forward of the reference (methods/gnn.py:78-132) and the
+// autograd graph PyTorch builds behind it.  Algorithm: tests/kernel_model.py
+// (unordered pairs with multiplicities, BN-cancelled conv biases dropped,
+// closed-form backward -- SURVEY.md Appendix A).
+#include "common.cuh"
+#include "simt_gemm.cuh"
+#include "wcompute.cuh"
+
+namespace mft {
+
+// =========================== operand functors ================================
+
+// A(r, k) = |x[b,i,k] - x[b,j,k]|   (gnn.py:79-81)
+struct AbsDiffA {
+    const float* x;
+    int ldx;
+    PairGeom g;
+    struct Ctx { const float* xi; const float* xj; };
+    __device__ __forceinline__ void init(float*) const {}
+    __device__ __forceinline__ Ctx row(int r) const {
+        PairRow p = decode_row(r, g);
+        Ctx c;
+        c.xi = x + (size_t)(p.b * g.N + p.i) * ldx;
+        c.xj = x + (size_t)(p.b * g.N + p.j) * ldx;
+        return c;
+    }
+    __device__ __forceinline__ float at(const Ctx& c, int k, const float*) const {
+        return fabsf(__ldg(c.xi + k) - __ldg(c.xj + k));
+    }
+    // (row, col) form for the wgrad kernel
+    __device__ __forceinline__ float at(int r, int k, const float*) const {
+        PairRow p = decode_row(r, g);
+        const float* xi = x + (size_t)(p.b * g.N + p.i) * ldx;
+        const float* xj = x + (size_t)(p.b * g.N + p.j) * ldx;
+        return fabsf(__ldg(xi + k) - __ldg(xj + k));
+    }
+};
+
+// A(r, k) = LeakyReLU(BN(H[r,k]))  with batch statistics from `sums` (gnn.py:85-86)
+struct BnActA {
+    const float* H;
+    int C;
+    const double* sums;
+    const float* gamma;
+    const float* beta;
+    double inv_count;
+    struct Ctx { const float* row; };
+    __device__ __forceinline__ void init(float* aux) const {
+        bn_smem_fill(bn_smem_at(aux), sums, gamma, beta, C, inv_count);
+    }
+    __device__ __forceinline__ Ctx row(int r) const { return Ctx{H + (size_t)r * C}; }
+    __device__ __forceinline__ float at(const Ctx& c, int k, const float* aux) const {
+        BnSmem s = bn_smem_at(const_cast<float*>(aux));
+        float hh = (c.row[k] - s.mean[k]) * s.rstd[k];
+        return lrelu(fmaf(hh, s.gamma[k], s.beta[k]));
+    }
+    __device__ __forceinline__ float at(int r, int k, const float* aux) const {
+        return at(Ctx{H + (size_t)r * C}, k, aux);
+    }
+};
+
+struct PlainA {
+    const float* p;
+    int ld;
+    struct Ctx { const float* row; };
+    __device__ __forceinline__ void init(float*) const {}
+    __device__ __forceinline__ Ctx row(int r) const { return Ctx{p + (size_t)r * ld}; }
+    __device__ __forceinline__ float at(const Ctx& c, int k, const float*) const { return c.row[k]; }
+    __device__ __forceinline__ float at(int r, int k, const float*) const { return p[(size_t)r * ld + k]; }
+};
+
+// =========================== epilogue functors ===============================
+
+#define MFT_EPI_COL(j) (c0 + 32 * ((j) >> 1) + ((j) & 1))
+
+// store pre-BN H and accumulate the weighted batch statistics
+struct EpiFwdStats {
+    static constexpr int kStats = 1;
+    float* H;
+    int C;
+    double* sums;
+    PairGeom g;
+    __device__ __forceinline__ void init(float*) const {}
+    __device__ __forceinline__ void tile(int r0, int c0, int M, int N, float (&acc)[8][6], float (&s0)[6],
+                                         float (&s1)[6], const float*) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int r = r0 + i;
+            if (r >= M) continue;
+            float w = decode_row(r, g).w;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                int c = MFT_EPI_COL(j);
+                if (c < N) {
+                    float v = acc[i][j];
+                    H[(size_t)r * C + c] = v;
+                    s0[j] = fmaf(w, v, s0[j]);
+                    s1[j] = fmaf(w * v, v, s1[j]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void commit(int c, float v0, float v1) const {
+        atomicAdd(sums + c, (double)v0);
+        atomicAdd(sums + C + c, (double)v1);
+    }
+};
+
+// dgrad epilogue: acc = dL/d a_{k-1}; dy = acc * lrelu'(BN(H_{k-1})); store dy and the two
+// BN-backward reductions sum(dy), sum(dy * hhat)
+struct EpiDy {
+    static constexpr int kStats = 1;
+    const float* H;      // pre-BN activations of layer k-1
+    float* dy;
+    int C;
+    const double* fsums; // forward statistics of layer k-1
+    const float* gamma;
+    const float* beta;
+    double inv_count;
+    double* bsums;
+    __device__ __forceinline__ void init(float* aux) const {
+        bn_smem_fill(bn_smem_at(aux), fsums, gamma, beta, C, inv_count);
+    }
+    __device__ __forceinline__ void tile(int r0, int c0, int M, int N, float (&acc)[8][6], float (&s0)[6],
+                                         float (&s1)[6], const float* aux) const {
+        BnSmem s = bn_smem_at(const_cast<float*>(aux));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int r = r0 + i;
+            if (r >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                int c = MFT_EPI_COL(j);
+                if (c < N) {
+                    float hh = (H[(size_t)r * C + c] - s.mean[c]) * s.rstd[c];
+                    float y = fmaf(hh, s.gamma[c], s.beta[c]);
+                    float d = acc[i][j] * dlrelu(y);
+                    dy[(size_t)r * C + c] = d;
+                    s0[j] += d;
+                    s1[j] = fmaf(d, hh, s1[j]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void commit(int c, float v0, float v1) const {
+        atomicAdd(bsums + c, (double)v0);
+        atomicAdd(bsums + C + c, (double)v1);
+    }
+};
+
+// layer-1 dgrad epilogue: acc = dL/dD (summed over the ordered twins); scatter
+// dx_i += sign(x_i - x_j) * acc, dx_j -= the same (abs + broadcast sub, gnn.py:79-81)
+struct EpiDx {
+    static constexpr int kStats = 0;
+    const float* x;
+    float* dx;
+    int ldx;
+    PairGeom g;
+    __device__ __forceinline__ void init(float*) const {}
+    __device__ __forceinline__ void tile(int r0, int c0, int M, int N, float (&acc)[8][6], float (&)[6],
+                                         float (&)[6], const float*) const {
+        float run[6];
+        int run_node = -1;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) run[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int r = r0 + i;
+            if (r >= M) break;
+            PairRow p = decode_row(r, g);
+            int ni = p.b * g.N + p.i, nj = p.b * g.N + p.j;
+            if (ni != run_node) {
+                if (run_node >= 0) flush(run_node, c0, N, run);
+                run_node = ni;
+            }
+            if (ni == nj) continue;   // sign(0) = 0 on the diagonal
+            const float* xi = x + (size_t)ni * ldx;
+            const float* xj = x + (size_t)nj * ldx;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                int c = MFT_EPI_COL(j);
+                if (c < N) {
+                    float df = __ldg(xi + c) - __ldg(xj + c);
+                    float sg = (df > 0.f) ? 1.f : ((df < 0.f) ? -1.f : 0.f);
+                    float v = sg * acc[i][j];
+                    run[j] += v;
+                    if (v != 0.f) atomicAdd(dx + (size_t)nj * ldx + c, -v);
+                }
+            }
+        }
+        if (run_node >= 0) flush(run_node, c0, N, run);
+    }
+    __device__ __forceinline__ void flush(int node, int c0, int N, float (&run)[6]) const {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            int c = MFT_EPI_COL(j);
+            if (c < N && run[j] != 0.f) atomicAdd(dx + (size_t)node * ldx + c, run[j]);
+            run[j] = 0.f;
+        }
+    }
+    __device__ __forceinline__ void commit(int, float, float) const {}
+};
+
+// =========================== small kernels ===================================
+
+__global__ void tri_table_kernel(int* tri, int N, int Rg) {
+    int rl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rl >= Rg) return;
+    int i, j;
+    decode_local(rl, N, i, j);
+    tri[rl] = (j << 16) | i;
+}
+
+constexpr int kRowWarps = 8;   // warps per CTA in the warp-per-row kernels
+constexpr int kChPerLane = kMaxC / 32;
+
+// S[b,i,j] = S[b,j,i] = conv2d_last(LeakyReLU(BN4(H4[r])))   (gnn.py:99-103)
+__global__ void __launch_bounds__(kRowWarps * 32)
+score_kernel(const float* __restrict__ H4, int C, const double* sums, const float* gamma, const float* beta,
+             const float* last_w, const float* last_b, PairGeom g, float* __restrict__ S) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float wl[kMaxC];
+    bn_smem_fill(bn_smem_at(aux), sums, gamma, beta, C, g.inv_pairs);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) wl[c] = last_w[c];
+    __syncthreads();
+    BnSmem s = bn_smem_at(aux);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float bias = last_b[0];
+    for (int r = blockIdx.x * kRowWarps + warp; r < g.R; r += gridDim.x * kRowWarps) {
+        const float* row = H4 + (size_t)r * C;
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float hh = (row[c] - s.mean[c]) * s.rstd[c];
+            acc = fmaf(lrelu(fmaf(hh, s.gamma[c], s.beta[c])), wl[c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            PairRow p = decode_row(r, g);
+            float v = acc + bias;
+            size_t base = (size_t)p.b * g.N * g.N;
+            S[base + (size_t)p.i * g.N + p.j] = v;
+            S[base + (size_t)p.j * g.N + p.i] = v;
+        }
+    }
+}
+
+// adj[b,i,:] = softmax_j(S[b,i,j] - 1e8 [i==j])   (gnn.py:105-115), one warp per row
+__global__ void __launch_bounds__(kRowWarps * 32)
+softmax_rows_kernel(const float* __restrict__ S, float* __restrict__ adj, int rows, int N) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int row = blockIdx.x * kRowWarps + warp;
+    if (row >= rows) return;
+    int i = row % N;
+    const float* s = S + (size_t)row * N;
+    float* a = adj + (size_t)row * N;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) {
+        float v = s[j] - (j == i ? kDiagMask : 0.f);
+        mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+        float v = s[j] - (j == i ? kDiagMask : 0.f);
+        sum += expf(v - mx);
+    }
+    sum = warp_sum(sum);
+    float inv = 1.f / sum;
+    for (int j = lane; j < N; j += 32) {
+        float v = s[j] - (j == i ? kDiagMask : 0.f);
+        a[j] = expf(v - mx) * inv;
+    }
+}
+
+// dS[b,i,j] = A_ij (dA_ij - sum_k A_ik dA_ik), one warp per row
+__global__ void __launch_bounds__(kRowWarps * 32)
+softmax_bwd_kernel(const float* __restrict__ adj, const float* __restrict__ d_adj, float* __restrict__ dS,
+                   int rows, int N) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int row = blockIdx.x * kRowWarps + warp;
+    if (row >= rows) return;
+    const float* a = adj + (size_t)row * N;
+    const float* d = d_adj + (size_t)row * N;
+    float dot = 0.f;
+    for (int j = lane; j < N; j += 32) dot = fmaf(a[j], d[j], dot);
+    dot = warp_sum(dot);
+    for (int j = lane; j < N; j += 32) dS[(size_t)row * N + j] = a[j] * (d[j] - dot);
+}
+
+// Backward through conv2d_last and the layer-4 LeakyReLU:
+//   G_r = dS_ij + dS_ji, dy4 = G_r * w_last * lrelu'(y4); reductions sum dy4, sum dy4*hhat4,
+//   sum G_r * a4 (= d conv2d_last.weight).  One warp per row, lanes over channels.
+__global__ void __launch_bounds__(kRowWarps * 32)
+dy4_kernel(const float* __restrict__ dS, const float* __restrict__ H4, int C, const double* fsums,
+           const float* gamma, const float* beta, const float* last_w, PairGeom g, float* __restrict__ dy4,
+           double* bsums, double* lastsum) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float wl[kMaxC];
+    __shared__ float red[3][kRowWarps][kMaxC];
+    bn_smem_fill(bn_smem_at(aux), fsums, gamma, beta, C, g.inv_pairs);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) wl[c] = last_w[c];
+    __syncthreads();
+    BnSmem s = bn_smem_at(aux);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float p0[kChPerLane], p1[kChPerLane], p2[kChPerLane];
+#pragma unroll
+    for (int q = 0; q < kChPerLane; ++q) { p0[q] = 0.f; p1[q] = 0.f; p2[q] = 0.f; }
+    for (int r = blockIdx.x * kRowWarps + warp; r < g.R; r += gridDim.x * kRowWarps) {
+        PairRow p = decode_row(r, g);
+        size_t base = (size_t)p.b * g.N * g.N;
+        float G = dS[base + (size_t)p.i * g.N + p.j];
+        if (p.i != p.j) G += dS[base + (size_t)p.j * g.N + p.i];
+        const float* row = H4 + (size_t)r * C;
+#pragma unroll
+        for (int q = 0; q < kChPerLane; ++q) {
+            int c = lane + 32 * q;
+            if (c < C) {
+                float hh = (row[c] - s.mean[c]) * s.rstd[c];
+                float y = fmaf(hh, s.gamma[c], s.beta[c]);
+                float d = G * wl[c] * dlrelu(y);
+                dy4[(size_t)r * C + c] = d;
+                p0[q] += d;
+                p1[q] = fmaf(d, hh, p1[q]);
+                p2[q] = fmaf(G, lrelu(y), p2[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kChPerLane; ++q) {
+        red[0][warp][lane + 32 * q] = p0[q];
+        red[1][warp][lane + 32 * q] = p1[q];
+        red[2][warp][lane + 32 * q] = p2[q];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRowWarps; ++w) { v0 += red[0][w][c]; v1 += red[1][w][c]; v2 += red[2][w][c]; }
+        atomicAdd(bsums + c, (double)v0);
+        atomicAdd(bsums + C + c, (double)v1);
+        atomicAdd(lastsum + c, (double)v2);
+    }
+}
+
+// BatchNorm backward applied in place: dH = gamma*rstd*(dy - w*m1 - w*hhat*m2), the twin-summed
+// form of the dense formula (w = row multiplicity; m1, m2 = means over all B*N*N ordered pairs).
+__global__ void __launch_bounds__(kRowWarps * 32)
+dh_kernel(float* __restrict__ dy, const float* __restrict__ H, int C, const double* fsums, const float* gamma,
+          const double* bsums, PairGeom g) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float m1[kMaxC], m2[kMaxC];
+    bn_smem_fill(bn_smem_at(aux), fsums, gamma, nullptr, C, g.inv_pairs);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        m1[c] = (float)(bsums[c] * g.inv_pairs);
+        m2[c] = (float)(bsums[C + c] * g.inv_pairs);
+    }
+    __syncthreads();
+    BnSmem s = bn_smem_at(aux);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = blockIdx.x * kRowWarps + warp; r < g.R; r += gridDim.x * kRowWarps) {
+        float w = decode_row(r, g).w;
+        const float* hrow = H + (size_t)r * C;
+        float* drow = dy + (size_t)r * C;
+        for (int c = lane; c < C; c += 32) {
+            float hh = (hrow[c] - s.mean[c]) * s.rstd[c];
+            drow[c] = s.gamma[c] * s.rstd[c] * (drow[c] - w * m1[c] - w * hh * m2[c]);
+        }
+    }
+}
+
+struct FinalizeArgs {
+    const double* bsums[4];
+    const double* lastsum;
+    float* bn_g[4];
+    float* bn_b[4];
+    float* conv_b[4];
+    float* last_w;
+    float* last_b;
+    int C[4];
+    int nf;
+};
+
+__global__ void finalize_grads_kernel(FinalizeArgs a) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = 0; k < 4; ++k) {
+        if (t < a.C[k]) {
+            if (a.bn_b[k]) a.bn_b[k][t] = (float)a.bsums[k][t];
+            if (a.bn_g[k]) a.bn_g[k][t] = (float)a.bsums[k][a.C[k] + t];
+            if (a.conv_b[k]) a.conv_b[k][t] = 0.f;   // BN removes the mean: exactly zero
+        }
+    }
+    if (t < a.nf && a.last_w) a.last_w[t] = (float)a.lastsum[t];
+    if (t == 0 && a.last_b) a.last_b[0] = 0.f;         // softmax shift invariance: exactly zero
+}
+
+// =========================== host orchestration ==============================
+
+static inline int row_grid(int R) { return min(cdiv(R, kRowWarps), 148 * 8); }
+
+WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
+    WcLayout L;
+    L.C[0] = F; L.C[1] = 2 * nf; L.C[2] = 2 * nf; L.C[3] = nf; L.C[4] = nf;
+    int Rg = N * (N + 1) / 2;
+    size_t R = (size_t)B * Rg;
+    Carver sv(saved);
+    for (int k = 0; k < 4; ++k) L.H[k] = sv.take<float>(R * L.C[k + 1]);
+    L.fsums = sv.take<double>(4 * 2 * kMaxC);
+    L.saved_bytes = sv.used();
+    Carver ws(workspace);
+    L.tri = ws.take<int>(Rg);
+    L.S = ws.take<float>((size_t)B * N * N);
+    L.dyA = ws.take<float>(R * 2 * nf);
+    L.dyB = ws.take<float>(R * 2 * nf);
+    L.bsums = ws.take<double>(5 * 2 * kMaxC);
+    L.workspace_bytes = ws.used();
+    return L;
+}
+
+int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p, float* adj,
+                 void* saved, void* workspace, int precision, cudaStream_t st) {
+    MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_fwd: bad shape B=%d N=%d F=%d nf=%d", B, N, F, nf);
+    MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_fwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
+    MFT_REQUIRE(N < 32768, "wcompute_fwd: N=%d too large", N);
+    MFT_REQUIRE(ldx >= F, "wcompute_fwd: ldx=%d < F=%d", ldx, F);
+    WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
+    PairGeom g = make_geom(B, N, L.tri);
+
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 4 * 2 * kMaxC, st));
+    tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
+    MFT_CHECK_LAUNCH();
+
+    if (precision == MFT_PREC_TF32) {
+        int rc = wcompute_fwd_layers_tf32(x, ldx, F, nf, p, L, g, st);
+        if (rc != MFT_OK) return rc;
+    } else {
+        for (int k = 0; k < 4; ++k) {
+            double* sums = L.fsums + (size_t)k * 2 * kMaxC;
+            EpiFwdStats epi{L.H[k], L.C[k + 1], sums, g};
+            WView wv = wview_nt(p->conv_w[k], L.C[k]);
+            if (k == 0) {
+                AbsDiffA a{x, ldx, g};
+                MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, g.R, L.C[1], F, st)));
+            } else {
+                const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+                BnActA a{L.H[k - 1], L.C[k], ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
+                MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, g.R, L.C[k + 1], L.C[k], st)));
+            }
+        }
+    }
+    score_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * 2 * kMaxC, p->bn_g[3],
+                                                            p->bn_b[3], p->last_w, p->last_b, g, L.S);
+    MFT_CHECK_LAUNCH();
+    softmax_rows_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(L.S, adj, B * N, N);
+    MFT_CHECK_LAUNCH();
+    return MFT_OK;
+}
+
+int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
+                 const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* gr, void* saved,
+                 void* workspace, int precision, cudaStream_t st) {
+    MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_bwd: bad shape");
+    MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_bwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
+    WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
+    PairGeom g = make_geom(B, N, L.tri);
+
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * 2 * kMaxC, st));
+    for (int k = 0; k < 4; ++k)
+        MFT_CHECK_CUDA(cudaMemsetAsync(gr->conv_w[k], 0, sizeof(float) * (size_t)L.C[k + 1] * L.C[k], st));
+    tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
+    MFT_CHECK_LAUNCH();
+
+    softmax_bwd_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(adj, d_adj, L.S, B * N, N);
+    MFT_CHECK_LAUNCH();
+    double* lastsum = L.bsums + 4 * 2 * kMaxC;
+    dy4_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * 2 * kMaxC, p->bn_g[3],
+                                                          p->bn_b[3], p->last_w, g, L.dyA, L.bsums + 3 * 2 * kMaxC,
+                                                          lastsum);
+    MFT_CHECK_LAUNCH();
+
+    float* cur = L.dyA;
+    float* nxt = L.dyB;
+    for (int k = 3; k >= 0; --k) {   // layer k+1 of the reference (conv2d_{k+1}, bn_{k+1})
+        const int Cout = L.C[k + 1], Cin = L.C[k];
+        const double* fs = L.fsums + (size_t)k * 2 * kMaxC;
+        const double* bs = L.bsums + (size_t)k * 2 * kMaxC;
+        dh_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(cur, L.H[k], Cout, fs, p->bn_g[k], bs, g);
+        MFT_CHECK_LAUNCH();
+        if (precision == MFT_PREC_TF32) {
+            int rc = wcompute_bwd_layer_tf32(k, cur, nxt, x, ldx, dx, F, nf, p, gr, L, g, st);
+            if (rc != MFT_OK) return rc;
+        } else {
+            PlainA dh{cur, Cout};
+            // wgrad: d conv2d_{k+1}.weight [Cout, Cin] = dH^T a_k
+            if (k == 0) {
+                AbsDiffA q{x, ldx, g};
+                MFT_CHECK_CUDA((launch_gemm_tn(dh, q, gr->conv_w[0], Cin, Cout, Cin, g.R, st)));
+            } else {
+                const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+                BnActA q{L.H[k - 1], Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
+                MFT_CHECK_CUDA((launch_gemm_tn(dh, q, gr->conv_w[k], Cin, Cout, Cin, g.R, st)));
+            }
+            // dgrad: dL/d a_k = dH W
+            WView wv = wview_nn(p->conv_w[k], Cin);
+            if (k == 0) {
+                EpiDx epi{x, dx, ldx, g};
+                MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
+            } else {
+                const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+                double* pbs = L.bsums + (size_t)(k - 1) * 2 * kMaxC;
+                EpiDy epi{L.H[k - 1], nxt, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
+                MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
+            }
+        }
+        float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+
+    FinalizeArgs fa;
+    for (int k = 0; k < 4; ++k) {
+        fa.bsums[k] = L.bsums + (size_t)k * 2 * kMaxC;
+        fa.bn_g[k] = gr->bn_g[k];
+        fa.bn_b[k] = gr->bn_b[k];
+        fa.conv_b[k] = gr->conv_b[k];
+        fa.C[k] = L.C[k + 1];
+    }
+    fa.lastsum = lastsum;
+    fa.last_w = gr->last_w;
+    fa.last_b = gr->last_b;
+    fa.nf = nf;
+    finalize_grads_kernel<<<1, kMaxC, 0, st>>>(fa);
+    MFT_CHECK_LAUNCH();
+    return MFT_OK;
+}
+
+}  // namespace mft

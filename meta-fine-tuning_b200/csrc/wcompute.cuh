@@ -1,0 +1,56 @@
+// Internal interfaces between the translation units of libmft_gnn.
+#pragma once
+
+#include "common.cuh"
+
+namespace mft {
+
+// Carved views of the Wcompute `saved` / `workspace` blobs.
+struct WcLayout {
+    int C[5];            // channel widths: F, 2nf, 2nf, nf, nf
+    float* H[4];         // saved: pre-BN activations of the four conv layers, [R, C[k+1]]
+    double* fsums;       // saved: forward batch statistics, 4 x [2*kMaxC]
+    int* tri;            // workspace: unordered-pair table [Rg]
+    float* S;            // workspace: scores / dS, [B,N,N]
+    float* dyA;          // workspace: ping-pong gradient buffers [R, 2nf]
+    float* dyB;
+    double* bsums;       // workspace: backward reductions, 5 x [2*kMaxC] (last = d conv2d_last.weight)
+    size_t saved_bytes, workspace_bytes;
+};
+
+WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace);
+
+int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p, float* adj,
+                 void* saved, void* workspace, int precision, cudaStream_t st);
+int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
+                 const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* gr, void* saved,
+                 void* workspace, int precision, cudaStream_t st);
+
+// tcgen05 (MFT_PREC_TF32) replacements for the four forward layer GEMMs and for the
+// dgrad + wgrad pair of one backward layer; same buffers in and out as the fp32 path.
+int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_wcompute_params* p,
+                             const WcLayout& L, const PairGeom& g, cudaStream_t st);
+int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, int ldx, float* dx, int F, int nf,
+                            const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
+                            const PairGeom& g, cudaStream_t st);
+
+struct GcLayout {
+    float* Y;            // saved: pre-BN Gconv output [B*N, n_out]
+    double* fsums;       // saved: BN1d statistics [2*kMaxC]
+    float* UV;           // workspace fwd: x [Wa;Wb]^T  [B*N, 2 n_out]
+    float* dY;           // workspace bwd: [B*N, n_out]
+    float* AX;           // workspace bwd: adj x  [B*N, F]
+    float* DU;           // workspace bwd: dY W   [B*N, 2F]
+    double* bsums;       // workspace bwd: [2*kMaxC] + fc bias sums [kMaxC]
+    size_t saved_bytes, workspace_bytes;
+};
+
+GcLayout gc_layout(int B, int N, int F, int n_out, void* saved, void* workspace);
+
+int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
+              int lrelu, float* out, int ldo, void* saved, void* workspace, cudaStream_t st);
+int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
+              int lrelu, const float* d_out, int ldo, float* dx, float* d_adj, const mft_gconv_grads* g,
+              void* saved, void* workspace, cudaStream_t st);
+
+}  // namespace mft

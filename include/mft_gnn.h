@@ -157,6 +157,18 @@ int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way,
                 const mft_gnn_params* p, float* dx, const mft_gnn_grads* g,
                 void* saved, void* workspace, int precision, void* stream);
 
+/* ---- measurement hooks (new; the reference has no profiler) ---- */
+
+/* Kernels launched by this library in this process so far (bench.py: gpu_launches). */
+unsigned long long mft_launch_count(void);
+/* Bracket every kernel launch with CUDA events on its stream (on != 0) or stop (0). */
+int mft_prof_enable(int on);
+int mft_prof_categories(void);
+const char* mft_prof_name(int cat);
+/* Synchronise, then ms[c] / counts[c] = summed device time and launches of category c
+ * since the last collect/enable; n = capacity of both arrays. */
+int mft_prof_collect(float* ms, int* counts, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,11 @@ SIGNATURES = {
     "mft_gnn_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, _vp, _vp, _i, _vp]),
     "mft_gnn_bwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, C.POINTER(GnnGrads), _vp, _vp,
                          _i, _vp]),
+    "mft_launch_count": (C.c_ulonglong, []),
+    "mft_prof_enable": (_i, [_i]),
+    "mft_prof_categories": (_i, []),
+    "mft_prof_name": (C.c_char_p, [_i]),
+    "mft_prof_collect": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int), _i]),
 }
 
 _lock = threading.Lock()
@@ -107,3 +112,13 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load_library().mft_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def profile_collect():
+    """{category: (total_ms, launches)} of the scopes recorded since mft_prof_enable(1)."""
+    lib = load_library()
+    n = lib.mft_prof_categories()
+    ms = (C.c_float * n)()
+    cnt = (C.c_int * n)()
+    check(lib.mft_prof_collect(ms, cnt, n), "mft_prof_collect")
+    return {lib.mft_prof_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}

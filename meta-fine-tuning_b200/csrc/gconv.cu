@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "simt_gemm.cuh"
 #include "wcompute.cuh"
+#include "prof.cuh"
 
 namespace mft {
 
@@ -219,22 +220,22 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     PlainOp a{x, ldx};
     WView wv{p->fc_w, 2 * F, 1, n_out, F};
     EpiStore epi{L.UV, 2 * n_out};
-    MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, rows, 2 * n_out, F, st)));
+    { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, rows, 2 * n_out, F, st))); }
 
     dim3 blk(kGcCols, kGcRows);
     if (has_bn) {
         MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 2 * kMaxC, st));
-        gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, L.Y, n_out,
+        { ProfScope ps(PC_GCONV_FWD, st); gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, L.Y, n_out,
                                                                    L.fsums);
-        MFT_CHECK_LAUNCH();
+        MFT_CHECK_LAUNCH(); }
         int total = rows * n_out;
-        gconv_apply_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.Y, rows, n_out, L.fsums, p->bn_g,
+        { ProfScope ps(PC_GCONV_FWD, st); gconv_apply_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.Y, rows, n_out, L.fsums, p->bn_g,
                                                                            p->bn_b, lrelu_on, out, ldo);
-        MFT_CHECK_LAUNCH();
+        MFT_CHECK_LAUNCH(); }
     } else {
-        gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, out, ldo,
+        { ProfScope ps(PC_GCONV_FWD, st); gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, out, ldo,
                                                                    nullptr);
-        MFT_CHECK_LAUNCH();
+        MFT_CHECK_LAUNCH(); }
     }
     return MFT_OK;
 }
@@ -251,48 +252,48 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 2 * kMaxC, st));
     MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)n_out * 2 * F, st));
     dim3 blk(kGcCols, kGcRows);
-    gconv_dz_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(d_out, ldo, L.Y, rows, n_out, L.fsums, p->bn_g, p->bn_b,
+    { ProfScope ps(PC_GCONV_BWD, st); gconv_dz_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(d_out, ldo, L.Y, rows, n_out, L.fsums, p->bn_g, p->bn_b,
                                                           has_bn, lrelu_on, L.dY, L.bsums);
-    MFT_CHECK_LAUNCH();
+    MFT_CHECK_LAUNCH(); }
     if (has_bn) {
         int total = rows * n_out;
-        gconv_dy_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.dY, L.Y, rows, n_out, L.fsums, p->bn_g,
+        { ProfScope ps(PC_GCONV_BWD, st); gconv_dy_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.dY, L.Y, rows, n_out, L.fsums, p->bn_g,
                                                                         L.bsums);
-        MFT_CHECK_LAUNCH();
+        MFT_CHECK_LAUNCH(); }
     }
-    gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, st>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
-    MFT_CHECK_LAUNCH();
+    { ProfScope ps(PC_GCONV_BWD, st); gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, st>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
+    MFT_CHECK_LAUNCH(); }
 
     // AX = adj x   [B*N, F]
     BView A{adj, (long)N * N, N, 1};
     BView X{x, (long)N * ldx, ldx, 1};
-    MFT_CHECK_CUDA(launch_bgemm(A, X, L.AX, (long)N * F, F, B, N, F, N, 0.f, st));
+    { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(A, X, L.AX, (long)N * F, F, B, N, F, N, 0.f, st)); }
 
     // d fc.weight [n_out, 2F] = [dY^T x | dY^T AX]
     PlainOp dy{L.dY, n_out};
     PlainOp qx{x, ldx};
     PlainOp qax{L.AX, F};
-    MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, st)));
-    MFT_CHECK_CUDA((launch_gemm_tn(dy, qax, g->fc_w + F, 2 * F, n_out, F, rows, st)));
+    { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, st))); }
+    { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA((launch_gemm_tn(dy, qax, g->fc_w + F, 2 * F, n_out, F, rows, st))); }
 
     // DU = dY W  [B*N, 2F]: first half feeds the identity operator, second half the adjacency
     EpiStore epi{L.DU, 2 * F};
-    MFT_CHECK_CUDA((launch_gemm_rows<false>(dy, wview_nn(p->fc_w, 2 * F), epi, rows, 2 * F, n_out, st)));
+    { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA((launch_gemm_rows<false>(dy, wview_nn(p->fc_w, 2 * F), epi, rows, 2 * F, n_out, st))); }
 
     // dx += DU1 + adj^T DU2
     {
         int total = rows * F;
-        add_cols_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(dx, ldx, L.DU, 2 * F, rows, F);
-        MFT_CHECK_LAUNCH();
+        { ProfScope ps(PC_GCONV_BWD, st); add_cols_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(dx, ldx, L.DU, 2 * F, rows, F);
+        MFT_CHECK_LAUNCH(); }
         BView At{adj, (long)N * N, 1, N};                       // (m=j, k=i) -> adj[b, i, j]
         BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (k=i, n=f)
-        MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st));
+        { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st)); }
     }
     // d_adj[b,i,j] = sum_f DU2[b,i,f] x[b,j,f]
     {
         BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (m=i, k=f)
         BView Xt{x, (long)N * ldx, 1, ldx};                     // (k=f, n=j) -> x[b, j, f]
-        MFT_CHECK_CUDA(launch_bgemm(D2, Xt, d_adj, (long)N * N, N, B, N, N, F, 0.f, st));
+        { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(D2, Xt, d_adj, (long)N * N, N, B, N, N, F, 0.f, st)); }
     }
     return MFT_OK;
 }

@@ -1,0 +1,87 @@
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "prof.cuh"
+
+namespace mft {
+
+static const char* kNames[PC_COUNT] = {
+    "misc",
+    "fwd_gemm_l1", "fwd_gemm_l2", "fwd_gemm_l3", "fwd_gemm_l4",
+    "score", "softmax",
+    "softmax_bwd", "dy4",
+    "bn_bwd_dh",
+    "wgrad_l1", "wgrad_l2", "wgrad_l3", "wgrad_l4",
+    "dgrad_l1", "dgrad_l2", "dgrad_l3", "dgrad_l4",
+    "finalize_grads",
+    "gconv_fwd", "gconv_bwd",
+    "prep",
+};
+
+const char* prof_name(int cat) { return (cat >= 0 && cat < PC_COUNT) ? kNames[cat] : "?"; }
+
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<bool> g_enabled{false};
+static std::mutex g_mu;
+struct Slot { cudaEvent_t a, b; int cat; };
+static std::vector<Slot> g_slots;
+static size_t g_used = 0;
+constexpr size_t kMaxSlots = 16384;
+
+ProfScope::ProfScope(int cat, cudaStream_t stream) : slot(-1), st(stream) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_enabled.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_used >= kMaxSlots) return;
+    if (g_used >= g_slots.size()) {
+        Slot s;
+        if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+        g_slots.push_back(s);
+    }
+    slot = (int)g_used++;
+    g_slots[slot].cat = cat;
+    cudaEventRecord(g_slots[slot].a, st);
+}
+
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaEventRecord(g_slots[slot].b, st);
+}
+
+}  // namespace mft
+
+using namespace mft;
+
+extern "C" {
+
+unsigned long long mft_launch_count(void) { return g_launches.load(); }
+
+int mft_prof_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_enabled.store(on != 0);
+    g_used = 0;
+    return MFT_OK;
+}
+
+int mft_prof_categories(void) { return PC_COUNT; }
+const char* mft_prof_name(int cat) { return prof_name(cat); }
+
+// Synchronises the device, then sums the elapsed time of every recorded scope per category.
+int mft_prof_collect(float* ms, int* counts, int n) {
+    MFT_CHECK_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int i = 0; i < n; ++i) { ms[i] = 0.f; counts[i] = 0; }
+    for (size_t i = 0; i < g_used; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, g_slots[i].a, g_slots[i].b) != cudaSuccess) continue;
+        int c = g_slots[i].cat;
+        if (c >= 0 && c < n) { ms[c] += t; counts[c] += 1; }
+    }
+    g_used = 0;
+    return MFT_OK;
+}
+
+}  // extern "C"

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "simt_gemm.cuh"
 #include "wcompute.cuh"
+#include "prof.cuh"
 
 namespace mft {
 
@@ -427,8 +428,11 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     PairGeom g = make_geom(B, N, L.tri);
 
     MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 4 * 2 * kMaxC, st));
-    tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
-    MFT_CHECK_LAUNCH();
+    {
+        ProfScope ps(PC_PREP, st);
+        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
+        MFT_CHECK_LAUNCH();
+    }
 
     if (precision == MFT_PREC_TF32) {
         int rc = wcompute_fwd_layers_tf32(x, ldx, F, nf, p, L, g, st);
@@ -438,6 +442,7 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             double* sums = L.fsums + (size_t)k * 2 * kMaxC;
             EpiFwdStats epi{L.H[k], L.C[k + 1], sums, g};
             WView wv = wview_nt(p->conv_w[k], L.C[k]);
+            ProfScope ps(PC_FWD_L1 + k, st);
             if (k == 0) {
                 AbsDiffA a{x, ldx, g};
                 MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, g.R, L.C[1], F, st)));
@@ -448,11 +453,17 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             }
         }
     }
-    score_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * 2 * kMaxC, p->bn_g[3],
-                                                            p->bn_b[3], p->last_w, p->last_b, g, L.S);
-    MFT_CHECK_LAUNCH();
-    softmax_rows_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(L.S, adj, B * N, N);
-    MFT_CHECK_LAUNCH();
+    {
+        ProfScope ps(PC_SCORE, st);
+        score_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * 2 * kMaxC, p->bn_g[3],
+                                                                p->bn_b[3], p->last_w, p->last_b, g, L.S);
+        MFT_CHECK_LAUNCH();
+    }
+    {
+        ProfScope ps(PC_SOFTMAX, st);
+        softmax_rows_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(L.S, adj, B * N, N);
+        MFT_CHECK_LAUNCH();
+    }
     return MFT_OK;
 }
 
@@ -467,16 +478,24 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * 2 * kMaxC, st));
     for (int k = 0; k < 4; ++k)
         MFT_CHECK_CUDA(cudaMemsetAsync(gr->conv_w[k], 0, sizeof(float) * (size_t)L.C[k + 1] * L.C[k], st));
-    tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
-    MFT_CHECK_LAUNCH();
-
-    softmax_bwd_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(adj, d_adj, L.S, B * N, N);
-    MFT_CHECK_LAUNCH();
+    {
+        ProfScope ps(PC_PREP, st);
+        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
+        MFT_CHECK_LAUNCH();
+    }
+    {
+        ProfScope ps(PC_SOFTMAX_BWD, st);
+        softmax_bwd_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(adj, d_adj, L.S, B * N, N);
+        MFT_CHECK_LAUNCH();
+    }
     double* lastsum = L.bsums + 4 * 2 * kMaxC;
-    dy4_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * 2 * kMaxC, p->bn_g[3],
-                                                          p->bn_b[3], p->last_w, g, L.dyA, L.bsums + 3 * 2 * kMaxC,
-                                                          lastsum);
-    MFT_CHECK_LAUNCH();
+    {
+        ProfScope ps(PC_DY4, st);
+        dy4_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * 2 * kMaxC, p->bn_g[3],
+                                                              p->bn_b[3], p->last_w, g, L.dyA,
+                                                              L.bsums + 3 * 2 * kMaxC, lastsum);
+        MFT_CHECK_LAUNCH();
+    }
 
     float* cur = L.dyA;
     float* nxt = L.dyB;
@@ -484,8 +503,11 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         const int Cout = L.C[k + 1], Cin = L.C[k];
         const double* fs = L.fsums + (size_t)k * 2 * kMaxC;
         const double* bs = L.bsums + (size_t)k * 2 * kMaxC;
-        dh_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(cur, L.H[k], Cout, fs, p->bn_g[k], bs, g);
-        MFT_CHECK_LAUNCH();
+        {
+            ProfScope ps(PC_DH, st);
+            dh_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(cur, L.H[k], Cout, fs, p->bn_g[k], bs, g);
+            MFT_CHECK_LAUNCH();
+        }
         if (precision == MFT_PREC_TF32) {
             int rc = wcompute_bwd_layer_tf32(k, cur, nxt, x, ldx, dx, F, nf, p, gr, L, g, st);
             if (rc != MFT_OK) return rc;
@@ -493,15 +515,18 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             PlainA dh{cur, Cout};
             // wgrad: d conv2d_{k+1}.weight [Cout, Cin] = dH^T a_k
             if (k == 0) {
+                ProfScope ps(PC_WGRAD_L1, st);
                 AbsDiffA q{x, ldx, g};
                 MFT_CHECK_CUDA((launch_gemm_tn(dh, q, gr->conv_w[0], Cin, Cout, Cin, g.R, st)));
             } else {
                 const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
                 BnActA q{L.H[k - 1], Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
+                ProfScope psc(PC_WGRAD_L1 + k, st);
                 MFT_CHECK_CUDA((launch_gemm_tn(dh, q, gr->conv_w[k], Cin, Cout, Cin, g.R, st)));
             }
             // dgrad: dL/d a_k = dH W
             WView wv = wview_nn(p->conv_w[k], Cin);
+            ProfScope psd(PC_DGRAD_L1 + k, st);
             if (k == 0) {
                 EpiDx epi{x, dx, ldx, g};
                 MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
@@ -527,8 +552,11 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     fa.last_w = gr->last_w;
     fa.last_b = gr->last_b;
     fa.nf = nf;
-    finalize_grads_kernel<<<1, kMaxC, 0, st>>>(fa);
-    MFT_CHECK_LAUNCH();
+    {
+        ProfScope ps(PC_FINALIZE, st);
+        finalize_grads_kernel<<<1, kMaxC, 0, st>>>(fa);
+        MFT_CHECK_LAUNCH();
+    }
     return MFT_OK;
 }
 

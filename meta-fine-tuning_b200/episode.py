@@ -1,0 +1,96 @@
+"""Host-side mirror of the GnnNet glue around ``GNN_nl`` (reference methods/gnnnet.py,
+methods/gnnnet_copy.py): label indexing, graph assembly, score selection, and a
+backbone-less head module with the reference's parameter names (``fc.*``, ``gnn.*``)
+so a reference checkpoint's head loads unchanged.
+
+Pure tensor bookkeeping on whatever device the inputs live on; the arithmetic of the
+head is in ``GNN_nl`` (CUDA kernels).  The reference's own ``GnnNet`` / ``DampNet``
+classes run unchanged on top of ``methods.gnn`` -- this mirror exists so that tests,
+``bench.py`` and ``smoke()`` can drive the same path without the reference tree.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .gnn import GNN_nl
+
+__all__ = ["support_label", "build_graphs", "select_scores", "query_labels", "GnnHead"]
+
+
+def support_label(n_way: int, n_support: int) -> torch.Tensor:
+    """[1, n_way*(n_support+1), n_way]: one-hot class of every support node, zeros for the
+    query slot that closes each class block (gnnnet.py:35-38)."""
+    lab = torch.from_numpy(np.repeat(range(n_way), n_support)).unsqueeze(1)
+    lab = torch.zeros(n_way * n_support, n_way).scatter(1, lab, 1).view(n_way, n_support, n_way)
+    lab = torch.cat([lab, torch.zeros(n_way, 1, n_way)], dim=1)
+    return lab.view(1, -1, n_way)
+
+
+def query_labels(n_way: int, n_query: int) -> torch.Tensor:
+    """gnnnet.py:220 / finetune.py:657: class-major query labels."""
+    return torch.from_numpy(np.repeat(range(n_way), n_query))
+
+
+def build_graphs(z: torch.Tensor, label: torch.Tensor, n_way: int, n_support: int, n_query: int,
+                 compress: bool = False) -> torch.Tensor:
+    """z [n_way, n_support+n_query, D] -> nodes [n_query, n_way*(n_s'+1), D+n_way].
+
+    Graph q = every support embedding + the q-th query of each class (gnnnet.py:83),
+    labels concatenated (gnnnet.py:212).  ``compress`` averages the supports in two halves
+    first (gnnnet_copy.py:34,67-72); ``label`` must then be built for round(n_support/2)."""
+    d = z.size(2)
+    if compress:
+        k = round(n_support / 2)
+        sup = z[:, :2 * k].view(n_way, 2, k, d).mean(dim=1)
+        q0 = 2 * k
+    else:
+        k = n_support
+        sup = z[:, :n_support]
+        q0 = n_support
+    sup = sup.unsqueeze(0).expand(n_query, n_way, k, d)
+    qry = z[:, q0:q0 + n_query].permute(1, 0, 2).unsqueeze(2)            # [n_query, n_way, 1, D]
+    nodes = torch.cat([sup, qry], dim=2).reshape(n_query, n_way * (k + 1), d)
+    lab = label.to(device=z.device, dtype=z.dtype).expand(n_query, -1, -1)
+    return torch.cat([nodes, lab], dim=2)
+
+
+def select_scores(out: torch.Tensor, n_way: int, n_support: int, n_query: int) -> torch.Tensor:
+    """Query node of every class, rows class-major -> [n_way*n_query, n_way] (gnnnet.py:216)."""
+    return out.view(n_query, n_way, n_support + 1, n_way)[:, :, -1].permute(1, 0, 2).contiguous().view(-1, n_way)
+
+
+class GnnHead(nn.Module):
+    """``fc`` + ``gnn`` of the reference GnnNet (gnnnet.py:30-31), driven on features.
+
+    ``set_forward(feat)`` is ``GnnNet.set_forward(x, is_feature=True)`` (gnnnet.py:71-87);
+    ``set_forward_loss(feat)`` adds the cross-entropy of gnnnet.py:219-224."""
+
+    def __init__(self, n_way: int, n_support: int, feat_dim: int = 512, compress: bool = False):
+        super().__init__()
+        self.n_way = n_way
+        self.n_support_in = n_support
+        self.compress = compress
+        self.n_support = round(n_support / 2) if compress else n_support
+        self.n_query = 16
+        self.feat_dim = feat_dim
+        self.fc = nn.Sequential(nn.Linear(feat_dim, 128), nn.BatchNorm1d(128, track_running_stats=False))
+        self.gnn = GNN_nl(128 + n_way, 96, n_way)
+        self.loss_fn = nn.CrossEntropyLoss()
+        self.register_buffer("support_label", support_label(n_way, self.n_support), persistent=False)
+
+    def nodes(self, feat: torch.Tensor) -> torch.Tensor:
+        z = self.fc(feat.reshape(-1, feat.size(-1)))
+        z = z.view(self.n_way, -1, z.size(1))
+        return build_graphs(z, self.support_label, self.n_way, self.n_support_in, self.n_query, self.compress)
+
+    def forward_gnn_nodes(self, nodes: torch.Tensor) -> torch.Tensor:
+        return select_scores(self.gnn(nodes), self.n_way, self.n_support, self.n_query)
+
+    def set_forward(self, feat: torch.Tensor) -> torch.Tensor:
+        return self.forward_gnn_nodes(self.nodes(feat))
+
+    def set_forward_loss(self, feat: torch.Tensor) -> torch.Tensor:
+        y = query_labels(self.n_way, self.n_query).to(feat.device)
+        return self.loss_fn(self.set_forward(feat), y)

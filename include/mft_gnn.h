@@ -169,6 +169,15 @@ const char* mft_prof_name(int cat);
  * since the last collect/enable; n = capacity of both arrays. */
 int mft_prof_collect(float* ms, int* counts, int n);
 
+/* ---- test entry: one tcgen05 "rows x weights" GEMM with plain operands ------------ */
+
+/* C[M,N] = A[M,K] * op(W)^T on the tensor-core path; W is [N,K] (transpose_w = 0) or
+ * [K,N] (transpose_w = 1).  K <= 256, any N (split into passes).  Used by the tests to
+ * pin descriptors / swizzle / pipeline independently of the edge-MLP fusion. */
+size_t mft_debug_umma_gemm_workspace_bytes(int N, int K);
+int mft_debug_umma_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w,
+                        float* C, int ldc, int M, int N, int K, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,8 @@ SIGNATURES = {
     "mft_gnn_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, _vp, _vp, _i, _vp]),
     "mft_gnn_bwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, C.POINTER(GnnGrads), _vp, _vp,
                          _i, _vp]),
+    "mft_debug_umma_gemm_workspace_bytes": (_sz, [_i, _i]),
+    "mft_debug_umma_gemm": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mft_launch_count": (C.c_ulonglong, []),
     "mft_prof_enable": (_i, [_i]),
     "mft_prof_categories": (_i, []),

@@ -26,7 +26,6 @@ int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_g
             void* saved, void* workspace, int precision, cudaStream_t st);
 int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* dx,
             const mft_gnn_grads* g, void* saved, void* workspace, int precision, cudaStream_t st);
-bool umma_shape_supported(int F, int nf);
 
 // The kernels are compiled for sm_100a only; refuse anything else up front instead of
 // failing with "no kernel image" somewhere in the middle of a call.
@@ -142,6 +141,17 @@ int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, con
     MFT_ENTER();
     MFT_REQUIRE(d_out && p && dx && g && saved && workspace, "mft_gnn_bwd: null pointer");
     return gnn_bwd(d_out, B, N, F0, nf, n_way, p, dx, g, saved, workspace, precision, (cudaStream_t)stream);
+}
+
+size_t mft_debug_umma_gemm_workspace_bytes(int N, int K) { return (umma_wimg_floats(N, K) + 64) * sizeof(float); }
+
+int mft_debug_umma_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w, float* C, int ldc,
+                        int M, int N, int K, void* workspace, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(A && W && C && workspace, "mft_debug_umma_gemm: null pointer");
+    MFT_REQUIRE(umma_wimg_floats(N, K) > 0, "mft_debug_umma_gemm: unsupported N=%d K=%d", N, K);
+    return umma_debug_gemm(A, lda, W, ldw, transpose_w, C, ldc, M, N, K, static_cast<float*>(workspace),
+                           (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -414,6 +414,7 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     L.dyA = ws.take<float>(R * 2 * nf);
     L.dyB = ws.take<float>(R * 2 * nf);
     L.bsums = ws.take<double>(5 * 2 * kMaxC);
+    L.wimg = ws.take<float>(umma_workspace_floats(F, nf) + 64);
     L.workspace_bytes = ws.used();
     return L;
 }

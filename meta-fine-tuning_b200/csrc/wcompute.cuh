@@ -15,8 +15,15 @@ struct WcLayout {
     float* dyA;          // workspace: ping-pong gradient buffers [R, 2nf]
     float* dyB;
     double* bsums;       // workspace: backward reductions, 5 x [2*kMaxC] (last = d conv2d_last.weight)
+    float* wimg;         // workspace: swizzled TF32 weight image of the tcgen05 path
     size_t saved_bytes, workspace_bytes;
 };
+
+size_t umma_workspace_floats(int F, int nf);
+bool umma_shape_supported(int F, int nf);
+int umma_debug_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w, float* C, int ldc, int M,
+                    int N, int K, float* wimg, cudaStream_t st);
+size_t umma_wimg_floats(int N, int K);
 
 WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace);
 

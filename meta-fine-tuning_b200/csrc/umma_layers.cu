@@ -581,13 +581,53 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
     return MFT_OK;
 }
 
+// dx[b,n,:] += sum_{m != n} sign(x_n - x_m) * dD[pair{n,m}]  -- the backward of abs() and of the
+// broadcast subtraction (gnn.py:79-81) as a gather: one CTA per node, no atomics.  dD holds the
+// twin-summed gradient of each unordered pair, so the same formula serves both ends of a pair.
+__global__ void __launch_bounds__(256)
+dx_gather_kernel(const float* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
+                 int ldx, int F, int N, int Rg) {
+    const int node = blockIdx.x;            // b*N + n
+    const int b = node / N, n = node - b * N;
+    const float* xn = x + (size_t)node * ldx;
+    const float* Db = dD + (size_t)b * Rg * ldd;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const float xv = xn[f];
+        float acc = 0.f;
+        for (int m = 0; m < N; ++m) {
+            if (m == n) continue;
+            const int i = min(n, m), j = max(n, m);
+            const int r = tri_start(i, N) + (j - i);
+            const float df = xv - __ldg(x + (size_t)(b * N + m) * ldx + f);
+            const float d = __ldg(Db + (size_t)r * ldd + f);
+            acc += (df > 0.f) ? d : ((df < 0.f) ? -d : 0.f);
+        }
+        dx[(size_t)node * ldx + f] += acc;
+    }
+}
+
+// dgrad of conv layer k (0-based): dL/d a_k = dH_k W_k on tensor cores; the epilogue turns it into
+// dy_{k-1} (+ BN-backward reductions) or, for layer 0, into dD followed by the dx gather.
 int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, int ldx, float* dx, int F, int nf,
                             const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                             const PairGeom& g, cudaStream_t st) {
-    (void)k; (void)dh; (void)dy_next; (void)x; (void)ldx; (void)dx; (void)F; (void)nf; (void)p; (void)gr;
-    (void)L; (void)g; (void)st;
-    set_error(MFT_ERR_UNSUPPORTED, "tf32 backward not wired yet");
-    return MFT_ERR_UNSUPPORTED;
+    (void)gr; (void)nf;
+    const int Cout = L.C[k + 1], Cin = L.C[k];
+    PlainU a{dh, Cout, Cout, 1};
+    if (k == 0) {
+        const int ldd = (F + 3) & ~3;
+        EpiStoreU e{L.dD, ldd, 1};
+        int rc = umma_rows_gemm(a, e, p->conv_w[0], Cin, 1, g.R, Cin, Cout, L.wimg, st, PC_DGRAD_L1);
+        if (rc != MFT_OK) return rc;
+        ProfScope ps(PC_DGRAD_L1, st);
+        dx_gather_kernel<<<g.B * g.N, 256, 0, st>>>(L.dD, ldd, x, dx, ldx, F, g.N, g.Rg);
+        MFT_CHECK_LAUNCH();
+        return MFT_OK;
+    }
+    const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+    double* pbs = L.bsums + (size_t)(k - 1) * 2 * kMaxC;
+    EpiDyU e{L.H[k - 1], dy_next, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
+    return umma_rows_gemm(a, e, p->conv_w[k], Cin, 1, g.R, Cin, Cout, L.wimg, st, PC_DGRAD_L1 + k);
 }
 
 // Debug / test entry: C[M, N] = A[M, K] * op(W)^T through the tcgen05 rows kernel with plain

@@ -415,6 +415,7 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     L.dyB = ws.take<float>(R * 2 * nf);
     L.bsums = ws.take<double>(5 * 2 * kMaxC);
     L.wimg = ws.take<float>(umma_workspace_floats(F, nf) + 64);
+    L.dD = ws.take<float>(umma_shape_supported(F, nf) ? R * (size_t)((F + 3) & ~3) : 0);
     L.workspace_bytes = ws.used();
     return L;
 }
@@ -509,10 +510,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             dh_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(cur, L.H[k], Cout, fs, p->bn_g[k], bs, g);
             MFT_CHECK_LAUNCH();
         }
-        if (precision == MFT_PREC_TF32) {
-            int rc = wcompute_bwd_layer_tf32(k, cur, nxt, x, ldx, dx, F, nf, p, gr, L, g, st);
-            if (rc != MFT_OK) return rc;
-        } else {
+        {
             PlainA dh{cur, Cout};
             // wgrad: d conv2d_{k+1}.weight [Cout, Cin] = dH^T a_k
             if (k == 0) {
@@ -526,16 +524,21 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
                 MFT_CHECK_CUDA((launch_gemm_tn(dh, q, gr->conv_w[k], Cin, Cout, Cin, g.R, st)));
             }
             // dgrad: dL/d a_k = dH W
-            WView wv = wview_nn(p->conv_w[k], Cin);
-            ProfScope psd(PC_DGRAD_L1 + k, st);
-            if (k == 0) {
-                EpiDx epi{x, dx, ldx, g};
-                MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
+            if (precision == MFT_PREC_TF32) {
+                int rc = wcompute_bwd_layer_tf32(k, cur, nxt, x, ldx, dx, F, nf, p, gr, L, g, st);
+                if (rc != MFT_OK) return rc;
             } else {
-                const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
-                double* pbs = L.bsums + (size_t)(k - 1) * 2 * kMaxC;
-                EpiDy epi{L.H[k - 1], nxt, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
-                MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
+                WView wv = wview_nn(p->conv_w[k], Cin);
+                ProfScope psd(PC_DGRAD_L1 + k, st);
+                if (k == 0) {
+                    EpiDx epi{x, dx, ldx, g};
+                    MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
+                } else {
+                    const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+                    double* pbs = L.bsums + (size_t)(k - 1) * 2 * kMaxC;
+                    EpiDy epi{L.H[k - 1], nxt, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
+                    MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
+                }
             }
         }
         float* tmp = cur; cur = nxt; nxt = tmp;

@@ -16,6 +16,7 @@ struct WcLayout {
     float* dyB;
     double* bsums;       // workspace: backward reductions, 5 x [2*kMaxC] (last = d conv2d_last.weight)
     float* wimg;         // workspace: swizzled TF32 weight image of the tcgen05 path
+    float* dD;           // workspace (tcgen05 path): dL/d|x_i-x_j| per unordered pair, [R, roundup4(F)]
     size_t saved_bytes, workspace_bytes;
 };
 

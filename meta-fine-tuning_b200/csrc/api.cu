@@ -154,4 +154,11 @@ int mft_debug_umma_gemm(const float* A, int lda, const float* W, int ldw, int tr
                            (cudaStream_t)stream);
 }
 
+int mft_debug_umma_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW, int ldw, int R, int Cout,
+                         int Cin, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(P && Q && dW, "mft_debug_umma_wgrad: null pointer");
+    return umma_debug_wgrad(P, ldp, Q, ldq, dW, ldw, R, Cout, Cin, (cudaStream_t)stream);
+}
+
 }  // extern "C"

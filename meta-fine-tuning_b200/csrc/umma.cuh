@@ -134,13 +134,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
 
 // Shared-memory matrix descriptor, SWIZZLE_128B, 8-row groups `sbo_bytes` apart
 // (1024 for the dense K-major layout above); `lbo_bytes` only matters for MN-major.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t lbo_bytes) {
+//
+// layout_type 2 = SWIZZLE_128B (16-byte chunks XOR row%8; K-major operands here);
+// layout_type 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR row%4): the only swizzled layout the
+// hardware accepts for MN-major 32-bit (tf32) operands -- atoms are 4 k-rows x 128 bytes.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t lbo_bytes,
+                                                    uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // leading byte offset, bits [16,30)
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;     // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                                // layout type: SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;                      // layout type
     return d;
 }
 

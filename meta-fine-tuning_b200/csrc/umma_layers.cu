@@ -75,37 +75,48 @@ __global__ void umma_weight_image_kernel(const float* __restrict__ W, int ldw, i
 }
 
 // ------------------------------------------------------------------ producer functors
-// load4(row, k): four consecutive K elements starting at k (k % 4 == 0), zero beyond K.
+// fetch(row, k, raw): issue the (read-only, non-coherent) global loads of four consecutive K
+// elements starting at k (k % 4 == 0); finish(raw, k, aux): turn them into operand values, zero
+// beyond K.  The split lets a producer thread keep all eight rows of a K block (and, for
+// kDouble operands, the next block as well) in flight before it touches any of them.
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 struct AbsDiffU {
+    static constexpr bool kDouble = false;   // x is small and L2 resident; 16 loads in flight suffice
     const float* x;
     int ldx, F;
     PairGeom g;
     int vec_ok;
     struct Row { const float* xi; const float* xj; };
+    struct Raw { float4 a, b; };
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ Row row(int r) const {
         PairRow p = decode_row(r, g);
         return Row{x + (size_t)(p.b * g.N + p.i) * ldx, x + (size_t)(p.b * g.N + p.j) * ldx};
     }
-    __device__ __forceinline__ float4 load4(const Row& rw, int k, const float*) const {
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k >= F) return o;
+    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
+        o.a = make_float4(0.f, 0.f, 0.f, 0.f);
+        o.b = o.a;
+        if (k >= F) return;
         if (vec_ok && k + 3 < F) {
-            float4 a = __ldg(reinterpret_cast<const float4*>(rw.xi + k));
-            float4 b = __ldg(reinterpret_cast<const float4*>(rw.xj + k));
-            return make_float4(fabsf(a.x - b.x), fabsf(a.y - b.y), fabsf(a.z - b.z), fabsf(a.w - b.w));
+            o.a = ldg4(rw.xi + k);
+            o.b = ldg4(rw.xj + k);
+            return;
         }
-        o.x = fabsf(__ldg(rw.xi + k) - __ldg(rw.xj + k));
-        if (k + 1 < F) o.y = fabsf(__ldg(rw.xi + k + 1) - __ldg(rw.xj + k + 1));
-        if (k + 2 < F) o.z = fabsf(__ldg(rw.xi + k + 2) - __ldg(rw.xj + k + 2));
-        if (k + 3 < F) o.w = fabsf(__ldg(rw.xi + k + 3) - __ldg(rw.xj + k + 3));
-        return o;
+        o.a.x = __ldg(rw.xi + k); o.b.x = __ldg(rw.xj + k);
+        if (k + 1 < F) { o.a.y = __ldg(rw.xi + k + 1); o.b.y = __ldg(rw.xj + k + 1); }
+        if (k + 2 < F) { o.a.z = __ldg(rw.xi + k + 2); o.b.z = __ldg(rw.xj + k + 2); }
+        if (k + 3 < F) { o.a.w = __ldg(rw.xi + k + 3); o.b.w = __ldg(rw.xj + k + 3); }
+    }
+    __device__ __forceinline__ float4 finish(const Raw& r, int, const float*) const {
+        return make_float4(fabsf(r.a.x - r.b.x), fabsf(r.a.y - r.b.y), fabsf(r.a.z - r.b.z), fabsf(r.a.w - r.b.w));
     }
 };
 
 // a = LeakyReLU(scale*h + shift), scale = gamma*rstd, shift = beta - mean*scale (C % 4 == 0)
 struct BnActU {
+    static constexpr bool kDouble = true;
     const float* H;
     int C;
     const double* sums;
@@ -113,6 +124,7 @@ struct BnActU {
     const float* beta;
     double inv_count;
     struct Row { const float* h; };
+    struct Raw { float4 h; };
     __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
         for (int c = tid; c < C; c += nthreads) {
             float m, r;
@@ -123,36 +135,40 @@ struct BnActU {
         }
     }
     __device__ __forceinline__ Row row(int r) const { return Row{H + (size_t)r * C}; }
-    __device__ __forceinline__ float4 load4(const Row& rw, int k, const float* aux) const {
+    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
+        o.h = (k < C) ? ldg4(rw.h + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ float4 finish(const Raw& r, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 h = *reinterpret_cast<const float4*>(rw.h + k);
         float4 sc = *reinterpret_cast<const float4*>(aux + k);
         float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
         float4 y;
-        y.x = fmaf(h.x, sc.x, sh.x); y.y = fmaf(h.y, sc.y, sh.y);
-        y.z = fmaf(h.z, sc.z, sh.z); y.w = fmaf(h.w, sc.w, sh.w);
+        y.x = fmaf(r.h.x, sc.x, sh.x); y.y = fmaf(r.h.y, sc.y, sh.y);
+        y.z = fmaf(r.h.z, sc.z, sh.z); y.w = fmaf(r.h.w, sc.w, sh.w);
         return make_float4(fmaxf(y.x, kSlope * y.x), fmaxf(y.y, kSlope * y.y), fmaxf(y.z, kSlope * y.z),
                            fmaxf(y.w, kSlope * y.w));
     }
 };
 
 struct PlainU {
+    static constexpr bool kDouble = true;
     const float* p;
     int ld, K;
     int vec_ok;
     struct Row { const float* q; };
+    struct Raw { float4 v; };
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ Row row(int r) const { return Row{p + (size_t)r * ld}; }
-    __device__ __forceinline__ float4 load4(const Row& rw, int k, const float*) const {
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k >= K) return o;
-        if (vec_ok && k + 3 < K) return *reinterpret_cast<const float4*>(rw.q + k);
-        o.x = rw.q[k];
-        if (k + 1 < K) o.y = rw.q[k + 1];
-        if (k + 2 < K) o.z = rw.q[k + 2];
-        if (k + 3 < K) o.w = rw.q[k + 3];
-        return o;
+    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
+        o.v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k >= K) return;
+        if (vec_ok && k + 3 < K) { o.v = ldg4(rw.q + k); return; }
+        o.v.x = __ldg(rw.q + k);
+        if (k + 1 < K) o.v.y = __ldg(rw.q + k + 1);
+        if (k + 2 < K) o.v.z = __ldg(rw.q + k + 2);
+        if (k + 3 < K) o.v.w = __ldg(rw.q + k + 3);
     }
+    __device__ __forceinline__ float4 finish(const Raw& r, int, const float*) const { return r.v; }
 };
 
 // ------------------------------------------------------------------ epilogue functors
@@ -167,7 +183,8 @@ struct EpiStoreU {
     int vec_ok;
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ float row_weight(int) const { return 1.f; }
-    __device__ __forceinline__ void apply(int r, float, int col, float4 v, int nvalid, float*, float*,
+    __device__ __forceinline__ float4 prefetch(int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void apply(int r, float, int col, float4 v, float4, int nvalid, float*, float*,
                                           const float*) const {
         float* o = out + (size_t)r * ld + col;
         if (vec_ok && nvalid == 4) {
@@ -192,7 +209,8 @@ struct EpiFwdStatsU {
     PairGeom g;
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ float row_weight(int r) const { return decode_row(r, g).w; }
-    __device__ __forceinline__ void apply(int r, float w, int col, float4 v, int, float* s0, float* s1,
+    __device__ __forceinline__ float4 prefetch(int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void apply(int r, float w, int col, float4 v, float4, int, float* s0, float* s1,
                                           const float*) const {
         *reinterpret_cast<float4*>(H + (size_t)r * C + col) = v;
         s0[0] = fmaf(w, v.x, s0[0]); s1[0] = fmaf(w * v.x, v.x, s1[0]);
@@ -231,9 +249,9 @@ struct EpiDyU {
         }
     }
     __device__ __forceinline__ float row_weight(int) const { return 1.f; }
-    __device__ __forceinline__ void apply(int r, float, int col, float4 v, int, float* s0, float* s1,
+    __device__ __forceinline__ float4 prefetch(int r, int col) const { return ldg4(H + (size_t)r * C + col); }
+    __device__ __forceinline__ void apply(int r, float, int col, float4 v, float4 h, int, float* s0, float* s1,
                                           const float* aux) const {
-        float4 h = *reinterpret_cast<const float4*>(H + (size_t)r * C + col);
         float4 sc = *reinterpret_cast<const float4*>(aux + col);
         float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + col);
         float4 d;
@@ -304,35 +322,69 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
 
     if (warp < 4) {
         // ===================== producers =====================
+        // Thread t owns 16-byte column c16 = t%8 of rows q*16 + t/8 (q = 0..7) of every K block, so
+        // its per-channel constants never change within a block and a warp's loads cover four
+        // full 128-byte row segments.  The fetch iterator runs one K block ahead of the write
+        // iterator (kDouble) so that global latency overlaps the transform + smem stores.
         const int rsub = tid >> 3, c16 = tid & 7;
         const int sw = rsub & 7;
         int st = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int row0 = tile * UM_ROWS;
-            typename AOp::Row rc[8];
-            bool valid[8];
+        typename AOp::Row rc[8];
+        typename AOp::Raw cur[8], nxt[8];
+        uint32_t vcur = 0, vnxt = 0, vrows = 0;
+        int f_tile = blockIdx.x, f_kc = 0;
+        auto load_rows = [&](int tile) {
+            vrows = 0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                int r = row0 + q * 16 + rsub;
-                valid[q] = r < s.R;
-                rc[q] = aop.row(valid[q] ? r : 0);
+                int r = tile * UM_ROWS + q * 16 + rsub;
+                bool ok = r < s.R;
+                vrows |= (ok ? 1u : 0u) << q;
+                rc[q] = aop.row(ok ? r : 0);
             }
-            for (int kc = 0; kc < s.KC; ++kc) {
-                mbar_wait(&empty[st], ph ^ 1);
-                float* dst = Asm + (size_t)st * UM_BLOCK_FLOATS;
-                const int k = kc * UM_KB + c16 * 4;
+        };
+        auto fetch = [&](typename AOp::Raw (&dst)[8], uint32_t& vmask, int kc) {
+            const int k = kc * UM_KB + c16 * 4;
+            vmask = vrows;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int rl = q * 16 + rsub;
-                    float4 v = valid[q] ? aop.load4(rc[q], k, aux_a) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-                    *reinterpret_cast<float4*>(dst + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
-                }
-                fence_proxy_async_smem();
-                mbar_arrive(&full[st]);
-                if (++st == s.stages) { st = 0; ph ^= 1; }
+            for (int q = 0; q < 8; ++q) aop.fetch(rc[q], k, dst[q]);   // row 0 stands in for invalid rows
+        };
+        if (f_tile < ntiles) {
+            load_rows(f_tile);
+            fetch(cur, vcur, 0);
+        }
+        int w_tile = f_tile, w_kc = 0;
+        while (w_tile < ntiles) {
+            if (++f_kc == s.KC) { f_kc = 0; f_tile += gridDim.x; }
+            const bool more = f_tile < ntiles;
+            if (AOp::kDouble && more) {
+                if (f_kc == 0) load_rows(f_tile);
+                fetch(nxt, vnxt, f_kc);
             }
+            mbar_wait(&empty[st], ph ^ 1);
+            float* dst = Asm + (size_t)st * UM_BLOCK_FLOATS;
+            const int k = w_kc * UM_KB + c16 * 4;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int rl = q * 16 + rsub;
+                float4 v = aop.finish(cur[q], k, aux_a);
+                if (!((vcur >> q) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                *reinterpret_cast<float4*>(dst + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&full[st]);
+            if (++st == s.stages) { st = 0; ph ^= 1; }
+            if (AOp::kDouble) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+                vcur = vnxt;
+            } else if (more) {
+                if (f_kc == 0) load_rows(f_tile);
+                fetch(cur, vcur, f_kc);
+            }
+            if (++w_kc == s.KC) { w_kc = 0; w_tile += gridDim.x; }
         }
     } else if (warp == 8) {
         // ===================== MMA issuer (one thread) =====================
@@ -407,14 +459,20 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
                     const int col = s.n0 + cl;            // global output column
                     if (cl < s.N_TILE && col < s.N) {
                         const int nvalid = min(4, s.N - col);
+                        float4 pre[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int r = row0 + q * 16 + rsub;
+                            pre[q] = (r < s.R) ? epi.prefetch(r, col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int rl = q * 16 + rsub;
                             const int r = row0 + rl;
                             if (r < s.R) {
                                 float4 a = *reinterpret_cast<const float4*>(stage + rl * UM_STAGE_LD + c4);
-                                epi.apply(r, Epi::kRowWeight ? wrow[rl] : 1.f, col, a, nvalid, s0[ch], s1[ch],
-                                          aux_e);
+                                epi.apply(r, Epi::kRowWeight ? wrow[rl] : 1.f, col, a, pre[q], nvalid, s0[ch],
+                                          s1[ch], aux_e);
                             }
                         }
                     }
@@ -442,6 +500,209 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
             for (int cl = et; cl < s.N_TILE; cl += 128)
                 if (s.n0 + cl < s.N) epi.commit(s.n0 + cl, red0[cl], red1[cl], aux_e);
         }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, UM_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ wgrad kernel
+// dW[co, ci] = sum_r P(r, co) * Q(r, ci) over the CTA's slice of pair rows, accumulated in TMEM
+// for the whole kernel and added into global dW once at the end.
+//
+// The reduction index is the ROW, so both operands are MN-major: P^T as A (M = co) and Q^T as B
+// (N = ci).  For 32-bit (tf32) MN-major operands the hardware accepts one swizzled layout only,
+// SWIZZLE_128B_BASE32B: atoms of 4 k-rows x 128 bytes (32 consecutive channels), the four
+// 32-byte chunks of row k stored at chunk index (c ^ (k % 4)).  Producers store [32 rows x 32
+// channels] blocks in that form; LBO = byte stride between 32-channel blocks, SBO = stride
+// between 4-row atoms (512, dense).  One K chunk = 32 rows = four tcgen05.mma K steps of 8 rows.
+//
+// M = co is covered by two M=128 instructions: rows [0,128) and, when Cout > 128, rows
+// [Cout-128, Cout) (overlap recomputed -- keeps the plain 128-lane TMEM layout).  For Cout < 128
+// the operand read runs past the last channel block into the neighbouring buffer: those
+// accumulator rows are garbage and never leave TMEM.
+constexpr int WG_ROWS = 32;                       // rows per K chunk
+constexpr int WG_BLOCK_FLOATS = WG_ROWS * UM_KB;  // [32 rows x 32 ch] = 1024 floats = 4 KB
+constexpr int WG_PROD_THREADS = 256;
+constexpr int WG_MAX_PB = 6;                      // Cout <= 192
+constexpr int WG_MAX_QB = 8;                      // Cin  <= 256
+
+struct WgradShape {
+    int R;
+    int Cout, Cin;     // valid channels of P and Q
+    int PB, QB;        // 32-channel blocks of P and Q
+    int N_TILE;        // MMA N = roundup16(Cin)
+    int stages;
+    int chunks_per_cta;
+};
+
+static inline size_t wgrad_smem_bytes(const WgradShape& s) {
+    return 1024 + (size_t)s.stages * (s.PB + s.QB) * WG_BLOCK_FLOATS * 4 + (size_t)UM_ROWS * UM_STAGE_LD * 4 +
+           (3 + 3) * kMaxC * 4 + 16 * 8 + 16;
+}
+
+template <class POp, class QOp>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape s) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_floats = (s.PB + s.QB) * WG_BLOCK_FLOATS;
+    float* ring = reinterpret_cast<float*>(smem);
+    float* stage = ring + (size_t)s.stages * stage_floats;
+    float* aux_p = stage + UM_ROWS * UM_STAGE_LD;
+    float* aux_q = aux_p + 3 * kMaxC;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aux_q + 3 * kMaxC);
+    uint64_t* full = bars;        // [UM_MAX_STAGES]
+    uint64_t* empty = bars + 4;   // [UM_MAX_STAGES]
+    uint64_t* done = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nchunks_total = (s.R + WG_ROWS - 1) / WG_ROWS;
+    const int c_begin = blockIdx.x * s.chunks_per_cta;
+    const int c_end = min(nchunks_total, c_begin + s.chunks_per_cta);
+    const int my_chunks = max(0, c_end - c_begin);
+
+    if (tid == 0) {
+        for (int i = 0; i < UM_MAX_STAGES; ++i) {
+            mbar_init(&full[i], WG_PROD_THREADS);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(done, 1);
+        fence_mbar_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, UM_TMEM_COLS);
+    pop.init(aux_p, tid, UM_THREADS);
+    qop.init(aux_q, tid, UM_THREADS);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool two_blocks = s.Cout > 128;
+
+    if (warp < 8) {
+        // ===================== producers: thread t -> row t/8 of the chunk, 16-byte column t%8
+        const int rl = tid >> 3, c16 = tid & 7;
+        // floats: 4-row atom (rl/4) * 128 + row-in-atom * 32 + swizzled 32-byte chunk * 8 + 16-byte half * 4
+        const int off = (rl >> 2) * 128 + (rl & 3) * 32 + ((((c16 >> 1) ^ (rl & 3))) << 3) + ((c16 & 1) << 2);
+        int st = 0;
+        uint32_t ph = 0;
+        typename POp::Raw praw[WG_MAX_PB];
+        typename QOp::Raw qraw[WG_MAX_QB];
+        bool ok = false;
+        auto fetch = [&](int chunk) {
+            const int r = chunk * WG_ROWS + rl;
+            ok = r < s.R;
+            typename POp::Row pr = pop.row(ok ? r : 0);
+            typename QOp::Row qr = qop.row(ok ? r : 0);
+#pragma unroll
+            for (int b = 0; b < WG_MAX_PB; ++b)
+                if (b < s.PB) pop.fetch(pr, b * UM_KB + c16 * 4, praw[b]);
+#pragma unroll
+            for (int b = 0; b < WG_MAX_QB; ++b)
+                if (b < s.QB) qop.fetch(qr, b * UM_KB + c16 * 4, qraw[b]);
+        };
+        if (my_chunks > 0) fetch(c_begin);
+        for (int c = c_begin; c < c_end; ++c) {
+            mbar_wait(&empty[st], ph ^ 1);
+            float* dst = ring + (size_t)st * stage_floats + off;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < WG_MAX_PB; ++b) {
+                if (b < s.PB) {
+                    float4 v = ok ? pop.finish(praw[b], b * UM_KB + c16 * 4, aux_p) : zero;
+                    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                    *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < WG_MAX_QB; ++b) {
+                if (b < s.QB) {
+                    float4 v = ok ? qop.finish(qraw[b], b * UM_KB + c16 * 4, aux_q) : zero;
+                    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                    *reinterpret_cast<float4*>(dst + (s.PB + b) * WG_BLOCK_FLOATS) = v;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&full[st]);
+            if (++st == s.stages) { st = 0; ph ^= 1; }
+            if (c + 1 < c_end) fetch(c + 1);
+        }
+    } else {
+        // ===================== MMA issuer
+        if (lane == 0 && my_chunks > 0) {
+            const uint32_t idesc = make_idesc_tf32(128, s.N_TILE, true, true);
+            const uint32_t ring0 = smem_u32(ring);
+            const uint32_t lbo = WG_BLOCK_FLOATS * 4;       // next 32-channel block
+            const uint32_t sbo = 512;                       // next 4-row atom
+            const uint32_t kstep = 1024;                    // 8 rows per MMA
+            const uint32_t m2_off = two_blocks ? (uint32_t)((s.Cout - 128) / UM_KB) * lbo : 0;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int c = c_begin; c < c_end; ++c) {
+                mbar_wait(&full[st], ph);
+                tc_fence_after_sync();
+                const uint32_t pb = ring0 + (uint32_t)st * stage_floats * 4;
+                const uint32_t qb = pb + (uint32_t)s.PB * lbo;
+                for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
+                    const uint32_t acc_on = (c > c_begin || ks > 0) ? 1u : 0u;
+                    const uint64_t bdesc = make_desc_sw128(qb + ks * kstep, sbo, lbo, 1);
+                    mma_tf32_ss(tmem_base, make_desc_sw128(pb + ks * kstep, sbo, lbo, 1), bdesc, idesc, acc_on);
+                    if (two_blocks)
+                        mma_tf32_ss(tmem_base + UM_ACC_STRIDE,
+                                    make_desc_sw128(pb + m2_off + ks * kstep, sbo, lbo, 1), bdesc, idesc, acc_on);
+                }
+                mma_commit(&empty[st]);
+                if (++st == s.stages) { st = 0; ph ^= 1; }
+            }
+            mma_commit(done);
+        }
+        __syncwarp();
+    }
+
+    // ===================== dump: warps 0-3 drain TMEM and add into global dW
+    if (warp < 4 && my_chunks > 0) {
+        mbar_wait(done, 0);
+        tc_fence_after_sync();
+        const int et = tid;                 // 0..127 = TMEM lane
+        const int rsub = et >> 3, c4 = (et & 7) * 4;
+        const int nchunks = (s.N_TILE + 31) / 32;
+        const int nblk = two_blocks ? 2 : 1;
+        for (int blk = 0; blk < nblk; ++blk) {
+            // block 0: lane l <-> co l; block 1: lane l <-> co (Cout-128)+l, only the rows block 0 lacks
+            const int co_base = blk == 0 ? 0 : s.Cout - 128;
+            const int lane_lo = blk == 0 ? 0 : 128 - (s.Cout - 128);
+            for (int ch = 0; ch < nchunks; ++ch) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + blk * UM_ACC_STRIDE + ch * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(stage + et * UM_STAGE_LD + q * 4) =
+                        make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                named_bar_sync(1, 128);
+                const int col = ch * 32 + c4;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int l = q * 16 + rsub;
+                    const int co = co_base + l;
+                    if (l >= lane_lo && co < s.Cout && col < s.Cin) {
+                        const float* sp = stage + l * UM_STAGE_LD + c4;
+                        float* gp = dW + (size_t)co * ldw + col;
+                        const int nv = min(4, s.Cin - col);
+                        for (int e = 0; e < nv; ++e) atomicAdd(gp + e, sp[e]);
+                    }
+                }
+                named_bar_sync(1, 128);
+            }
+        }
+        tc_fence_before_sync();
     }
 
     tc_fence_before_sync();
@@ -536,6 +797,48 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
     return MFT_OK;
 }
 
+template <class POp, class QOp>
+static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R, int Cout, int Cin,
+                      cudaStream_t st, int cat) {
+    WgradShape s{};
+    s.R = R; s.Cout = Cout; s.Cin = Cin;
+    s.PB = cdiv(Cout, UM_KB);
+    s.QB = cdiv(Cin, UM_KB);
+    s.N_TILE = (Cin + 15) & ~15;
+    if (s.PB > WG_MAX_PB || s.QB > WG_MAX_QB || s.N_TILE > 256 || Cout > 192 || (Cout > 128 && Cout % UM_KB != 0)) {
+        set_error(MFT_ERR_UNSUPPORTED, "umma_wgrad: unsupported Cout=%d Cin=%d", Cout, Cin);
+        return MFT_ERR_UNSUPPORTED;
+    }
+    s.stages = 0;
+    for (int stg = UM_MAX_STAGES; stg >= 2; --stg) {
+        s.stages = stg;
+        if (wgrad_smem_bytes(s) <= kSmemLimit) break;
+        s.stages = 0;
+    }
+    if (s.stages == 0) {
+        set_error(MFT_ERR_UNSUPPORTED, "umma_wgrad: no shared-memory plan for Cout=%d Cin=%d", Cout, Cin);
+        return MFT_ERR_UNSUPPORTED;
+    }
+    const int nchunks = cdiv(R, WG_ROWS);
+    const int grid = min(nchunks, num_sms());
+    s.chunks_per_cta = cdiv(nchunks, grid);
+    size_t smem = wgrad_smem_bytes(s);
+    MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<POp, QOp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    ProfScope ps(cat, st);
+    umma_wgrad_kernel<POp, QOp><<<cdiv(nchunks, s.chunks_per_cta), UM_THREADS, smem, st>>>(pop, qop, dW, ldw, s);
+    MFT_CHECK_LAUNCH();
+    return MFT_OK;
+}
+
+// Test entry: dW[Cout, Cin] += P[R, Cout]^T Q[R, Cin] with plain operands.
+int umma_debug_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW, int ldw, int R, int Cout,
+                     int Cin, cudaStream_t st) {
+    PlainU p{P, ldp, Cout, (ldp % 4 == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0) ? 1 : 0};
+    PlainU q{Q, ldq, Cin, (ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0) ? 1 : 0};
+    return umma_wgrad(p, q, dW, ldw, R, Cout, Cin, st, PC_MISC);
+}
+
 bool umma_shape_supported(int F, int nf) {
     if (nf % 16 != 0 || 2 * nf > kMaxC || 2 * nf > UM_MAX_NTILE) return false;
     int n0s[4], nt[4];
@@ -628,6 +931,21 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
     double* pbs = L.bsums + (size_t)(k - 1) * 2 * kMaxC;
     EpiDyU e{L.H[k - 1], dy_next, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
     return umma_rows_gemm(a, e, p->conv_w[k], Cin, 1, g.R, Cin, Cout, L.wimg, st, PC_DGRAD_L1 + k);
+}
+
+// wgrad of conv layer k: d conv2d_{k+1}.weight [Cout, Cin] += dH_k^T a_k (a_0 = |x_i - x_j|).
+int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, int F,
+                              const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
+                              const PairGeom& g, cudaStream_t st) {
+    const int Cout = L.C[k + 1], Cin = L.C[k];
+    PlainU P{dh, Cout, Cout, 1};
+    if (k == 0) {
+        AbsDiffU Q{x, ldx, F, g, (ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0};
+        return umma_wgrad(P, Q, gr->conv_w[0], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1);
+    }
+    const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+    BnActU Q{L.H[k - 1], Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
+    return umma_wgrad(P, Q, gr->conv_w[k], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1 + k);
 }
 
 // Debug / test entry: C[M, N] = A[M, K] * op(W)^T through the tcgen05 rows kernel with plain

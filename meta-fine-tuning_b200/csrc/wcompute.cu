@@ -513,7 +513,10 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         {
             PlainA dh{cur, Cout};
             // wgrad: d conv2d_{k+1}.weight [Cout, Cin] = dH^T a_k
-            if (k == 0) {
+            if (precision == MFT_PREC_TF32) {
+                int rc = wcompute_wgrad_layer_tf32(k, cur, x, ldx, F, p, gr, L, g, st);
+                if (rc != MFT_OK) return rc;
+            } else if (k == 0) {
                 ProfScope ps(PC_WGRAD_L1, st);
                 AbsDiffA q{x, ldx, g};
                 MFT_CHECK_CUDA((launch_gemm_tn(dh, q, gr->conv_w[0], Cin, Cout, Cin, g.R, st)));

@@ -25,6 +25,8 @@ bool umma_shape_supported(int F, int nf);
 int umma_debug_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w, float* C, int ldc, int M,
                     int N, int K, float* wimg, cudaStream_t st);
 size_t umma_wimg_floats(int N, int K);
+int umma_debug_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW, int ldw, int R, int Cout,
+                     int Cin, cudaStream_t st);
 
 WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace);
 
@@ -41,6 +43,10 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
 int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, int ldx, float* dx, int F, int nf,
                             const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                             const PairGeom& g, cudaStream_t st);
+
+int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, int F,
+                              const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
+                              const PairGeom& g, cudaStream_t st);
 
 struct GcLayout {
     float* Y;            // saved: pre-BN Gconv output [B*N, n_out]

@@ -60,3 +60,29 @@ def test_umma_gemm_unaligned_leading_dimension():
     out = _umma_gemm(A, W, False, N, K)
     ref = (A.double() @ W.double().t()).float()
     assert float((out - ref).norm() / ref.norm()) < 1e-3
+
+
+@pytest.mark.parametrize("R,Cout,Cin", [
+    (32, 96, 96),           # one K chunk
+    (1000, 96, 96),         # layer 4
+    (4000, 96, 192),        # layer 3: M = 96 (< 128: garbage accumulator rows must stay inside TMEM)
+    (5000, 192, 192),       # layer 2: two overlapping M=128 blocks
+    (3333, 192, 133),       # layer 1, F = 133 (N = 144, masked tail columns, ragged rows)
+    (89040, 192, 229),      # 5w20s row count, F = 229 (N = 240)
+    (777, 32, 16),          # tiny-fixture widths (nf = 16)
+])
+def test_umma_wgrad_matches_fp32(R, Cout, Cin):
+    from mft_b200 import _lib
+    lib = _lib.load_library()
+    g = torch.Generator(device="cuda").manual_seed(R + Cout + Cin)
+    P = torch.randn(R, Cout, device="cuda", generator=g)
+    Q = torch.randn(R, Cin, device="cuda", generator=g)
+    dW = torch.zeros(Cout, Cin, device="cuda")
+    rc = lib.mft_debug_umma_wgrad(P.data_ptr(), P.stride(0), Q.data_ptr(), Q.stride(0), dW.data_ptr(),
+                                  dW.stride(0), R, Cout, Cin, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "mft_debug_umma_wgrad")
+    torch.cuda.synchronize()
+    ref = (P.double().t() @ Q.double()).float()
+    assert torch.isfinite(dW).all()
+    err = float((dW - ref).norm() / ref.norm())
+    assert err < 1e-3, err

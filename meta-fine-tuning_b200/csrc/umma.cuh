@@ -158,6 +158,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// Register re-balancing between warp roles (all warps of a warpgroup execute it).
+template <int N> __device__ __forceinline__ void reg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void reg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;

@@ -33,12 +33,18 @@ using namespace umma;
 constexpr int UM_ROWS = 128;
 constexpr int UM_KB = 32;                 // tf32 elements per K block (128 bytes)
 constexpr int UM_BLOCK_FLOATS = UM_ROWS * UM_KB;   // one A stage = 4096 floats = 16 KB
-constexpr int UM_THREADS = 288;           // 4 producer + 4 epilogue + 1 MMA warp
+constexpr int UM_PROD_WARPS = 8;
+constexpr int UM_PROD_THREADS = UM_PROD_WARPS * 32;
+constexpr int UM_EPI_WARP0 = UM_PROD_WARPS;          // epilogue warps 8..11 (warp % 4 = TMEM lane quadrant)
+constexpr int UM_MMA_WARP = UM_PROD_WARPS + 4;
+constexpr int UM_THREADS = (UM_PROD_WARPS + 5) * 32;  // 8 producer + 4 epilogue + 1 MMA warp = 416
+constexpr int UM_PREFETCH = 2;            // K blocks a producer thread keeps in flight ahead of the one it writes
 constexpr int UM_STAGE_LD = 36;           // padded row length of the epilogue staging tile
 constexpr int UM_ACC_STRIDE = 256;        // TMEM columns between the two accumulators
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_MAX_STAGES = 4;
 constexpr int UM_MAX_CHUNKS = 8;          // 32-column epilogue chunks (N_TILE <= 256)
+constexpr int UM_STAT_CHUNKS = 6;         // chunks that can carry column statistics (N_TILE <= 192)
 constexpr int UM_MAX_NTILE = 240;
 constexpr int UM_MAX_KC = 8;
 
@@ -82,12 +88,18 @@ __global__ void umma_weight_image_kernel(const float* __restrict__ W, int ldw, i
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// NOTE on fetch(): it must be nothing but loads into fresh registers.  Zero-initialising a Raw and
+// then conditionally loading into it makes ptxas protect the write-after-write with a scoreboard
+// wait, and with six scoreboard slots for a dozen loads that serialises every load of a K block
+// behind the previous one (seen in ncu as long_scoreboard stalls on CS2R).  So addresses are
+// clamped into bounds instead, and finish() masks what lies beyond K.
+
 struct AbsDiffU {
-    static constexpr bool kDouble = false;   // x is small and L2 resident; 16 loads in flight suffice
+    static constexpr bool kDouble = false;   // x is small and L2 resident; 8 loads in flight suffice
     const float* x;
     int ldx, F;
     PairGeom g;
-    int vec_ok;
+    int vec_ok;                              // rows 16-byte aligned and ldx >= roundup4(F)
     struct Row { const float* xi; const float* xj; };
     struct Raw { float4 a, b; };
     __device__ __forceinline__ void init(float*, int, int) const {}
@@ -96,21 +108,24 @@ struct AbsDiffU {
         return Row{x + (size_t)(p.b * g.N + p.i) * ldx, x + (size_t)(p.b * g.N + p.j) * ldx};
     }
     __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
-        o.a = make_float4(0.f, 0.f, 0.f, 0.f);
-        o.b = o.a;
-        if (k >= F) return;
-        if (vec_ok && k + 3 < F) {
-            o.a = ldg4(rw.xi + k);
-            o.b = ldg4(rw.xj + k);
-            return;
+        if (vec_ok) {
+            const int kk = min(k, ((F + 3) & ~3) - 4);
+            o.a = ldg4(rw.xi + kk);
+            o.b = ldg4(rw.xj + kk);
+        } else {
+            const int k0 = min(k, F - 1), k1 = min(k + 1, F - 1), k2 = min(k + 2, F - 1), k3 = min(k + 3, F - 1);
+            o.a = make_float4(__ldg(rw.xi + k0), __ldg(rw.xi + k1), __ldg(rw.xi + k2), __ldg(rw.xi + k3));
+            o.b = make_float4(__ldg(rw.xj + k0), __ldg(rw.xj + k1), __ldg(rw.xj + k2), __ldg(rw.xj + k3));
         }
-        o.a.x = __ldg(rw.xi + k); o.b.x = __ldg(rw.xj + k);
-        if (k + 1 < F) { o.a.y = __ldg(rw.xi + k + 1); o.b.y = __ldg(rw.xj + k + 1); }
-        if (k + 2 < F) { o.a.z = __ldg(rw.xi + k + 2); o.b.z = __ldg(rw.xj + k + 2); }
-        if (k + 3 < F) { o.a.w = __ldg(rw.xi + k + 3); o.b.w = __ldg(rw.xj + k + 3); }
     }
-    __device__ __forceinline__ float4 finish(const Raw& r, int, const float*) const {
-        return make_float4(fabsf(r.a.x - r.b.x), fabsf(r.a.y - r.b.y), fabsf(r.a.z - r.b.z), fabsf(r.a.w - r.b.w));
+    __device__ __forceinline__ float4 finish(const Raw& r, int k, const float*) const {
+        float4 v = make_float4(fabsf(r.a.x - r.b.x), fabsf(r.a.y - r.b.y), fabsf(r.a.z - r.b.z),
+                               fabsf(r.a.w - r.b.w));
+        if (k + 0 >= F) v.x = 0.f;
+        if (k + 1 >= F) v.y = 0.f;
+        if (k + 2 >= F) v.z = 0.f;
+        if (k + 3 >= F) v.w = 0.f;
+        return v;
     }
 };
 
@@ -135,9 +150,7 @@ struct BnActU {
         }
     }
     __device__ __forceinline__ Row row(int r) const { return Row{H + (size_t)r * C}; }
-    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
-        o.h = (k < C) ? ldg4(rw.h + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const { o.h = ldg4(rw.h + min(k, C - 4)); }
     __device__ __forceinline__ float4 finish(const Raw& r, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
         float4 sc = *reinterpret_cast<const float4*>(aux + k);
@@ -154,21 +167,27 @@ struct PlainU {
     static constexpr bool kDouble = true;
     const float* p;
     int ld, K;
-    int vec_ok;
+    int vec_ok;                              // rows 16-byte aligned and K % 4 == 0
     struct Row { const float* q; };
     struct Raw { float4 v; };
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ Row row(int r) const { return Row{p + (size_t)r * ld}; }
     __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
-        o.v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k >= K) return;
-        if (vec_ok && k + 3 < K) { o.v = ldg4(rw.q + k); return; }
-        o.v.x = __ldg(rw.q + k);
-        if (k + 1 < K) o.v.y = __ldg(rw.q + k + 1);
-        if (k + 2 < K) o.v.z = __ldg(rw.q + k + 2);
-        if (k + 3 < K) o.v.w = __ldg(rw.q + k + 3);
+        if (vec_ok) {
+            o.v = ldg4(rw.q + min(k, K - 4));
+        } else {
+            const int k0 = min(k, K - 1), k1 = min(k + 1, K - 1), k2 = min(k + 2, K - 1), k3 = min(k + 3, K - 1);
+            o.v = make_float4(__ldg(rw.q + k0), __ldg(rw.q + k1), __ldg(rw.q + k2), __ldg(rw.q + k3));
+        }
     }
-    __device__ __forceinline__ float4 finish(const Raw& r, int, const float*) const { return r.v; }
+    __device__ __forceinline__ float4 finish(const Raw& r, int k, const float*) const {
+        float4 v = r.v;
+        if (k + 0 >= K) v.x = 0.f;
+        if (k + 1 >= K) v.y = 0.f;
+        if (k + 2 >= K) v.z = 0.f;
+        if (k + 3 >= K) v.w = 0.f;
+        return v;
+    }
 };
 
 // ------------------------------------------------------------------ epilogue functors
@@ -301,7 +320,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
 
     if (tid == 0) {
         for (int i = 0; i < UM_MAX_STAGES; ++i) {
-            mbar_init(&full[i], 128);
+            mbar_init(&full[i], UM_PROD_THREADS);
             mbar_init(&empty[i], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -311,7 +330,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         mbar_init(wbar, 1);
         fence_mbar_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, UM_TMEM_COLS);
+    if (warp == UM_MMA_WARP) tmem_alloc(tmem_slot, UM_TMEM_COLS);
     aop.init(aux_a, tid, UM_THREADS);
     epi.init(aux_e, tid, UM_THREADS);
     for (int c = tid; c < 512; c += UM_THREADS) red0[c] = 0.f;   // red0 and red1 are contiguous
@@ -320,73 +339,74 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < UM_PROD_WARPS) {
         // ===================== producers =====================
-        // Thread t owns 16-byte column c16 = t%8 of rows q*16 + t/8 (q = 0..7) of every K block, so
+        // Thread t owns 16-byte column c16 = t%8 of rows q*32 + t/8 (q = 0..3) of every K block, so
         // its per-channel constants never change within a block and a warp's loads cover four
-        // full 128-byte row segments.  The fetch iterator runs one K block ahead of the write
-        // iterator (kDouble) so that global latency overlaps the transform + smem stores.
+        // full 128-byte row segments.  The fetch iterator runs UM_PREFETCH K blocks ahead of the
+        // write iterator so that global latency overlaps the transform + smem stores.
+        reg_dec<88>();   // 8 warps x 40 regs released ...
+        constexpr int RQ = UM_ROWS * 8 / UM_PROD_THREADS;      // rows per thread per K block (4)
+        constexpr int RSTEP = UM_PROD_THREADS / 8;              // 32
+        constexpr int NBUF = AOp::kDouble ? UM_PREFETCH + 1 : 1;
         const int rsub = tid >> 3, c16 = tid & 7;
         const int sw = rsub & 7;
         int st = 0;
         uint32_t ph = 0;
-        typename AOp::Row rc[8];
-        typename AOp::Raw cur[8], nxt[8];
-        uint32_t vcur = 0, vnxt = 0, vrows = 0;
+        typename AOp::Row rc[RQ];
+        typename AOp::Raw raw[NBUF][RQ];
+        uint32_t vmask[NBUF];
+        uint32_t vrows = 0;
         int f_tile = blockIdx.x, f_kc = 0;
         auto load_rows = [&](int tile) {
             vrows = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                int r = tile * UM_ROWS + q * 16 + rsub;
+            for (int q = 0; q < RQ; ++q) {
+                int r = tile * UM_ROWS + q * RSTEP + rsub;
                 bool ok = r < s.R;
                 vrows |= (ok ? 1u : 0u) << q;
-                rc[q] = aop.row(ok ? r : 0);
+                rc[q] = aop.row(ok ? r : 0);           // row 0 stands in for rows past the end
             }
         };
-        auto fetch = [&](typename AOp::Raw (&dst)[8], uint32_t& vmask, int kc) {
-            const int k = kc * UM_KB + c16 * 4;
-            vmask = vrows;
+        // issue the loads of the block the fetch iterator points at into raw[slot], then advance it
+        auto fetch_next = [&](typename AOp::Raw (&dst)[RQ], uint32_t& vm) {
+            if (f_tile >= ntiles) return;
+            if (f_kc == 0) load_rows(f_tile);
+            const int k = f_kc * UM_KB + c16 * 4;
+            vm = vrows;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) aop.fetch(rc[q], k, dst[q]);   // row 0 stands in for invalid rows
-        };
-        if (f_tile < ntiles) {
-            load_rows(f_tile);
-            fetch(cur, vcur, 0);
-        }
-        int w_tile = f_tile, w_kc = 0;
-        while (w_tile < ntiles) {
+            for (int q = 0; q < RQ; ++q) aop.fetch(rc[q], k, dst[q]);
             if (++f_kc == s.KC) { f_kc = 0; f_tile += gridDim.x; }
-            const bool more = f_tile < ntiles;
-            if (AOp::kDouble && more) {
-                if (f_kc == 0) load_rows(f_tile);
-                fetch(nxt, vnxt, f_kc);
-            }
+        };
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) fetch_next(raw[b], vmask[b]);
+        int w_tile = blockIdx.x, w_kc = 0;
+        while (w_tile < ntiles) {
             mbar_wait(&empty[st], ph ^ 1);
             float* dst = Asm + (size_t)st * UM_BLOCK_FLOATS;
             const int k = w_kc * UM_KB + c16 * 4;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int rl = q * 16 + rsub;
-                float4 v = aop.finish(cur[q], k, aux_a);
-                if (!((vcur >> q) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < RQ; ++q) {
+                const int rl = q * RSTEP + rsub;
+                float4 v = aop.finish(raw[0][q], k, aux_a);
+                if (!((vmask[0] >> q) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
                 v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                 *reinterpret_cast<float4*>(dst + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
             }
             fence_proxy_async_smem();
             mbar_arrive(&full[st]);
             if (++st == s.stages) { st = 0; ph ^= 1; }
-            if (AOp::kDouble) {
+            // rotate the in-flight buffers and refill the last one
 #pragma unroll
-                for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
-                vcur = vnxt;
-            } else if (more) {
-                if (f_kc == 0) load_rows(f_tile);
-                fetch(cur, vcur, f_kc);
+            for (int b = 0; b + 1 < NBUF; ++b) {
+#pragma unroll
+                for (int q = 0; q < RQ; ++q) raw[b][q] = raw[b + 1][q];
+                vmask[b] = vmask[b + 1];
             }
+            fetch_next(raw[NBUF - 1], vmask[NBUF - 1]);
             if (++w_kc == s.KC) { w_kc = 0; w_tile += gridDim.x; }
         }
-    } else if (warp == 8) {
+    } else if (warp == UM_MMA_WARP) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(wbar, w_bytes);
@@ -426,13 +446,14 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         __syncwarp();
     } else {
         // ===================== epilogue =====================
-        const int et = tid - 128;          // 0..127 = row of the tile this thread drains from TMEM
+        reg_inc<208>();  // ... cover the 4 epilogue warps x 80 (the pool is per CTA)
+        const int et = tid - UM_EPI_WARP0 * 32;   // 0..127 = row of the tile this thread drains from TMEM
         const int ew = warp & 3;           // TMEM lane window of this warp
         const int rsub = et >> 3, c4 = (et & 7) * 4;
         const int nchunks = (s.N_TILE + 31) / 32;
-        float s0[UM_MAX_CHUNKS][4], s1[UM_MAX_CHUNKS][4];
+        float s0[UM_STAT_CHUNKS][4], s1[UM_STAT_CHUNKS][4];
 #pragma unroll
-        for (int ch = 0; ch < UM_MAX_CHUNKS; ++ch)
+        for (int ch = 0; ch < UM_STAT_CHUNKS; ++ch)
 #pragma unroll
             for (int e = 0; e < 4; ++e) { s0[ch][e] = 0.f; s1[ch][e] = 0.f; }
         int it = 0;
@@ -463,7 +484,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int r = row0 + q * 16 + rsub;
-                            pre[q] = (r < s.R) ? epi.prefetch(r, col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            pre[q] = epi.prefetch(min(r, s.R - 1), col);   // pure load, clamped in bounds
                         }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -471,8 +492,8 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
                             const int r = row0 + rl;
                             if (r < s.R) {
                                 float4 a = *reinterpret_cast<const float4*>(stage + rl * UM_STAGE_LD + c4);
-                                epi.apply(r, Epi::kRowWeight ? wrow[rl] : 1.f, col, a, pre[q], nvalid, s0[ch],
-                                          s1[ch], aux_e);
+                                epi.apply(r, Epi::kRowWeight ? wrow[rl] : 1.f, col, a, pre[q], nvalid,
+                                          s0[ch < UM_STAT_CHUNKS ? ch : 0], s1[ch < UM_STAT_CHUNKS ? ch : 0], aux_e);
                             }
                         }
                     }
@@ -484,7 +505,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         }
         if (Epi::kStats) {
 #pragma unroll
-            for (int ch = 0; ch < UM_MAX_CHUNKS; ++ch) {
+            for (int ch = 0; ch < UM_STAT_CHUNKS; ++ch) {
                 if (ch < nchunks) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -504,7 +525,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == UM_MMA_WARP) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, UM_TMEM_COLS);
     }
@@ -528,6 +549,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
 constexpr int WG_ROWS = 32;                       // rows per K chunk
 constexpr int WG_BLOCK_FLOATS = WG_ROWS * UM_KB;  // [32 rows x 32 ch] = 1024 floats = 4 KB
 constexpr int WG_PROD_THREADS = 256;
+constexpr int WG_THREADS = WG_PROD_THREADS + 32;   // 8 producer warps (0-3 also drain TMEM at the end) + 1 MMA warp
 constexpr int WG_MAX_PB = 6;                      // Cout <= 192
 constexpr int WG_MAX_QB = 8;                      // Cin  <= 256
 
@@ -546,7 +568,7 @@ static inline size_t wgrad_smem_bytes(const WgradShape& s) {
 }
 
 template <class POp, class QOp>
-__global__ void __launch_bounds__(UM_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape s) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -577,8 +599,8 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, UM_TMEM_COLS);
-    pop.init(aux_p, tid, UM_THREADS);
-    qop.init(aux_q, tid, UM_THREADS);
+    pop.init(aux_p, tid, WG_THREADS);
+    qop.init(aux_q, tid, WG_THREADS);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -714,6 +736,13 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
 }
 
 // ------------------------------------------------------------------ host side
+static inline int plain_vec_ok(const float* p, int ld, int K) {
+    return (ld % 4 == 0 && K % 4 == 0 && K >= 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) ? 1 : 0;
+}
+static inline int absdiff_vec_ok(const float* x, int ldx, int F) {
+    return (ldx % 4 == 0 && ldx >= ((F + 3) & ~3) && F >= 4 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -826,7 +855,7 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
     MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<POp, QOp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     ProfScope ps(cat, st);
-    umma_wgrad_kernel<POp, QOp><<<cdiv(nchunks, s.chunks_per_cta), UM_THREADS, smem, st>>>(pop, qop, dW, ldw, s);
+    umma_wgrad_kernel<POp, QOp><<<cdiv(nchunks, s.chunks_per_cta), WG_THREADS, smem, st>>>(pop, qop, dW, ldw, s);
     MFT_CHECK_LAUNCH();
     return MFT_OK;
 }
@@ -834,8 +863,8 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
 // Test entry: dW[Cout, Cin] += P[R, Cout]^T Q[R, Cin] with plain operands.
 int umma_debug_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW, int ldw, int R, int Cout,
                      int Cin, cudaStream_t st) {
-    PlainU p{P, ldp, Cout, (ldp % 4 == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0) ? 1 : 0};
-    PlainU q{Q, ldq, Cin, (ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0) ? 1 : 0};
+    PlainU p{P, ldp, Cout, plain_vec_ok(P, ldp, Cout)};
+    PlainU q{Q, ldq, Cin, plain_vec_ok(Q, ldq, Cin)};
     return umma_wgrad(p, q, dW, ldw, R, Cout, Cin, st, PC_MISC);
 }
 
@@ -871,7 +900,7 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
         EpiFwdStatsU epi{L.H[k], L.C[k + 1], sums, g};
         int rc;
         if (k == 0) {
-            AbsDiffU a{x, ldx, F, g, (ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0};
+            AbsDiffU a{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
             rc = umma_rows_gemm(a, epi, p->conv_w[0], F, 0, g.R, L.C[1], F, L.wimg, st, PC_FWD_L1);
         } else {
             const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
@@ -940,7 +969,7 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
     const int Cout = L.C[k + 1], Cin = L.C[k];
     PlainU P{dh, Cout, Cout, 1};
     if (k == 0) {
-        AbsDiffU Q{x, ldx, F, g, (ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0};
+        AbsDiffU Q{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
         return umma_wgrad(P, Q, gr->conv_w[0], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1);
     }
     const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
@@ -952,7 +981,7 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
 // operands (tests/test_gpu_umma.py checks it against an fp32 product).
 int umma_debug_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w, float* C, int ldc, int M,
                     int N, int K, float* wimg, cudaStream_t st) {
-    PlainU a{A, lda, K, (lda % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) ? 1 : 0};
+    PlainU a{A, lda, K, plain_vec_ok(A, lda, K)};
     EpiStoreU e{C, ldc, (ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0};
     return umma_rows_gemm(a, e, W, ldw, transpose_w, M, N, K, wimg, st, PC_MISC);
 }

@@ -49,6 +49,7 @@ static int require_sm100() {
 }  // namespace mft
 
 using namespace mft;
+namespace mft { extern long long* g_umma_dbg; }
 
 #define MFT_ENTER()                         \
     do {                                    \
@@ -159,6 +160,13 @@ int mft_debug_umma_wgrad(const float* P, int ldp, const float* Q, int ldq, float
     MFT_ENTER();
     MFT_REQUIRE(P && Q && dW, "mft_debug_umma_wgrad: null pointer");
     return umma_debug_wgrad(P, ldp, Q, ldq, dW, ldw, R, Cout, Cin, (cudaStream_t)stream);
+}
+
+/* Debug: have every following tcgen05 rows-GEMM launch write a per-CTA clock64 timeline
+ * ([grid][16] long long) into `buf` (device memory), or stop when buf == NULL. */
+int mft_debug_set_timeline(void* buf) {
+    g_umma_dbg = static_cast<long long*>(buf);
+    return MFT_OK;
 }
 
 }  // extern "C"

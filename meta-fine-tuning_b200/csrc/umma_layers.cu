@@ -56,6 +56,7 @@ struct UmmaShape {
     int K;        // valid K
     int KC;       // K blocks (ceil(K/32))
     int stages;   // A ring depth
+    long long* dbg;   // optional [gridDim.x][16] clock64 timeline (debug builds of the tests only)
 };
 
 static inline size_t umma_smem_bytes(const UmmaShape& s) {
@@ -320,12 +321,12 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
 
     if (tid == 0) {
         for (int i = 0; i < UM_MAX_STAGES; ++i) {
-            mbar_init(&full[i], UM_PROD_THREADS);
+            mbar_init(&full[i], UM_PROD_WARPS);     // one elected arrival per producer warp
             mbar_init(&empty[i], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 128);
+            mbar_init(&tempty[a], 4);               // one per epilogue warp
         }
         mbar_init(wbar, 1);
         fence_mbar_init();
@@ -338,6 +339,9 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    long long* dbg = s.dbg ? s.dbg + (size_t)blockIdx.x * 16 : nullptr;
+#define MFT_MARK(slot) do { if (dbg && lane == 0) dbg[slot] = clock64(); } while (0)
+    if (dbg && tid == 0) dbg[0] = clock64();
 
     if (warp < UM_PROD_WARPS) {
         // ===================== producers =====================
@@ -381,31 +385,43 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
 #pragma unroll
         for (int b = 0; b < NBUF; ++b) fetch_next(raw[b], vmask[b]);
         int w_tile = blockIdx.x, w_kc = 0;
-        while (w_tile < ntiles) {
+        // One step = write the K block held in buffer b, then refill b with the block NBUF ahead.
+        // Buffers are addressed statically (the loop is unrolled NBUF times): copying a register
+        // that an in-flight load still targets would wait for that load and flatten the pipeline.
+        auto step = [&](typename AOp::Raw (&buf)[RQ], uint32_t& vm) -> bool {
+            if (w_tile >= ntiles) return false;
             mbar_wait(&empty[st], ph ^ 1);
             float* dst = Asm + (size_t)st * UM_BLOCK_FLOATS;
             const int k = w_kc * UM_KB + c16 * 4;
 #pragma unroll
             for (int q = 0; q < RQ; ++q) {
                 const int rl = q * RSTEP + rsub;
-                float4 v = aop.finish(raw[0][q], k, aux_a);
-                if (!((vmask[0] >> q) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 v = aop.finish(buf[q], k, aux_a);
+                if (!((vm >> q) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
                 v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                 *reinterpret_cast<float4*>(dst + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
             }
             fence_proxy_async_smem();
-            mbar_arrive(&full[st]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st]);
             if (++st == s.stages) { st = 0; ph ^= 1; }
-            // rotate the in-flight buffers and refill the last one
-#pragma unroll
-            for (int b = 0; b + 1 < NBUF; ++b) {
-#pragma unroll
-                for (int q = 0; q < RQ; ++q) raw[b][q] = raw[b + 1][q];
-                vmask[b] = vmask[b + 1];
+            fetch_next(buf, vm);
+            if (++w_kc == s.KC) {
+                w_kc = 0;
+                if (warp == 0 && w_tile == (int)blockIdx.x) MFT_MARK(2);   // first tile written
+                w_tile += gridDim.x;
             }
-            fetch_next(raw[NBUF - 1], vmask[NBUF - 1]);
-            if (++w_kc == s.KC) { w_kc = 0; w_tile += gridDim.x; }
+            return true;
+        };
+        for (;;) {
+            bool go = true;
+#pragma unroll
+            for (int b = 0; b < NBUF; ++b) {
+                if (go) go = step(raw[b], vmask[b]);
+            }
+            if (!go) break;
         }
+        if (warp == 0) MFT_MARK(3);                                        // producers done
     } else if (warp == UM_MMA_WARP) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
@@ -415,6 +431,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
                 bulk_g2s(reinterpret_cast<uint8_t*>(Wsm) + (size_t)kc * blk,
                          reinterpret_cast<const uint8_t*>(wimg) + (size_t)kc * blk, blk, wbar);
             mbar_wait(wbar, 0);
+            MFT_MARK(1);                                                   // weights resident
             const uint32_t idesc = make_idesc_tf32(UM_ROWS, s.N_TILE);
             const int ksteps = (s.K + 7) / 8;
             const uint32_t a0 = smem_u32(Asm), b0 = smem_u32(Wsm);
@@ -441,15 +458,21 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
                     if (++st == s.stages) { st = 0; ph ^= 1; }
                 }
                 mma_commit(&tfull[acc]);
+                if (it == 0) MFT_MARK(4);                                  // first tile issued
             }
+            MFT_MARK(5);                                                   // all MMAs issued
         }
         __syncwarp();
     } else {
         // ===================== epilogue =====================
         reg_inc<208>();  // ... cover the 4 epilogue warps x 80 (the pool is per CTA)
-        const int et = tid - UM_EPI_WARP0 * 32;   // 0..127 = row of the tile this thread drains from TMEM
-        const int ew = warp & 3;           // TMEM lane window of this warp
-        const int rsub = et >> 3, c4 = (et & 7) * 4;
+        // Warp w drains TMEM lanes 32w..32w+31 = rows 32w.. of the tile and owns a private
+        // [32][36] staging slab: TMEM -> registers (one row per lane) -> slab -> registers in
+        // (row = i*4 + lane/8, 16-byte column = lane%8) order, so that every global access is four
+        // full 128-byte row segments per instruction.  Only __syncwarp is needed.
+        const int ew = warp & 3;
+        float* slab = stage + ew * 32 * UM_STAGE_LD;
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
         const int nchunks = (s.N_TILE + 31) / 32;
         float s0[UM_STAT_CHUNKS][4], s1[UM_STAT_CHUNKS][4];
 #pragma unroll
@@ -460,49 +483,59 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int row0 = tile * UM_ROWS;
-            if (Epi::kRowWeight) wrow[et] = (row0 + et < s.R) ? epi.row_weight(row0 + et) : 0.f;
+            const int row0 = tile * UM_ROWS + ew * 32;        // first row of this warp's slab
+            float wq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = row0 + q * 4 + rsub;
+                wq[q] = (Epi::kRowWeight && r < s.R) ? epi.row_weight(r) : 0.f;
+            }
             mbar_wait(&tfull[acc], aph);
             tc_fence_after_sync();
+            if (warp == UM_EPI_WARP0 && it == 0) MFT_MARK(12);             // first accumulator ready
 #pragma unroll
             for (int ch = 0; ch < UM_MAX_CHUNKS; ++ch) {
                 if (ch < nchunks) {
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * UM_ACC_STRIDE + ch * 32, v);
+                    const int cl = ch * 32 + c4;          // column inside this pass
+                    const int col = s.n0 + cl;            // global output column
+                    const bool live = cl < s.N_TILE && col < s.N;
+                    float4 pre[8];
+                    if (live) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)       // pure loads, row clamped in bounds
+                            pre[q] = epi.prefetch(min(row0 + q * 4 + rsub, s.R - 1), col);
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4*>(stage + et * UM_STAGE_LD + q * 4) =
+                        *reinterpret_cast<float4*>(slab + lane * UM_STAGE_LD + q * 4) =
                             make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                    named_bar_sync(1, 128);
-                    const int cl = ch * 32 + c4;          // column inside this pass
-                    const int col = s.n0 + cl;            // global output column
-                    if (cl < s.N_TILE && col < s.N) {
+                    __syncwarp();
+                    if (live) {
                         const int nvalid = min(4, s.N - col);
-                        float4 pre[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const int r = row0 + q * 16 + rsub;
-                            pre[q] = epi.prefetch(min(r, s.R - 1), col);   // pure load, clamped in bounds
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int rl = q * 16 + rsub;
+                            const int rl = q * 4 + rsub;
                             const int r = row0 + rl;
                             if (r < s.R) {
-                                float4 a = *reinterpret_cast<const float4*>(stage + rl * UM_STAGE_LD + c4);
-                                epi.apply(r, Epi::kRowWeight ? wrow[rl] : 1.f, col, a, pre[q], nvalid,
-                                          s0[ch < UM_STAT_CHUNKS ? ch : 0], s1[ch < UM_STAT_CHUNKS ? ch : 0], aux_e);
+                                float4 a = *reinterpret_cast<const float4*>(slab + rl * UM_STAGE_LD + c4);
+                                epi.apply(r, wq[q], col, a, pre[q], nvalid, s0[ch < UM_STAT_CHUNKS ? ch : 0],
+                                          s1[ch < UM_STAT_CHUNKS ? ch : 0], aux_e);
                             }
                         }
                     }
-                    named_bar_sync(1, 128);
+                    __syncwarp();
                 }
             }
             tc_fence_before_sync();
-            mbar_arrive(&tempty[acc]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (warp == UM_EPI_WARP0 && it < 4) MFT_MARK(8 + it);          // epilogue finished tile `it`
         }
+        if (warp == UM_EPI_WARP0) MFT_MARK(6);                             // epilogue tiles done
         if (Epi::kStats) {
 #pragma unroll
             for (int ch = 0; ch < UM_STAT_CHUNKS; ++ch) {
@@ -518,11 +551,13 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
                 }
             }
             named_bar_sync(1, 128);
-            for (int cl = et; cl < s.N_TILE; cl += 128)
+            for (int cl = tid - UM_EPI_WARP0 * 32; cl < s.N_TILE; cl += 128)
                 if (s.n0 + cl < s.N) epi.commit(s.n0 + cl, red0[cl], red1[cl], aux_e);
         }
     }
 
+    if (warp == UM_EPI_WARP0) MFT_MARK(7);                                 // statistics committed
+#undef MFT_MARK
     tc_fence_before_sync();
     __syncthreads();
     if (warp == UM_MMA_WARP) {
@@ -743,6 +778,7 @@ static inline int absdiff_vec_ok(const float* x, int ldx, int F) {
     return (ldx % 4 == 0 && ldx >= ((F + 3) & ~3) && F >= 4 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
 }
 
+long long* g_umma_dbg = nullptr;   // set by mft_debug_set_timeline()
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -806,7 +842,7 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
     for (int p = 0; p < passes; ++p) {
         UmmaShape s{};
         plan_pass(nts[p], K, s);
-        s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K;
+        s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.dbg = g_umma_dbg;
         float* img = wimg + (size_t)p * s.N_TILE * s.KC * UM_KB;
         {
             ProfScope ps(PC_PREP, st);

@@ -149,6 +149,65 @@ def test_full_size_5w20s_forward_and_properties():
     assert torch.allclose(adj_p, adj[:, perm][:, :, perm], atol=2e-6)
 
 
+# ------------------------------------------------------------------------------------------
+# tcgen05 TF32 path.  north_star: logits within rel 1e-3 of the reference.  Gradients: TF32
+# rounding moves every pre-activation by ~1e-3 relative, so LeakyReLU slope flips are the rule,
+# not the exception; SURVEY.md 7.4 measured 1e-2 (dx) / 3e-2 median, 6.5e-2 worst (parameters) for
+# a TF32-emulated run of the reference itself.  Asserted: finite, and <= 0.15 per tensor.
+# ------------------------------------------------------------------------------------------
+OUT_TOL_TF32 = 1e-3
+GRAD_TOL_TF32 = 0.15
+
+
+@pytest.mark.parametrize("name,fin,nf,n_way", [("gnn_tiny.npz", 13, 16, 3), ("gnn_5w5s.npz", 133, 96, 5)])
+def test_golden_tf32(golden_dir, name, fin, nf, n_way):
+    rec, params = _golden(golden_dir, name)
+    out, dx, grads = U.run_cuda_gnn(rec["x"], params, rec["proj"], fin, nf, n_way, "tf32", True)
+    assert U.rel(out, rec["out64"]) < OUT_TOL_TF32
+    assert U.rel(dx, rec["dx64"]) < GRAD_TOL_TF32
+    for k in params:
+        g = grads[k].reshape(rec["g." + k].shape)
+        assert np.isfinite(g).all(), k
+        if U.is_zero_grad(k):
+            assert np.abs(g).max() <= 1e-6, k
+        else:
+            assert U.rel(g, rec["g." + k]) < GRAD_TOL_TF32, (k, U.rel(g, rec["g." + k]))
+
+
+@pytest.mark.parametrize("bsz,n,seed", [(16, 30, 3), (15, 105, 4), (6, 130, 5)])
+def test_seeded_vs_oracle_tf32_logits(bsz, n, seed):
+    """Forward parity of the tensor-core path at the three head sizes (5-shot, 20-shot, compressed
+    50-shot node counts), F = 133/181/229 exercising the K-tail and N-pass-split code paths."""
+    import mft_b200
+    fin, nf, n_way = 133, 96, 5
+    p64 = O.random_params(fin, nf, n_way, seed, torch.float64)
+    params = {k: v.float().numpy() for k, v in p64.items()}
+    g = torch.Generator().manual_seed(77 + seed)
+    x = torch.randn(bsz, n, fin, generator=g)
+    with torch.no_grad():
+        out_t = O.gnn_nl(x.double(), {k: torch.as_tensor(v).double() for k, v in params.items()}).numpy()
+    mft_b200.set_precision("tf32")
+    net = U.load_params_into(mft_b200.GNN_nl(fin, nf, n_way), params).cuda()
+    with torch.no_grad():
+        out = net(x.cuda())
+    mft_b200.set_precision("auto")
+    assert U.rel(out.double().cpu().numpy(), out_t) < OUT_TOL_TF32
+
+
+def test_tf32_and_fp32_paths_agree_on_gradients_direction():
+    """The two arithmetic paths share every kernel but the GEMMs; their gradients must point the
+    same way (cosine > 0.98 per large tensor) even where slope flips blur the relative error."""
+    rec, params = _golden(os.path.join(os.path.dirname(__file__), "golden"), "gnn_5w5s.npz")
+    a = U.run_cuda_gnn(rec["x"], params, rec["proj"], 133, 96, 5, "fp32", True)
+    b = U.run_cuda_gnn(rec["x"], params, rec["proj"], 133, 96, 5, "tf32", True)
+    for k in params:
+        if U.is_zero_grad(k) or a[2][k].size < 1000:
+            continue
+        u, v = a[2][k].ravel(), b[2][k].ravel()
+        cos = float(u @ v / (np.linalg.norm(u) * np.linalg.norm(v)))
+        assert cos > 0.98, (k, cos)
+
+
 def test_non_cuda_input_raises():
     import mft_b200
     net = mft_b200.GNN_nl(13, 16, 3)

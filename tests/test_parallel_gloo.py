@@ -1,0 +1,70 @@
+"""world_size-2 gloo tests (CPU) of the episode-parallel host logic: gradient averaging equals
+the single-process gradient of the mean loss over the same episodes, episode ownership, and the
+final gather of per-episode results.  The per-episode compute here is the CPU oracle (tests may
+use it); on the GPU box the same helpers wrap the CUDA modules under NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mft_b200 import parallel
+from oracle import gnn_oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _episode(seed, fin=9, n=5, bsz=2, n_way=3):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(bsz, n, fin, generator=g), torch.randn(bsz, n, n_way, generator=g)
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    p = {k: v.clone().requires_grad_(True) for k, v in O.random_params(9, 8, 3, 0, torch.float64).items()}
+    x, proj = _episode(100 + rank)                         # one episode per rank per step
+    loss = (O.gnn_nl(x.double(), p) * proj.double()).sum()
+    loss.backward()
+    params = [torch.nn.Parameter(v.detach()) for v in p.values()]
+    for prm, v in zip(params, p.values()):
+        prm.grad = v.grad.clone()
+    n = parallel.allreduce_mean_grads(params, world)
+    owned = parallel.owned_episodes(7, rank, world)
+    res = parallel.gather_episode_results([float(e) * 10 for e in owned], 7, rank, world)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "r0.npz"), n=n, res=res.numpy(),
+                 **{f"g{i}": prm.grad.numpy() for i, prm in enumerate(params)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_gradients_equal_single_process_mean(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(str(tmp_path), "r0.npz"))
+    p = {k: v.clone().requires_grad_(True) for k, v in O.random_params(9, 8, 3, 0, torch.float64).items()}
+    total = 0
+    for rank in range(world):
+        x, proj = _episode(100 + rank)
+        total = total + (O.gnn_nl(x.double(), p) * proj.double()).sum()
+    (total / world).backward()
+    assert int(got["n"]) == sum(v.numel() for v in p.values())
+    for i, v in enumerate(p.values()):
+        assert np.allclose(got[f"g{i}"], v.grad.numpy(), rtol=1e-10, atol=1e-12)
+    assert np.array_equal(got["res"], np.arange(7) * 10.0)
+
+
+def test_episode_ownership_partitions_everything():
+    for world in (1, 2, 4, 8):
+        seen = sorted(e for r in range(world) for e in parallel.owned_episodes(600, r, world))
+        assert seen == list(range(600))
+        assert all(parallel.owner_of(e, world) == e % world for e in range(0, 600, 37))

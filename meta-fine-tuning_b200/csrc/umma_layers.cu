@@ -57,6 +57,7 @@ struct UmmaShape {
     int KC;       // K blocks (ceil(K/32))
     int stages;   // A ring depth
     long long* dbg;   // optional [gridDim.x][16] clock64 timeline (debug builds of the tests only)
+    int reverse;      // walk the row tiles from the last to the first (see next_direction())
 };
 
 static inline size_t umma_smem_bytes(const UmmaShape& s) {
@@ -96,7 +97,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // clamped into bounds instead, and finish() masks what lies beyond K.
 
 struct AbsDiffU {
-    static constexpr bool kDouble = false;   // x is small and L2 resident; 8 loads in flight suffice
+    static constexpr int kAhead = 0;         // x is small and L2 resident; 8 loads in flight suffice
     const float* x;
     int ldx, F;
     PairGeom g;
@@ -119,7 +120,7 @@ struct AbsDiffU {
             o.b = make_float4(__ldg(rw.xj + k0), __ldg(rw.xj + k1), __ldg(rw.xj + k2), __ldg(rw.xj + k3));
         }
     }
-    __device__ __forceinline__ float4 finish(const Raw& r, int k, const float*) const {
+    __device__ __forceinline__ float4 finish(const Raw& r, const Row&, int k, const float*) const {
         float4 v = make_float4(fabsf(r.a.x - r.b.x), fabsf(r.a.y - r.b.y), fabsf(r.a.z - r.b.z),
                                fabsf(r.a.w - r.b.w));
         if (k + 0 >= F) v.x = 0.f;
@@ -132,7 +133,7 @@ struct AbsDiffU {
 
 // a = LeakyReLU(scale*h + shift), scale = gamma*rstd, shift = beta - mean*scale (C % 4 == 0)
 struct BnActU {
-    static constexpr bool kDouble = true;
+    static constexpr int kAhead = 2;
     const float* H;
     int C;
     const double* sums;
@@ -152,7 +153,7 @@ struct BnActU {
     }
     __device__ __forceinline__ Row row(int r) const { return Row{H + (size_t)r * C}; }
     __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const { o.h = ldg4(rw.h + min(k, C - 4)); }
-    __device__ __forceinline__ float4 finish(const Raw& r, int k, const float* aux) const {
+    __device__ __forceinline__ float4 finish(const Raw& r, const Row&, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
         float4 sc = *reinterpret_cast<const float4*>(aux + k);
         float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
@@ -165,7 +166,7 @@ struct BnActU {
 };
 
 struct PlainU {
-    static constexpr bool kDouble = true;
+    static constexpr int kAhead = 2;
     const float* p;
     int ld, K;
     int vec_ok;                              // rows 16-byte aligned and K % 4 == 0
@@ -181,13 +182,56 @@ struct PlainU {
             o.v = make_float4(__ldg(rw.q + k0), __ldg(rw.q + k1), __ldg(rw.q + k2), __ldg(rw.q + k3));
         }
     }
-    __device__ __forceinline__ float4 finish(const Raw& r, int k, const float*) const {
+    __device__ __forceinline__ float4 finish(const Raw& r, const Row&, int k, const float*) const {
         float4 v = r.v;
         if (k + 0 >= K) v.x = 0.f;
         if (k + 1 >= K) v.y = 0.f;
         if (k + 2 >= K) v.z = 0.f;
         if (k + 3 >= K) v.w = 0.f;
         return v;
+    }
+};
+
+// dH = gamma*rstd*(dy - w*m1 - w*hhat*m2): BatchNorm backward of the twin-summed gradient, fused
+// into the operand build so that dH never exists in HBM.  With P = gamma*rstd, S = P*rstd*m2,
+// Q = P*m1 - S*mean this is  dH = P*dy - w*(Q + S*h)  (C % 4 == 0).
+struct DhU {
+    static constexpr int kAhead = 1;
+    const float* dy;
+    const float* H;
+    int C;
+    const double* fsums;
+    const float* gamma;
+    const double* bsums;
+    double inv_count;
+    PairGeom g;
+    struct Row { int off; float w; };
+    struct Raw { float4 d, h; };
+    __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
+        for (int c = tid; c < C; c += nthreads) {
+            float m, r;
+            bn_mean_rstd(fsums, C, c, inv_count, m, r);
+            float P = gamma[c] * r;
+            float S = P * r * (float)(bsums[C + c] * inv_count);
+            aux[c] = P;
+            aux[kMaxC + c] = P * (float)(bsums[c] * inv_count) - S * m;
+            aux[2 * kMaxC + c] = S;
+        }
+    }
+    __device__ __forceinline__ Row row(int r) const { return Row{r * C, decode_row(r, g).w}; }
+    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
+        const int kk = min(k, C - 4);
+        o.d = ldg4(dy + (size_t)rw.off + kk);
+        o.h = ldg4(H + (size_t)rw.off + kk);
+    }
+    __device__ __forceinline__ float4 finish(const Raw& r, const Row& rw, int k, const float* aux) const {
+        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 P = *reinterpret_cast<const float4*>(aux + k);
+        float4 Q = *reinterpret_cast<const float4*>(aux + kMaxC + k);
+        float4 S = *reinterpret_cast<const float4*>(aux + 2 * kMaxC + k);
+        const float nw = -rw.w;
+        return make_float4(fmaf(nw, fmaf(S.x, r.h.x, Q.x), P.x * r.d.x), fmaf(nw, fmaf(S.y, r.h.y, Q.y), P.y * r.d.y),
+                           fmaf(nw, fmaf(S.z, r.h.z, Q.z), P.z * r.d.z), fmaf(nw, fmaf(S.w, r.h.w, Q.w), P.w * r.d.w));
     }
 };
 
@@ -318,6 +362,9 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int ntiles = (s.R + UM_ROWS - 1) / UM_ROWS;
+    // physical row tile of logical tile t: consecutive launches alternate direction so that a
+    // kernel starts on the rows its predecessor touched last (still L2 resident)
+    auto phys = [&](int t) { return s.reverse ? ntiles - 1 - t : t; };
 
     if (tid == 0) {
         for (int i = 0; i < UM_MAX_STAGES; ++i) {
@@ -349,16 +396,17 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         // its per-channel constants never change within a block and a warp's loads cover four
         // full 128-byte row segments.  The fetch iterator runs UM_PREFETCH K blocks ahead of the
         // write iterator so that global latency overlaps the transform + smem stores.
-        reg_dec<88>();   // 8 warps x 40 regs released ...
+        reg_dec<96>();   // 8 warps x 32 regs released ...
         constexpr int RQ = UM_ROWS * 8 / UM_PROD_THREADS;      // rows per thread per K block (4)
         constexpr int RSTEP = UM_PROD_THREADS / 8;              // 32
-        constexpr int NBUF = AOp::kDouble ? UM_PREFETCH + 1 : 1;
+        constexpr int NBUF = AOp::kAhead + 1;
         const int rsub = tid >> 3, c16 = tid & 7;
         const int sw = rsub & 7;
         int st = 0;
         uint32_t ph = 0;
-        typename AOp::Row rc[RQ];
+        typename AOp::Row rc[RQ];               // rows of the tile the fetch iterator is in
         typename AOp::Raw raw[NBUF][RQ];
+        typename AOp::Row rrow[NBUF][RQ];       // rows each in-flight buffer belongs to
         uint32_t vmask[NBUF];
         uint32_t vrows = 0;
         int f_tile = blockIdx.x, f_kc = 0;
@@ -366,29 +414,32 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
             vrows = 0;
 #pragma unroll
             for (int q = 0; q < RQ; ++q) {
-                int r = tile * UM_ROWS + q * RSTEP + rsub;
+                int r = phys(tile) * UM_ROWS + q * RSTEP + rsub;
                 bool ok = r < s.R;
                 vrows |= (ok ? 1u : 0u) << q;
                 rc[q] = aop.row(ok ? r : 0);           // row 0 stands in for rows past the end
             }
         };
         // issue the loads of the block the fetch iterator points at into raw[slot], then advance it
-        auto fetch_next = [&](typename AOp::Raw (&dst)[RQ], uint32_t& vm) {
+        auto fetch_next = [&](typename AOp::Raw (&dst)[RQ], typename AOp::Row (&drow)[RQ], uint32_t& vm) {
             if (f_tile >= ntiles) return;
             if (f_kc == 0) load_rows(f_tile);
             const int k = f_kc * UM_KB + c16 * 4;
             vm = vrows;
 #pragma unroll
-            for (int q = 0; q < RQ; ++q) aop.fetch(rc[q], k, dst[q]);
+            for (int q = 0; q < RQ; ++q) {
+                aop.fetch(rc[q], k, dst[q]);
+                drow[q] = rc[q];
+            }
             if (++f_kc == s.KC) { f_kc = 0; f_tile += gridDim.x; }
         };
 #pragma unroll
-        for (int b = 0; b < NBUF; ++b) fetch_next(raw[b], vmask[b]);
+        for (int b = 0; b < NBUF; ++b) fetch_next(raw[b], rrow[b], vmask[b]);
         int w_tile = blockIdx.x, w_kc = 0;
         // One step = write the K block held in buffer b, then refill b with the block NBUF ahead.
         // Buffers are addressed statically (the loop is unrolled NBUF times): copying a register
         // that an in-flight load still targets would wait for that load and flatten the pipeline.
-        auto step = [&](typename AOp::Raw (&buf)[RQ], uint32_t& vm) -> bool {
+        auto step = [&](typename AOp::Raw (&buf)[RQ], typename AOp::Row (&brow)[RQ], uint32_t& vm) -> bool {
             if (w_tile >= ntiles) return false;
             mbar_wait(&empty[st], ph ^ 1);
             float* dst = Asm + (size_t)st * UM_BLOCK_FLOATS;
@@ -396,7 +447,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
 #pragma unroll
             for (int q = 0; q < RQ; ++q) {
                 const int rl = q * RSTEP + rsub;
-                float4 v = aop.finish(buf[q], k, aux_a);
+                float4 v = aop.finish(buf[q], brow[q], k, aux_a);
                 if (!((vm >> q) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
                 v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                 *reinterpret_cast<float4*>(dst + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
@@ -405,7 +456,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[st]);
             if (++st == s.stages) { st = 0; ph ^= 1; }
-            fetch_next(buf, vm);
+            fetch_next(buf, brow, vm);
             if (++w_kc == s.KC) {
                 w_kc = 0;
                 if (warp == 0 && w_tile == (int)blockIdx.x) MFT_MARK(2);   // first tile written
@@ -417,7 +468,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
             bool go = true;
 #pragma unroll
             for (int b = 0; b < NBUF; ++b) {
-                if (go) go = step(raw[b], vmask[b]);
+                if (go) go = step(raw[b], rrow[b], vmask[b]);
             }
             if (!go) break;
         }
@@ -465,7 +516,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         __syncwarp();
     } else {
         // ===================== epilogue =====================
-        reg_inc<208>();  // ... cover the 4 epilogue warps x 80 (the pool is per CTA)
+        reg_inc<192>();  // ... cover the 4 epilogue warps x 64 (the pool is per CTA)
         // Warp w drains TMEM lanes 32w..32w+31 = rows 32w.. of the tile and owns a private
         // [32][36] staging slab: TMEM -> registers (one row per lane) -> slab -> registers in
         // (row = i*4 + lane/8, 16-byte column = lane%8) order, so that every global access is four
@@ -483,7 +534,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int row0 = tile * UM_ROWS + ew * 32;        // first row of this warp's slab
+            const int row0 = phys(tile) * UM_ROWS + ew * 32;  // first row of this warp's slab
             float wq[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -595,6 +646,7 @@ struct WgradShape {
     int N_TILE;        // MMA N = roundup16(Cin)
     int stages;
     int chunks_per_cta;
+    int reverse;
 };
 
 static inline size_t wgrad_smem_bytes(const WgradShape& s) {
@@ -621,13 +673,16 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int nchunks_total = (s.R + WG_ROWS - 1) / WG_ROWS;
-    const int c_begin = blockIdx.x * s.chunks_per_cta;
+    // CTA b owns a contiguous chunk range; with `reverse` the ranges are handed out from the end so
+    // that the kernel starts on the rows the previous launch touched last (L2 residency)
+    const int owner = s.reverse ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    const int c_begin = owner * s.chunks_per_cta;
     const int c_end = min(nchunks_total, c_begin + s.chunks_per_cta);
     const int my_chunks = max(0, c_end - c_begin);
 
     if (tid == 0) {
         for (int i = 0; i < UM_MAX_STAGES; ++i) {
-            mbar_init(&full[i], WG_PROD_THREADS);
+            mbar_init(&full[i], WG_PROD_THREADS / 32);   // one elected arrival per producer warp
             mbar_init(&empty[i], 1);
         }
         mbar_init(done, 1);
@@ -652,19 +707,31 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
         typename POp::Raw praw[WG_MAX_PB];
         typename QOp::Raw qraw[WG_MAX_QB];
         bool ok = false;
-        auto fetch = [&](int chunk) {
+        typename POp::Row pr;
+        typename QOp::Row qr;
+        // Q operands with kAhead == 0 (|x_i - x_j| from the small L2-resident node matrix) are
+        // fetched and consumed inside the step, after the P blocks have been stored, so that their
+        // registers do not add to P's in-flight set.
+        constexpr bool kLateQ = (QOp::kAhead == 0);
+        auto fetch_p = [&](int chunk) {
             const int r = chunk * WG_ROWS + rl;
             ok = r < s.R;
-            typename POp::Row pr = pop.row(ok ? r : 0);
-            typename QOp::Row qr = qop.row(ok ? r : 0);
+            pr = pop.row(ok ? r : 0);
 #pragma unroll
             for (int b = 0; b < WG_MAX_PB; ++b)
                 if (b < s.PB) pop.fetch(pr, b * UM_KB + c16 * 4, praw[b]);
+        };
+        auto fetch_q = [&](int chunk) {
+            const int r = chunk * WG_ROWS + rl;
+            qr = qop.row(r < s.R ? r : 0);
 #pragma unroll
             for (int b = 0; b < WG_MAX_QB; ++b)
                 if (b < s.QB) qop.fetch(qr, b * UM_KB + c16 * 4, qraw[b]);
         };
-        if (my_chunks > 0) fetch(c_begin);
+        if (my_chunks > 0) {
+            fetch_p(c_begin);
+            if (!kLateQ) fetch_q(c_begin);
+        }
         for (int c = c_begin; c < c_end; ++c) {
             mbar_wait(&empty[st], ph ^ 1);
             float* dst = ring + (size_t)st * stage_floats + off;
@@ -672,23 +739,28 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
 #pragma unroll
             for (int b = 0; b < WG_MAX_PB; ++b) {
                 if (b < s.PB) {
-                    float4 v = ok ? pop.finish(praw[b], b * UM_KB + c16 * 4, aux_p) : zero;
+                    float4 v = ok ? pop.finish(praw[b], pr, b * UM_KB + c16 * 4, aux_p) : zero;
                     v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                     *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
                 }
             }
+            if (kLateQ) fetch_q(c);
 #pragma unroll
             for (int b = 0; b < WG_MAX_QB; ++b) {
                 if (b < s.QB) {
-                    float4 v = ok ? qop.finish(qraw[b], b * UM_KB + c16 * 4, aux_q) : zero;
+                    float4 v = ok ? qop.finish(qraw[b], qr, b * UM_KB + c16 * 4, aux_q) : zero;
                     v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                     *reinterpret_cast<float4*>(dst + (s.PB + b) * WG_BLOCK_FLOATS) = v;
                 }
             }
             fence_proxy_async_smem();
-            mbar_arrive(&full[st]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[st]);
             if (++st == s.stages) { st = 0; ph ^= 1; }
-            if (c + 1 < c_end) fetch(c + 1);
+            if (c + 1 < c_end) {
+                fetch_p(c + 1);
+                if (!kLateQ) fetch_q(c + 1);
+            }
         }
     } else {
         // ===================== MMA issuer
@@ -779,6 +851,11 @@ static inline int absdiff_vec_ok(const float* x, int ldx, int F) {
 }
 
 long long* g_umma_dbg = nullptr;   // set by mft_debug_set_timeline()
+
+// Serpentine schedule: every pair-row kernel of the tensor-core path flips the direction in which
+// it walks the rows, so the tail of what one launch wrote is the head of what the next one reads.
+static int g_direction = 0;
+static int next_direction() { return (g_direction ^= 1); }
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -840,9 +917,10 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
     const int ntiles = cdiv(R, UM_ROWS);
     const int grid = min(ntiles, num_sms());
     for (int p = 0; p < passes; ++p) {
+        const int dir = next_direction();
         UmmaShape s{};
         plan_pass(nts[p], K, s);
-        s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.dbg = g_umma_dbg;
+        s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.dbg = g_umma_dbg; s.reverse = dir;
         float* img = wimg + (size_t)p * s.N_TILE * s.KC * UM_KB;
         {
             ProfScope ps(PC_PREP, st);
@@ -887,6 +965,7 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
     const int nchunks = cdiv(R, WG_ROWS);
     const int grid = min(nchunks, num_sms());
     s.chunks_per_cta = cdiv(nchunks, grid);
+    s.reverse = next_direction();
     size_t smem = wgrad_smem_bytes(s);
     MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<POp, QOp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
@@ -981,7 +1060,8 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
                             const PairGeom& g, cudaStream_t st) {
     (void)gr; (void)nf;
     const int Cout = L.C[k + 1], Cin = L.C[k];
-    PlainU a{dh, Cout, Cout, 1};
+    DhU a{dh, L.H[k], Cout, L.fsums + (size_t)k * 2 * kMaxC, p->bn_g[k], L.bsums + (size_t)k * 2 * kMaxC,
+          g.inv_pairs, g};
     if (k == 0) {
         const int ldd = (F + 3) & ~3;
         EpiStoreU e{L.dD, ldd, 1};
@@ -1003,7 +1083,8 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
                               const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                               const PairGeom& g, cudaStream_t st) {
     const int Cout = L.C[k + 1], Cin = L.C[k];
-    PlainU P{dh, Cout, Cout, 1};
+    DhU P{dh, L.H[k], Cout, L.fsums + (size_t)k * 2 * kMaxC, p->bn_g[k], L.bsums + (size_t)k * 2 * kMaxC,
+          g.inv_pairs, g};
     if (k == 0) {
         AbsDiffU Q{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
         return umma_wgrad(P, Q, gr->conv_w[0], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1);

@@ -505,7 +505,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         const int Cout = L.C[k + 1], Cin = L.C[k];
         const double* fs = L.fsums + (size_t)k * 2 * kMaxC;
         const double* bs = L.bsums + (size_t)k * 2 * kMaxC;
-        {
+        if (precision != MFT_PREC_TF32) {   // the tensor-core path applies BN-backward inside its operand producers
             ProfScope ps(PC_DH, st);
             dh_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(cur, L.H[k], Cout, fs, p->bn_g[k], bs, g);
             MFT_CHECK_LAUNCH();

@@ -178,8 +178,8 @@ size_t mft_debug_umma_gemm_workspace_bytes(int N, int K);
 int mft_debug_umma_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w,
                         float* C, int ldc, int M, int N, int K, void* workspace, void* stream);
 /* dW[Cout,Cin] += P[R,Cout]^T * Q[R,Cin] on the tensor-core wgrad kernel (Cout <= 192, Cin <= 256). */
-/* Per-CTA clock64 timeline of the following rows-GEMM launches into buf [grid][16] (NULL = off). */
-int mft_debug_set_timeline(void* buf);
+/* Per-CTA clock64 timeline of ONE rows-GEMM launch, the (skip+1)-th from now, into buf [grid][16]. */
+int mft_debug_set_timeline(void* buf, int skip);
 int mft_debug_umma_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW, int ldw,
                          int R, int Cout, int Cin, void* stream);
 

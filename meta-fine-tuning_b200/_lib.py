@@ -74,7 +74,7 @@ SIGNATURES = {
     "mft_debug_umma_gemm_workspace_bytes": (_sz, [_i, _i]),
     "mft_debug_umma_gemm": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mft_debug_umma_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
-    "mft_debug_set_timeline": (_i, [_vp]),
+    "mft_debug_set_timeline": (_i, [_vp, _i]),
     "mft_launch_count": (C.c_ulonglong, []),
     "mft_prof_enable": (_i, [_i]),
     "mft_prof_categories": (_i, []),

@@ -49,7 +49,7 @@ static int require_sm100() {
 }  // namespace mft
 
 using namespace mft;
-namespace mft { extern long long* g_umma_dbg; }
+namespace mft { extern long long* g_umma_dbg; extern int g_umma_dbg_skip; }
 
 #define MFT_ENTER()                         \
     do {                                    \
@@ -163,9 +163,10 @@ int mft_debug_umma_wgrad(const float* P, int ldp, const float* Q, int ldq, float
 }
 
 /* Debug: have every following tcgen05 rows-GEMM launch write a per-CTA clock64 timeline
- * ([grid][16] long long) into `buf` (device memory), or stop when buf == NULL. */
-int mft_debug_set_timeline(void* buf) {
+ * ([grid][16] long long) into `buf` (device memory) for ONE launch: the (skip+1)-th from now. */
+int mft_debug_set_timeline(void* buf, int skip) {
     g_umma_dbg = static_cast<long long*>(buf);
+    g_umma_dbg_skip = skip;
     return MFT_OK;
 }
 

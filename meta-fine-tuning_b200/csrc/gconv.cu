@@ -74,8 +74,8 @@ gconv_combine_kernel(const float* __restrict__ adj, const float* __restrict__ UV
             float v0 = 0.f, v1 = 0.f;
 #pragma unroll
             for (int q = 0; q < kGcRows; ++q) { v0 += red[0][q][c]; v1 += red[1][q][c]; }
-            atomicAdd(sums + c, (double)v0);
-            atomicAdd(sums + n_out + c, (double)v1);
+            stat_add(sums, n_out, c, 0, v0);
+            stat_add(sums, n_out, c, 1, v1);
         }
     }
 }
@@ -138,8 +138,8 @@ gconv_dz_kernel(const float* __restrict__ d_out, int ldo, const float* __restric
             float v0 = 0.f, v1 = 0.f;
 #pragma unroll
             for (int q = 0; q < kGcRows; ++q) { v0 += red[0][q][c]; v1 += red[1][q][c]; }
-            atomicAdd(bsums + c, (double)v0);
-            atomicAdd(bsums + n_out + c, (double)v1);
+            stat_add(bsums, n_out, c, 0, v0);
+            stat_add(bsums, n_out, c, 1, v1);
         }
     }
 }
@@ -151,8 +151,8 @@ __global__ void gconv_dy_kernel(float* __restrict__ dY, const float* __restrict_
     __shared__ float m1[kMaxC], m2[kMaxC];
     bn_smem_fill(bn_smem_at(aux), fsums, gamma, nullptr, n_out, 1.0 / (double)rows);
     for (int c = threadIdx.x; c < n_out; c += blockDim.x) {
-        m1[c] = (float)(bsums[c] / (double)rows);
-        m2[c] = (float)(bsums[n_out + c] / (double)rows);
+        m1[c] = (float)(stat_get(bsums, n_out, c, 0) / (double)rows);
+        m2[c] = (float)(stat_get(bsums, n_out, c, 1) / (double)rows);
     }
     __syncthreads();
     BnSmem s = bn_smem_at(aux);
@@ -169,11 +169,11 @@ __global__ void gconv_small_grads_kernel(const double* bsums, int n_out, int has
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_out) return;
     if (has_bn) {
-        if (bn_b) bn_b[c] = (float)bsums[c];
-        if (bn_g) bn_g[c] = (float)bsums[n_out + c];
+        if (bn_b) bn_b[c] = (float)stat_get(bsums, n_out, c, 0);
+        if (bn_g) bn_g[c] = (float)stat_get(bsums, n_out, c, 1);
         if (fc_b) fc_b[c] = 0.f;                   // BatchNorm1d removes the mean: exactly zero
     } else if (fc_b) {
-        fc_b[c] = (float)bsums[c];
+        fc_b[c] = (float)stat_get(bsums, n_out, c, 0);
     }
 }
 
@@ -194,14 +194,14 @@ GcLayout gc_layout(int B, int N, int F, int n_out, void* saved, void* workspace)
     size_t rows = (size_t)B * N;
     Carver sv(saved);
     L.Y = sv.take<float>(rows * n_out);
-    L.fsums = sv.take<double>(2 * kMaxC);
+    L.fsums = sv.take<double>(kStatSlot);
     L.saved_bytes = sv.used();
     Carver ws(workspace);
     L.UV = ws.take<float>(rows * 2 * n_out);
     L.dY = ws.take<float>(rows * n_out);
     L.AX = ws.take<float>(rows * F);
     L.DU = ws.take<float>(rows * 2 * F);
-    L.bsums = ws.take<double>(2 * kMaxC);
+    L.bsums = ws.take<double>(kStatSlot);
     L.workspace_bytes = ws.used();
     return L;
 }
@@ -224,7 +224,7 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
 
     dim3 blk(kGcCols, kGcRows);
     if (has_bn) {
-        MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 2 * kMaxC, st));
+        MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * kStatSlot, st));
         { ProfScope ps(PC_GCONV_FWD, st); gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, L.Y, n_out,
                                                                    L.fsums);
         MFT_CHECK_LAUNCH(); }
@@ -249,7 +249,7 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     const int rows = B * N;
     const int has_bn = p->bn_g != nullptr;
 
-    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 2 * kMaxC, st));
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * kStatSlot, st));
     MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)n_out * 2 * F, st));
     dim3 blk(kGcCols, kGcRows);
     { ProfScope ps(PC_GCONV_BWD, st); gconv_dz_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(d_out, ldo, L.Y, rows, n_out, L.fsums, p->bn_g, p->bn_b,

@@ -158,6 +158,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
+// ------------------------------------------------------------------ TMA (tensor map) 2-D tile load
+// Box {inner = c0.., outer = c1..} of the mapped row-major matrix -> shared memory, swizzled as the
+// tensor map says; completes `bytes of the box` on the mbarrier.  tmap: address of a CUtensorMap in
+// kernel-parameter (__grid_constant__) or global memory.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 // Register re-balancing between warp roles (all warps of a warpgroup execute it).
 template <int N> __device__ __forceinline__ void reg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));

@@ -20,6 +20,7 @@
 // Pipelines: full/empty mbarriers per A stage (producers <-> MMA), tmem_full/tmem_empty per
 // accumulator (MMA <-> epilogue).  Every wait is bounded (umma::mbar_wait traps on timeout).
 #include <cstdio>
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
 #include "common.cuh"
 #include "wcompute.cuh"
@@ -37,7 +38,8 @@ constexpr int UM_PROD_WARPS = 8;
 constexpr int UM_PROD_THREADS = UM_PROD_WARPS * 32;
 constexpr int UM_EPI_WARP0 = UM_PROD_WARPS;          // epilogue warps 8..11 (warp % 4 = TMEM lane quadrant)
 constexpr int UM_MMA_WARP = UM_PROD_WARPS + 4;
-constexpr int UM_THREADS = (UM_PROD_WARPS + 5) * 32;  // 8 producer + 4 epilogue + 1 MMA warp = 416
+constexpr int UM_TMA_WARP = UM_MMA_WARP + 1;           // issues the tensor-map tile loads of kTma operands
+constexpr int UM_THREADS = (UM_PROD_WARPS + 6) * 32;  // 8 producer + 4 epilogue + MMA + TMA warp = 448
 constexpr int UM_PREFETCH = 2;            // K blocks a producer thread keeps in flight ahead of the one it writes
 constexpr int UM_STAGE_LD = 36;           // padded row length of the epilogue staging tile
 constexpr int UM_ACC_STRIDE = 256;        // TMEM columns between the two accumulators
@@ -62,7 +64,7 @@ struct UmmaShape {
 
 static inline size_t umma_smem_bytes(const UmmaShape& s) {
     return 1024 + (size_t)s.KC * s.N_TILE * 128 + (size_t)s.stages * UM_BLOCK_FLOATS * 4 +
-           (size_t)UM_ROWS * UM_STAGE_LD * 4 + (3 + 4) * kMaxC * 4 + UM_ROWS * 4 + 2 * 256 * 4 + 16 * 8 + 16;
+           (size_t)UM_ROWS * UM_STAGE_LD * 4 + (3 + 4) * kMaxC * 4 + UM_ROWS * 4 + 2 * 256 * 4 + 20 * 8 + 16;
 }
 
 // ------------------------------------------------------------------ weight image
@@ -97,6 +99,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // clamped into bounds instead, and finish() masks what lies beyond K.
 
 struct AbsDiffU {
+    static constexpr bool kTma = false;
     static constexpr int kAhead = 0;         // x is small and L2 resident; 8 loads in flight suffice
     const float* x;
     int ldx, F;
@@ -133,6 +136,7 @@ struct AbsDiffU {
 
 // a = LeakyReLU(scale*h + shift), scale = gamma*rstd, shift = beta - mean*scale (C % 4 == 0)
 struct BnActU {
+    static constexpr bool kTma = false;
     static constexpr int kAhead = 2;
     const float* H;
     int C;
@@ -166,6 +170,7 @@ struct BnActU {
 };
 
 struct PlainU {
+    static constexpr bool kTma = false;
     static constexpr int kAhead = 2;
     const float* p;
     int ld, K;
@@ -196,6 +201,7 @@ struct PlainU {
 // into the operand build so that dH never exists in HBM.  With P = gamma*rstd, S = P*rstd*m2,
 // Q = P*m1 - S*mean this is  dH = P*dy - w*(Q + S*h)  (C % 4 == 0).
 struct DhU {
+    static constexpr bool kTma = false;
     static constexpr int kAhead = 1;
     const float* dy;
     const float* H;
@@ -212,9 +218,9 @@ struct DhU {
             float m, r;
             bn_mean_rstd(fsums, C, c, inv_count, m, r);
             float P = gamma[c] * r;
-            float S = P * r * (float)(bsums[C + c] * inv_count);
+            float S = P * r * (float)(stat_get(bsums, C, c, 1) * inv_count);
             aux[c] = P;
-            aux[kMaxC + c] = P * (float)(bsums[c] * inv_count) - S * m;
+            aux[kMaxC + c] = P * (float)(stat_get(bsums, C, c, 0) * inv_count) - S * m;
             aux[2 * kMaxC + c] = S;
         }
     }
@@ -235,11 +241,54 @@ struct DhU {
     }
 };
 
+// Tensor-map variant of BnActU for the rows kernel: the raw [128 rows x 32 ch] block of H lands in
+// the ring stage by TMA, already in the K-major SWIZZLE_128B arrangement the MMA wants (the TMA and
+// UMMA 128-byte swizzles are the same function), and the producer warps apply BN + LeakyReLU + TF32
+// rounding IN PLACE.  No register staging, no scoreboard-limited prefetch: every free stage has a
+// 16 KB load in flight.
+struct BnActT {
+    static constexpr bool kTma = true;
+    static constexpr int kAhead = 0;
+    alignas(64) CUtensorMap tmap;
+    int C;
+    const double* sums;
+    const float* gamma;
+    const float* beta;
+    double inv_count;
+    struct Row { int dummy; };
+    struct Raw { int dummy; };
+    __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
+        for (int c = tid; c < C; c += nthreads) {
+            float m, r;
+            bn_mean_rstd(sums, C, c, inv_count, m, r);
+            float sc = gamma[c] * r;
+            aux[c] = sc;
+            aux[kMaxC + c] = beta[c] - m * sc;
+        }
+    }
+    __device__ __forceinline__ Row row(int) const { return Row{0}; }
+    __device__ __forceinline__ void fetch(const Row&, int, Raw&) const {}
+    __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ float4 transform(float4 h, int k, const float* aux) const {
+        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 sc = *reinterpret_cast<const float4*>(aux + k);
+        float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
+        float4 y;
+        y.x = fmaf(h.x, sc.x, sh.x); y.y = fmaf(h.y, sc.y, sh.y);
+        y.z = fmaf(h.z, sc.z, sh.z); y.w = fmaf(h.w, sc.w, sh.w);
+        return make_float4(fmaxf(y.x, kSlope * y.x), fmaxf(y.y, kSlope * y.y), fmaxf(y.z, kSlope * y.z),
+                           fmaxf(y.w, kSlope * y.w));
+    }
+};
+
 // ------------------------------------------------------------------ epilogue functors
 // apply(): four consecutive output columns col..col+3 (col % 4 == 0) of global row r;
 // nvalid = how many of them exist.  s0/s1: the thread's running column statistics.
 
 struct EpiStoreU {
+    static constexpr bool kPrefetch = false;
     static constexpr bool kStats = false;
     static constexpr bool kRowWeight = false;
     float* out;
@@ -265,6 +314,7 @@ struct EpiStoreU {
 
 // forward: store pre-BN H, accumulate sum w*h and sum w*h^2 (C % 4 == 0)
 struct EpiFwdStatsU {
+    static constexpr bool kPrefetch = false;
     static constexpr bool kStats = true;
     static constexpr bool kRowWeight = true;
     float* H;
@@ -283,14 +333,15 @@ struct EpiFwdStatsU {
         s0[3] = fmaf(w, v.w, s0[3]); s1[3] = fmaf(w * v.w, v.w, s1[3]);
     }
     __device__ __forceinline__ void commit(int c, float v0, float v1, const float*) const {
-        atomicAdd(sums + c, (double)v0);
-        atomicAdd(sums + C + c, (double)v1);
+        stat_add(sums, C, c, 0, v0);
+        stat_add(sums, C, c, 1, v1);
     }
 };
 
 // dgrad: acc = dL/d a_{k-1}; dy = acc * lrelu'(BN(H_{k-1})), stored; reductions sum dy and
 // sum dy*hhat (accumulated as sum dy*h and corrected per CTA: hhat = (h - mean) * rstd)
 struct EpiDyU {
+    static constexpr bool kPrefetch = true;    // needs H_{k-1}(r, col): loaded one chunk ahead
     static constexpr bool kStats = true;
     static constexpr bool kRowWeight = false;
     const float* H;
@@ -331,15 +382,16 @@ struct EpiDyU {
     }
     __device__ __forceinline__ void commit(int c, float v0, float v1, const float* aux) const {
         float m = aux[2 * kMaxC + c], r = aux[3 * kMaxC + c];
-        atomicAdd(bsums + c, (double)v0);
-        atomicAdd(bsums + C + c, (double)(r * (v1 - m * v0)));
+        stat_add(bsums, C, c, 0, v0);
+        stat_add(bsums, C, c, 1, r * (v1 - m * v0));
     }
 };
 
 // ------------------------------------------------------------------ the kernel
 template <class AOp, class Epi>
 __global__ void __launch_bounds__(UM_THREADS, 1)
-umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) {
+umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi epi, const float* __restrict__ wimg,
+                 const __grid_constant__ UmmaShape s) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t w_bytes = (uint32_t)s.KC * s.N_TILE * 128;
@@ -357,7 +409,8 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
     uint64_t* tfull = bars + 8;     // [2]
     uint64_t* tempty = bars + 10;   // [2]
     uint64_t* wbar = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* rawfull = bars + 13;  // [UM_MAX_STAGES]  (TMA operands: raw block landed)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -370,6 +423,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         for (int i = 0; i < UM_MAX_STAGES; ++i) {
             mbar_init(&full[i], UM_PROD_WARPS);     // one elected arrival per producer warp
             mbar_init(&empty[i], 1);
+            mbar_init(&rawfull[i], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
@@ -399,6 +453,35 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         reg_dec<96>();   // 8 warps x 32 regs released ...
         constexpr int RQ = UM_ROWS * 8 / UM_PROD_THREADS;      // rows per thread per K block (4)
         constexpr int RSTEP = UM_PROD_THREADS / 8;              // 32
+        if constexpr (AOp::kTma) {
+            // in-place transform of the block the TMA warp landed in ring stage `st`
+            const int rsub = tid >> 3, c16 = tid & 7;
+            const int sw = rsub & 7;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int row0 = phys(tile) * UM_ROWS;
+                for (int kc = 0; kc < s.KC; ++kc) {
+                    mbar_wait(&rawfull[st], ph);
+                    float* blk = Asm + (size_t)st * UM_BLOCK_FLOATS;
+                    const int k = kc * UM_KB + c16 * 4;
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q) {
+                        const int rl = q * RSTEP + rsub;
+                        float4* ptr = reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2));
+                        float4 v = aop.transform(*ptr, k, aux_a);
+                        if (row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                        *ptr = v;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[st]);
+                    if (++st == s.stages) { st = 0; ph ^= 1; }
+                }
+                if (warp == 0 && tile == (int)blockIdx.x) MFT_MARK(2);
+            }
+        } else {
         constexpr int NBUF = AOp::kAhead + 1;
         const int rsub = tid >> 3, c16 = tid & 7;
         const int sw = rsub & 7;
@@ -472,6 +555,7 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
             }
             if (!go) break;
         }
+        }   // !kTma
         if (warp == 0) MFT_MARK(3);                                        // producers done
     } else if (warp == UM_MMA_WARP) {
         // ===================== MMA issuer (one thread) =====================
@@ -514,6 +598,25 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
             MFT_MARK(5);                                                   // all MMAs issued
         }
         __syncwarp();
+    } else if (warp == UM_TMA_WARP) {
+        // ===================== TMA loader (one thread; kTma operands only) =====================
+        if constexpr (AOp::kTma) {
+            if (lane == 0) {
+                tma_prefetch_desc(&aop.tmap);
+                int st = 0;
+                uint32_t ph = 0;
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                    const int row0 = phys(tile) * UM_ROWS;
+                    for (int kc = 0; kc < s.KC; ++kc) {
+                        mbar_wait(&empty[st], ph ^ 1);
+                        mbar_arrive_expect_tx(&rawfull[st], UM_BLOCK_FLOATS * 4);
+                        tma_load_2d(Asm + (size_t)st * UM_BLOCK_FLOATS, &aop.tmap, kc * UM_KB, row0, &rawfull[st]);
+                        if (++st == s.stages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
     } else {
         // ===================== epilogue =====================
         reg_inc<192>();  // ... cover the 4 epilogue warps x 64 (the pool is per CTA)
@@ -544,20 +647,25 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
             mbar_wait(&tfull[acc], aph);
             tc_fence_after_sync();
             if (warp == UM_EPI_WARP0 && it == 0) MFT_MARK(12);             // first accumulator ready
+            // Software pipeline over the 32-column chunks: the TMEM load of chunk ch+1 (and, for
+            // epilogues that need a global operand, its loads) are issued as soon as chunk ch has
+            // been copied to the slab, so they are in flight while chunk ch is written out.
+            const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * UM_ACC_STRIDE;
+            uint32_t v[32];
+            float4 pre[Epi::kPrefetch ? 2 : 1][8];
+            auto chunk_live = [&](int ch) { return ch * 32 + c4 < s.N_TILE && s.n0 + ch * 32 + c4 < s.N; };
+            auto load_pre = [&](int ch, float4 (&dst)[8]) {
+                if (Epi::kPrefetch && chunk_live(ch)) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)       // pure loads, row clamped in bounds
+                        dst[q] = epi.prefetch(min(row0 + q * 4 + rsub, s.R - 1), s.n0 + ch * 32 + c4);
+                }
+            };
+            tmem_ld_32x32(tbase, v);
+            load_pre(0, pre[0]);
 #pragma unroll
             for (int ch = 0; ch < UM_MAX_CHUNKS; ++ch) {
                 if (ch < nchunks) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * UM_ACC_STRIDE + ch * 32, v);
-                    const int cl = ch * 32 + c4;          // column inside this pass
-                    const int col = s.n0 + cl;            // global output column
-                    const bool live = cl < s.N_TILE && col < s.N;
-                    float4 pre[8];
-                    if (live) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)       // pure loads, row clamped in bounds
-                            pre[q] = epi.prefetch(min(row0 + q * 4 + rsub, s.R - 1), col);
-                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
@@ -565,7 +673,13 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
                             make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
                     __syncwarp();
-                    if (live) {
+                    if (ch + 1 < nchunks) {
+                        tmem_ld_32x32(tbase + (ch + 1) * 32, v);
+                        load_pre(ch + 1, pre[Epi::kPrefetch ? ((ch + 1) & 1) : 0]);
+                    }
+                    const int cl = ch * 32 + c4;          // column inside this pass
+                    const int col = s.n0 + cl;            // global output column
+                    if (cl < s.N_TILE && col < s.N) {
                         const int nvalid = min(4, s.N - col);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -573,8 +687,8 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
                             const int r = row0 + rl;
                             if (r < s.R) {
                                 float4 a = *reinterpret_cast<const float4*>(slab + rl * UM_STAGE_LD + c4);
-                                epi.apply(r, wq[q], col, a, pre[q], nvalid, s0[ch < UM_STAT_CHUNKS ? ch : 0],
-                                          s1[ch < UM_STAT_CHUNKS ? ch : 0], aux_e);
+                                epi.apply(r, wq[q], col, a, pre[Epi::kPrefetch ? (ch & 1) : 0][q], nvalid,
+                                          s0[ch < UM_STAT_CHUNKS ? ch : 0], s1[ch < UM_STAT_CHUNKS ? ch : 0], aux_e);
                             }
                         }
                     }
@@ -588,22 +702,34 @@ umma_rows_kernel(AOp aop, Epi epi, const float* __restrict__ wimg, UmmaShape s) 
         }
         if (warp == UM_EPI_WARP0) MFT_MARK(6);                             // epilogue tiles done
         if (Epi::kStats) {
+            // lanes sharing a column (lane, lane^8, lane^16, lane^24) combine by shuffle; each warp then
+            // owns one row of the [4][256] partials (red0/red1 alias the idle slab) -- no smem atomics
+            float* part0 = stage;                       // [4][256]
+            float* part1 = stage + 4 * 256;             // [4][256]
+            named_bar_sync(1, 128);                     // every epilogue warp is done with its slab
 #pragma unroll
             for (int ch = 0; ch < UM_STAT_CHUNKS; ++ch) {
                 if (ch < nchunks) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        int cl = ch * 32 + c4 + e;
-                        if (cl < 256) {
-                            atomicAdd(&red0[cl], s0[ch][e]);
-                            atomicAdd(&red1[cl], s1[ch][e]);
+                        float a0 = s0[ch][e], a1 = s1[ch][e];
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+                        const int cl = ch * 32 + c4 + e;
+                        if (lane < 8 && cl < 256) {
+                            part0[ew * 256 + cl] = a0;
+                            part1[ew * 256 + cl] = a1;
                         }
                     }
                 }
             }
             named_bar_sync(1, 128);
             for (int cl = tid - UM_EPI_WARP0 * 32; cl < s.N_TILE; cl += 128)
-                if (s.n0 + cl < s.N) epi.commit(s.n0 + cl, red0[cl], red1[cl], aux_e);
+                if (s.n0 + cl < s.N)
+                    epi.commit(s.n0 + cl, part0[cl] + part0[256 + cl] + part0[512 + cl] + part0[768 + cl],
+                               part1[cl] + part1[256 + cl] + part1[512 + cl] + part1[768 + cl], aux_e);
         }
     }
 
@@ -843,6 +969,44 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
 }
 
 // ------------------------------------------------------------------ host side
+// ---- tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Row-major fp32 matrix [rows, cols] with leading dimension ld (elements): boxes of box_cols x box_rows.
+static int make_tmap_2d(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_cols, int box_rows,
+                        CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) {
+        set_error(MFT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        return MFT_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error(MFT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+        return MFT_ERR_CUDA;
+    }
+    return MFT_OK;
+}
+
 static inline int plain_vec_ok(const float* p, int ld, int K) {
     return (ld % 4 == 0 && K % 4 == 0 && K >= 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) ? 1 : 0;
 }
@@ -851,6 +1015,7 @@ static inline int absdiff_vec_ok(const float* x, int ldx, int F) {
 }
 
 long long* g_umma_dbg = nullptr;   // set by mft_debug_set_timeline()
+int g_umma_dbg_skip = 0;           // rows-kernel launches to let pass before recording one
 
 // Serpentine schedule: every pair-row kernel of the tensor-core path flips the direction in which
 // it walks the rows, so the tail of what one launch wrote is the head of what the next one reads.
@@ -920,7 +1085,9 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
         const int dir = next_direction();
         UmmaShape s{};
         plan_pass(nts[p], K, s);
-        s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.dbg = g_umma_dbg; s.reverse = dir;
+        s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.reverse = dir;
+        s.dbg = nullptr;
+        if (g_umma_dbg && g_umma_dbg_skip-- == 0) { s.dbg = g_umma_dbg; g_umma_dbg = nullptr; }
         float* img = wimg + (size_t)p * s.N_TILE * s.KC * UM_KB;
         {
             ProfScope ps(PC_PREP, st);
@@ -1011,15 +1178,18 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
         return MFT_ERR_UNSUPPORTED;
     }
     for (int k = 0; k < 4; ++k) {
-        double* sums = L.fsums + (size_t)k * 2 * kMaxC;
+        double* sums = L.fsums + (size_t)k * kStatSlot;
         EpiFwdStatsU epi{L.H[k], L.C[k + 1], sums, g};
         int rc;
         if (k == 0) {
             AbsDiffU a{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
             rc = umma_rows_gemm(a, epi, p->conv_w[0], F, 0, g.R, L.C[1], F, L.wimg, st, PC_FWD_L1);
         } else {
-            const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
-            BnActU a{L.H[k - 1], L.C[k], ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
+            const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
+            BnActT a{};
+            rc = make_tmap_2d(&a.tmap, L.H[k - 1], g.R, L.C[k], L.C[k], UM_KB, UM_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc != MFT_OK) return rc;
+            a.C = L.C[k]; a.sums = ps; a.gamma = p->bn_g[k - 1]; a.beta = p->bn_b[k - 1]; a.inv_count = g.inv_pairs;
             rc = umma_rows_gemm(a, epi, p->conv_w[k], L.C[k], 0, g.R, L.C[k + 1], L.C[k], L.wimg, st,
                                 PC_FWD_L1 + k);
         }
@@ -1060,7 +1230,7 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
                             const PairGeom& g, cudaStream_t st) {
     (void)gr; (void)nf;
     const int Cout = L.C[k + 1], Cin = L.C[k];
-    DhU a{dh, L.H[k], Cout, L.fsums + (size_t)k * 2 * kMaxC, p->bn_g[k], L.bsums + (size_t)k * 2 * kMaxC,
+    DhU a{dh, L.H[k], Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
           g.inv_pairs, g};
     if (k == 0) {
         const int ldd = (F + 3) & ~3;
@@ -1072,8 +1242,8 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
         MFT_CHECK_LAUNCH();
         return MFT_OK;
     }
-    const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
-    double* pbs = L.bsums + (size_t)(k - 1) * 2 * kMaxC;
+    const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
+    double* pbs = L.bsums + (size_t)(k - 1) * kStatSlot;
     EpiDyU e{L.H[k - 1], dy_next, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
     return umma_rows_gemm(a, e, p->conv_w[k], Cin, 1, g.R, Cin, Cout, L.wimg, st, PC_DGRAD_L1 + k);
 }
@@ -1083,13 +1253,13 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
                               const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                               const PairGeom& g, cudaStream_t st) {
     const int Cout = L.C[k + 1], Cin = L.C[k];
-    DhU P{dh, L.H[k], Cout, L.fsums + (size_t)k * 2 * kMaxC, p->bn_g[k], L.bsums + (size_t)k * 2 * kMaxC,
+    DhU P{dh, L.H[k], Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
           g.inv_pairs, g};
     if (k == 0) {
         AbsDiffU Q{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
         return umma_wgrad(P, Q, gr->conv_w[0], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1);
     }
-    const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+    const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
     BnActU Q{L.H[k - 1], Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
     return umma_wgrad(P, Q, gr->conv_w[k], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1 + k);
 }

@@ -103,8 +103,8 @@ struct EpiFwdStats {
         }
     }
     __device__ __forceinline__ void commit(int c, float v0, float v1) const {
-        atomicAdd(sums + c, (double)v0);
-        atomicAdd(sums + C + c, (double)v1);
+        stat_add(sums, C, c, 0, v0);
+        stat_add(sums, C, c, 1, v1);
     }
 };
 
@@ -145,8 +145,8 @@ struct EpiDy {
         }
     }
     __device__ __forceinline__ void commit(int c, float v0, float v1) const {
-        atomicAdd(bsums + c, (double)v0);
-        atomicAdd(bsums + C + c, (double)v1);
+        stat_add(bsums, C, c, 0, v0);
+        stat_add(bsums, C, c, 1, v1);
     }
 };
 
@@ -338,9 +338,9 @@ dy4_kernel(const float* __restrict__ dS, const float* __restrict__ H4, int C, co
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
 #pragma unroll
         for (int w = 0; w < kRowWarps; ++w) { v0 += red[0][w][c]; v1 += red[1][w][c]; v2 += red[2][w][c]; }
-        atomicAdd(bsums + c, (double)v0);
-        atomicAdd(bsums + C + c, (double)v1);
-        atomicAdd(lastsum + c, (double)v2);
+        stat_add(bsums, C, c, 0, v0);
+        stat_add(bsums, C, c, 1, v1);
+        stat_add(lastsum, C, c, 0, v2);
     }
 }
 
@@ -353,8 +353,8 @@ dh_kernel(float* __restrict__ dy, const float* __restrict__ H, int C, const doub
     __shared__ float m1[kMaxC], m2[kMaxC];
     bn_smem_fill(bn_smem_at(aux), fsums, gamma, nullptr, C, g.inv_pairs);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        m1[c] = (float)(bsums[c] * g.inv_pairs);
-        m2[c] = (float)(bsums[C + c] * g.inv_pairs);
+        m1[c] = (float)(stat_get(bsums, C, c, 0) * g.inv_pairs);
+        m2[c] = (float)(stat_get(bsums, C, c, 1) * g.inv_pairs);
     }
     __syncthreads();
     BnSmem s = bn_smem_at(aux);
@@ -386,12 +386,12 @@ __global__ void finalize_grads_kernel(FinalizeArgs a) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     for (int k = 0; k < 4; ++k) {
         if (t < a.C[k]) {
-            if (a.bn_b[k]) a.bn_b[k][t] = (float)a.bsums[k][t];
-            if (a.bn_g[k]) a.bn_g[k][t] = (float)a.bsums[k][a.C[k] + t];
+            if (a.bn_b[k]) a.bn_b[k][t] = (float)stat_get(a.bsums[k], a.C[k], t, 0);
+            if (a.bn_g[k]) a.bn_g[k][t] = (float)stat_get(a.bsums[k], a.C[k], t, 1);
             if (a.conv_b[k]) a.conv_b[k][t] = 0.f;   // BN removes the mean: exactly zero
         }
     }
-    if (t < a.nf && a.last_w) a.last_w[t] = (float)a.lastsum[t];
+    if (t < a.nf && a.last_w) a.last_w[t] = (float)stat_get(a.lastsum, a.nf, t, 0);
     if (t == 0 && a.last_b) a.last_b[0] = 0.f;         // softmax shift invariance: exactly zero
 }
 
@@ -406,14 +406,14 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     size_t R = (size_t)B * Rg;
     Carver sv(saved);
     for (int k = 0; k < 4; ++k) L.H[k] = sv.take<float>(R * L.C[k + 1]);
-    L.fsums = sv.take<double>(4 * 2 * kMaxC);
+    L.fsums = sv.take<double>(4 * kStatSlot);
     L.saved_bytes = sv.used();
     Carver ws(workspace);
     L.tri = ws.take<int>(Rg);
     L.S = ws.take<float>((size_t)B * N * N);
     L.dyA = ws.take<float>(R * 2 * nf);
     L.dyB = ws.take<float>(R * 2 * nf);
-    L.bsums = ws.take<double>(5 * 2 * kMaxC);
+    L.bsums = ws.take<double>(5 * kStatSlot);
     L.wimg = ws.take<float>(umma_workspace_floats(F, nf) + 64);
     L.dD = ws.take<float>(umma_shape_supported(F, nf) ? R * (size_t)((F + 3) & ~3) : 0);
     L.workspace_bytes = ws.used();
@@ -429,7 +429,7 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
     PairGeom g = make_geom(B, N, L.tri);
 
-    MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 4 * 2 * kMaxC, st));
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 4 * kStatSlot, st));
     {
         ProfScope ps(PC_PREP, st);
         tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
@@ -441,7 +441,7 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         if (rc != MFT_OK) return rc;
     } else {
         for (int k = 0; k < 4; ++k) {
-            double* sums = L.fsums + (size_t)k * 2 * kMaxC;
+            double* sums = L.fsums + (size_t)k * kStatSlot;
             EpiFwdStats epi{L.H[k], L.C[k + 1], sums, g};
             WView wv = wview_nt(p->conv_w[k], L.C[k]);
             ProfScope ps(PC_FWD_L1 + k, st);
@@ -449,7 +449,7 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
                 AbsDiffA a{x, ldx, g};
                 MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, g.R, L.C[1], F, st)));
             } else {
-                const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+                const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
                 BnActA a{L.H[k - 1], L.C[k], ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
                 MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, g.R, L.C[k + 1], L.C[k], st)));
             }
@@ -457,7 +457,7 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     }
     {
         ProfScope ps(PC_SCORE, st);
-        score_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * 2 * kMaxC, p->bn_g[3],
+        score_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3],
                                                                 p->bn_b[3], p->last_w, p->last_b, g, L.S);
         MFT_CHECK_LAUNCH();
     }
@@ -477,7 +477,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
     PairGeom g = make_geom(B, N, L.tri);
 
-    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * 2 * kMaxC, st));
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * kStatSlot, st));
     for (int k = 0; k < 4; ++k)
         MFT_CHECK_CUDA(cudaMemsetAsync(gr->conv_w[k], 0, sizeof(float) * (size_t)L.C[k + 1] * L.C[k], st));
     {
@@ -490,12 +490,12 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         softmax_bwd_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(adj, d_adj, L.S, B * N, N);
         MFT_CHECK_LAUNCH();
     }
-    double* lastsum = L.bsums + 4 * 2 * kMaxC;
+    double* lastsum = L.bsums + 4 * kStatSlot;
     {
         ProfScope ps(PC_DY4, st);
-        dy4_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * 2 * kMaxC, p->bn_g[3],
+        dy4_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3],
                                                               p->bn_b[3], p->last_w, g, L.dyA,
-                                                              L.bsums + 3 * 2 * kMaxC, lastsum);
+                                                              L.bsums + 3 * kStatSlot, lastsum);
         MFT_CHECK_LAUNCH();
     }
 
@@ -503,8 +503,8 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     float* nxt = L.dyB;
     for (int k = 3; k >= 0; --k) {   // layer k+1 of the reference (conv2d_{k+1}, bn_{k+1})
         const int Cout = L.C[k + 1], Cin = L.C[k];
-        const double* fs = L.fsums + (size_t)k * 2 * kMaxC;
-        const double* bs = L.bsums + (size_t)k * 2 * kMaxC;
+        const double* fs = L.fsums + (size_t)k * kStatSlot;
+        const double* bs = L.bsums + (size_t)k * kStatSlot;
         if (precision != MFT_PREC_TF32) {   // the tensor-core path applies BN-backward inside its operand producers
             ProfScope ps(PC_DH, st);
             dh_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(cur, L.H[k], Cout, fs, p->bn_g[k], bs, g);
@@ -521,7 +521,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
                 AbsDiffA q{x, ldx, g};
                 MFT_CHECK_CUDA((launch_gemm_tn(dh, q, gr->conv_w[0], Cin, Cout, Cin, g.R, st)));
             } else {
-                const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
+                const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
                 BnActA q{L.H[k - 1], Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
                 ProfScope psc(PC_WGRAD_L1 + k, st);
                 MFT_CHECK_CUDA((launch_gemm_tn(dh, q, gr->conv_w[k], Cin, Cout, Cin, g.R, st)));
@@ -537,8 +537,8 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
                     EpiDx epi{x, dx, ldx, g};
                     MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
                 } else {
-                    const double* ps = L.fsums + (size_t)(k - 1) * 2 * kMaxC;
-                    double* pbs = L.bsums + (size_t)(k - 1) * 2 * kMaxC;
+                    const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
+                    double* pbs = L.bsums + (size_t)(k - 1) * kStatSlot;
                     EpiDy epi{L.H[k - 1], nxt, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
                     MFT_CHECK_CUDA((launch_gemm_rows<false>(dh, wv, epi, g.R, Cin, Cout, st)));
                 }
@@ -549,7 +549,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
 
     FinalizeArgs fa;
     for (int k = 0; k < 4; ++k) {
-        fa.bsums[k] = L.bsums + (size_t)k * 2 * kMaxC;
+        fa.bsums[k] = L.bsums + (size_t)k * kStatSlot;
         fa.bn_g[k] = gr->bn_g[k];
         fa.bn_b[k] = gr->bn_b[k];
         fa.conv_b[k] = gr->conv_b[k];

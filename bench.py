@@ -216,13 +216,31 @@ def run_ours(args):
             nodes_dev.append(head.nodes(feat).contiguous())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step(nodes):
+    def fwd_bwd(nodes):
+        scores = head.forward_gnn_nodes(nodes)
+        return torch.nn.functional.cross_entropy(scores, y)
+
+    def eager_step(nodes):
         for prm in gnn_params:
             prm.grad = None
-        nodes = nodes.detach().requires_grad_(True)
-        scores = head.forward_gnn_nodes(nodes)
-        loss = torch.nn.functional.cross_entropy(scores, y)
+        loss = fwd_bwd(nodes.detach().requires_grad_(True))
         loss.backward()
+        return loss
+
+    use_graph = not args.no_graph
+    launches_per_step = None
+    if use_graph:
+        # launches of one step, counted on an eager run (a replay does not pass through the library)
+        eager_step(nodes_dev[0]); torch.cuda.synchronize()
+        l0 = lib.mft_launch_count(); eager_step(nodes_dev[0]); torch.cuda.synchronize()
+        launches_per_step = lib.mft_launch_count() - l0
+        gstep = mft_b200.GraphedStep(fwd_bwd, [nodes_dev[0]], gnn_params)
+
+    def step(nodes):
+        if use_graph:
+            loss = gstep(nodes)
+        else:
+            loss = eager_step(nodes)
         if world > 1:
             parallel.allreduce_mean_grads(gnn_params, world)
         return loss
@@ -248,20 +266,29 @@ def run_ours(args):
         ev[k][1].record()
     barrier()
     launches = lib.mft_launch_count() - launches0
+    if use_graph:
+        launches = launches_per_step * args.steps
     clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(ms)
 
     # ---- end to end: host (pinned) features in, loss out, copies inside the timed region
     feats_host = [synthetic_features(args.shape, 5000 + 1000 * rank + it).pin_memory() for it in range(total)]
+    all_params = list(head.parameters())
+    if use_graph:
+        g_e2e = mft_b200.GraphedStep(lambda f: head.set_forward_loss(f), [feats_host[0].to(dev)], all_params,
+                                        inputs_require_grad=False)
+
     def e2e_step(fh):
-        for prm in head.parameters():
-            prm.grad = None
-        feat = fh.to(dev, non_blocking=True)
-        loss = head.set_forward_loss(feat)
-        loss.backward()
+        if use_graph:
+            loss = g_e2e(fh)                      # pinned host -> static device tensor inside the call
+        else:
+            for prm in all_params:
+                prm.grad = None
+            loss = head.set_forward_loss(fh.to(dev, non_blocking=True))
+            loss.backward()
         if world > 1:
-            parallel.allreduce_mean_grads(list(head.parameters()), world)
+            parallel.allreduce_mean_grads(all_params, world)
         return float(loss.item())           # device -> host read of the step's result
     for it in range(args.warmup):
         e2e_step(feats_host[it])
@@ -274,16 +301,21 @@ def run_ours(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
 
-    # ---- per-category device time of the library's kernels (same steps, events around each launch)
+    # ---- per-category device time of the library's kernels (same steps, events around each launch).
+    # Every rank runs the steps (they contain the gradient all-reduce); only rank 0 records.
     prof = {}
+    nprof = min(args.steps, 3)
     if rank == 0:
         lib.mft_prof_enable(1)
-        nprof = min(args.steps, 3)
-        for k in range(nprof):
-            step(nodes_dev[args.warmup + k])
+    for k in range(nprof):
+        eager_step(nodes_dev[args.warmup + k])
+        if world > 1:
+            parallel.allreduce_mean_grads(gnn_params, world)
+    if rank == 0:
         raw = _lib.profile_collect()
         lib.mft_prof_enable(0)
         prof = {k: (v[0] / nprof, v[1] // nprof) for k, v in raw.items()}
+    barrier()
 
     # ---- max over ranks
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -316,6 +348,7 @@ def run_ours(args):
                 "parallelism": f"episode-dp{world}" + (" + nccl allreduce(gnn grads, 1.34 MB)" if world > 1 else ""),
                 "l2": "256 MiB fill between timed steps (L2 flushed); activation tape per step is 620 MB > L2",
                 "timing": "CUDA events per step on torch's current stream, summed over K steps, max over ranks",
+                "launch": "CUDA graph replay of fwd+bwd (captured once)" if use_graph else "eager launches",
             },
             "clocks": clocks,
             "e2e": {"value": e2e_eps, "unit": "episodes/s",
@@ -357,12 +390,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="5w20s", choices=sorted(SHAPES))
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -91,6 +91,12 @@ class GnnHead(nn.Module):
     def set_forward(self, feat: torch.Tensor) -> torch.Tensor:
         return self.forward_gnn_nodes(self.nodes(feat))
 
+    def _labels(self, device) -> torch.Tensor:
+        key = (self.n_way, self.n_query, str(device))
+        cache = self.__dict__.setdefault("_label_cache", {})
+        if key not in cache:                       # built once per (shape, device): no H2D copy per step
+            cache[key] = query_labels(self.n_way, self.n_query).to(device)
+        return cache[key]
+
     def set_forward_loss(self, feat: torch.Tensor) -> torch.Tensor:
-        y = query_labels(self.n_way, self.n_query).to(feat.device)
-        return self.loss_fn(self.set_forward(feat), y)
+        return self.loss_fn(self.set_forward(feat), self._labels(feat.device))

@@ -46,22 +46,18 @@ struct EpiStore {
 constexpr int kGcRows = 4;    // rows (nodes) per CTA in the per-node kernels
 constexpr int kGcCols = 64;   // threads along the output channel
 
-// Y[b,i,c] = V[b,i,c] + sum_j adj[b,i,j] U[b,j,c] + bias[c]; optional batch statistics.
+// Y[r, c] += bias[c]; optional BatchNorm1d batch statistics (sum y, sum y^2) over the B*N rows.
 __global__ void __launch_bounds__(kGcRows * kGcCols)
-gconv_combine_kernel(const float* __restrict__ adj, const float* __restrict__ UV, const float* __restrict__ bias,
-                     int rows, int N, int n_out, float* __restrict__ Y, int ldy, double* sums) {
+gconv_bias_stats_kernel(float* __restrict__ Y, int ldy, const float* __restrict__ bias, int rows, int n_out,
+                        double* sums) {
     __shared__ float red[2][kGcRows][kMaxC];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int row = blockIdx.x * kGcRows + ty;
     const bool live = row < rows;
-    const int b = live ? row / N : 0;
-    const float* arow = adj + (size_t)(live ? row : 0) * N;
-    const float* Ub = UV + (size_t)b * N * 2 * n_out + n_out;
     for (int c = tx; c < n_out; c += kGcCols) {
         float y = 0.f;
         if (live) {
-            y = UV[(size_t)row * 2 * n_out + c] + bias[c];
-            for (int j = 0; j < N; ++j) y = fmaf(arow[j], Ub[(size_t)j * 2 * n_out + c], y);
+            y = Y[(size_t)row * ldy + c] + bias[c];
             Y[(size_t)row * ldy + c] = y;
         }
         red[0][ty][c] = y;
@@ -216,26 +212,35 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     const bool has_bn = p->bn_g != nullptr;
     MFT_REQUIRE(has_bn || !lrelu_on, "gconv_fwd: LeakyReLU without BatchNorm is not a reference configuration");
 
-    // UV = x [Wa; Wb]^T : fc.weight [n_out, 2F] viewed as [2 n_out, F]
-    PlainOp a{x, ldx};
-    WView wv{p->fc_w, 2 * F, 1, n_out, F};
-    EpiStore epi{L.UV, 2 * n_out};
-    { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA((launch_gemm_rows<true>(a, wv, epi, rows, 2 * n_out, F, st))); }
-
-    dim3 blk(kGcCols, kGcRows);
+    // V = x Wa^T -> Y ;  U = x Wb^T ;  Y += adj U   (three small batched GEMMs), then one pass adds the
+    // bias and accumulates the BatchNorm1d statistics, and one applies BN + LeakyReLU.
+    const bool direct = !has_bn;                     // no BN: the result goes straight to `out`
+    float* Y = direct ? out : L.Y;
+    const int ldy = direct ? ldo : n_out;
+    BView X{x, 0, ldx, 1};                           // (m = row, k = f)
+    BView Wa{p->fc_w, 0, 1, 2 * F};                  // (k = f, n = c) -> fc_w[c*2F + f]
+    BView Wb{p->fc_w + F, 0, 1, 2 * F};
+    { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wa, Y, 0, ldy, 1, rows, n_out, F, 0.f, st)); }
+    { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wb, L.UV, 0, n_out, 1, rows, n_out, F, 0.f, st)); }
+    {
+        BView Am{adj, (long)N * N, N, 1};            // (m = i, k = j)
+        BView Um{L.UV, (long)N * n_out, n_out, 1};   // (k = j, n = c)
+        ProfScope ps(PC_GCONV_FWD, st);
+        MFT_CHECK_CUDA(launch_bgemm(Am, Um, Y, (long)N * ldy, ldy, B, N, n_out, N, 1.f, st));
+    }
+    if (has_bn) MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * kStatSlot, st));
+    {
+        ProfScope ps(PC_GCONV_FWD, st);
+        gconv_bias_stats_kernel<<<cdiv(rows, kGcRows), dim3(kGcCols, kGcRows), 0, st>>>(Y, ldy, p->fc_b, rows, n_out,
+                                                                                      has_bn ? L.fsums : nullptr);
+        MFT_CHECK_LAUNCH();
+    }
     if (has_bn) {
-        MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * kStatSlot, st));
-        { ProfScope ps(PC_GCONV_FWD, st); gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, L.Y, n_out,
-                                                                   L.fsums);
-        MFT_CHECK_LAUNCH(); }
         int total = rows * n_out;
-        { ProfScope ps(PC_GCONV_FWD, st); gconv_apply_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.Y, rows, n_out, L.fsums, p->bn_g,
+        ProfScope ps(PC_GCONV_FWD, st);
+        gconv_apply_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.Y, rows, n_out, L.fsums, p->bn_g,
                                                                            p->bn_b, lrelu_on, out, ldo);
-        MFT_CHECK_LAUNCH(); }
-    } else {
-        { ProfScope ps(PC_GCONV_FWD, st); gconv_combine_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(adj, L.UV, p->fc_b, rows, N, n_out, out, ldo,
-                                                                   nullptr);
-        MFT_CHECK_LAUNCH(); }
+        MFT_CHECK_LAUNCH();
     }
     return MFT_OK;
 }
@@ -277,8 +282,12 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA((launch_gemm_tn(dy, qax, g->fc_w + F, 2 * F, n_out, F, rows, st))); }
 
     // DU = dY W  [B*N, 2F]: first half feeds the identity operator, second half the adjacency
-    EpiStore epi{L.DU, 2 * F};
-    { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA((launch_gemm_rows<false>(dy, wview_nn(p->fc_w, 2 * F), epi, rows, 2 * F, n_out, st))); }
+    {
+        BView Dy{L.dY, 0, n_out, 1};                 // (m = row, k = c)
+        BView Wf{p->fc_w, 0, 2 * F, 1};              // (k = c, n = f') -> fc_w[c*2F + f']
+        ProfScope ps(PC_GCONV_BWD, st);
+        MFT_CHECK_CUDA(launch_bgemm(Dy, Wf, L.DU, 0, 2 * F, 1, rows, 2 * F, n_out, 0.f, st));
+    }
 
     // dx += DU1 + adj^T DU2
     {

@@ -7,31 +7,52 @@ constexpr int BG_T = 32;
 
 __global__ void __launch_bounds__(256)
 bgemm_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int M, int N, int K, float beta) {
-    __shared__ float As[BG_T][BG_T + 1];   // [m][k]
-    __shared__ float Bs[BG_T][BG_T + 1];   // [k][n]
+    // 32x32 output tile, K chunks of 32, next chunk prefetched into registers while the current one
+    // is multiplied (these products are small and latency bound: 105 <= K <= 1680)
+    __shared__ float As[2][BG_T][BG_T + 1];   // [m][k]
+    __shared__ float Bs[2][BG_T][BG_T + 1];   // [k][n]
     const int b = blockIdx.z;
     const int m0 = blockIdx.y * BG_T, n0 = blockIdx.x * BG_T;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     const float* Ab = A.p + (size_t)b * A.sb;
     const float* Bb = Bm.p + (size_t)b * Bm.sb;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < K; k0 += BG_T) {
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             int r = ty + 8 * q;
             int m = m0 + r, k = k0 + tx;
-            As[r][tx] = (m < M && k < K) ? Ab[(size_t)m * A.s0 + (size_t)k * A.s1] : 0.f;
+            ra[q] = (m < M && k < K) ? __ldg(Ab + (size_t)m * A.s0 + (size_t)k * A.s1) : 0.f;
             int kk = k0 + r, n = n0 + tx;
-            Bs[r][tx] = (kk < K && n < N) ? Bb[(size_t)kk * Bm.s0 + (size_t)n * Bm.s1] : 0.f;
+            rb[q] = (kk < K && n < N) ? __ldg(Bb + (size_t)kk * Bm.s0 + (size_t)n * Bm.s1) : 0.f;
         }
-        __syncthreads();
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            As[buf][ty + 8 * q][tx] = ra[q];
+            Bs[buf][ty + 8 * q][tx] = rb[q];
+        }
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < K; k0 += BG_T) {
+        const bool more = k0 + BG_T < K;
+        if (more) fetch(k0 + BG_T);
 #pragma unroll
         for (int k = 0; k < BG_T; ++k) {
-            float bv = Bs[k][tx];
+            float bv = Bs[buf][k][tx];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] = fmaf(As[ty + 8 * q][k], bv, acc[q]);
+            for (int q = 0; q < 4; ++q) acc[q] = fmaf(As[buf][ty + 8 * q][k], bv, acc[q]);
         }
-        __syncthreads();
+        if (more) {
+            stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

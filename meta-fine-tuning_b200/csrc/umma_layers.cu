@@ -1223,6 +1223,47 @@ dx_gather_kernel(const float* __restrict__ dD, int ldd, const float* __restrict_
     }
 }
 
+// Vector form for 16-byte aligned rows: 64 lanes x float4 over the features, 4 slices over the
+// partner nodes m (four independent load streams per thread, combined through shared memory).
+__global__ void __launch_bounds__(256)
+dx_gather_vec_kernel(const float* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
+                     int ldx, int F, int N, int Rg) {
+    __shared__ float4 part[4][64];
+    const int node = blockIdx.x;
+    const int b = node / N, n = node - b * N;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int f = tx * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f < F) {
+        const float4 xv = ldg4(x + (size_t)node * ldx + f);
+        const float* Db = dD + (size_t)b * Rg * ldd + f;
+        const float* xb = x + (size_t)b * N * ldx + f;
+#pragma unroll 4
+        for (int m = ty; m < N; m += 4) {
+            if (m == n) continue;
+            const int i = min(n, m), j = max(n, m);
+            const int r = tri_start(i, N) + (j - i);
+            const float4 xm = ldg4(xb + (size_t)m * ldx);
+            const float4 d = ldg4(Db + (size_t)r * ldd);
+            acc.x += (xv.x > xm.x) ? d.x : ((xv.x < xm.x) ? -d.x : 0.f);
+            acc.y += (xv.y > xm.y) ? d.y : ((xv.y < xm.y) ? -d.y : 0.f);
+            acc.z += (xv.z > xm.z) ? d.z : ((xv.z < xm.z) ? -d.z : 0.f);
+            acc.w += (xv.w > xm.w) ? d.w : ((xv.w < xm.w) ? -d.w : 0.f);
+        }
+    }
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && f < F) {
+        float4 a = part[0][tx], b1 = part[1][tx], c = part[2][tx], d = part[3][tx];
+        float* o = dx + (size_t)node * ldx + f;
+        float v[4] = {a.x + b1.x + c.x + d.x, a.y + b1.y + c.y + d.y, a.z + b1.z + c.z + d.z,
+                      a.w + b1.w + c.w + d.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (f + e < F) o[e] += v[e];
+    }
+}
+
 // dgrad of conv layer k (0-based): dL/d a_k = dH_k W_k on tensor cores; the epilogue turns it into
 // dy_{k-1} (+ BN-backward reductions) or, for layer 0, into dD followed by the dx gather.
 int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, int ldx, float* dx, int F, int nf,
@@ -1238,7 +1279,12 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
         int rc = umma_rows_gemm(a, e, p->conv_w[0], Cin, 1, g.R, Cin, Cout, L.wimg, st, PC_DGRAD_L1);
         if (rc != MFT_OK) return rc;
         ProfScope ps(PC_DGRAD_L1, st);
-        dx_gather_kernel<<<g.B * g.N, 256, 0, st>>>(L.dD, ldd, x, dx, ldx, F, g.N, g.Rg);
+        // x rows 16-byte aligned and padded to a multiple of 4 floats (always true for the xcat of gnn_fwd):
+        // beyond-F lanes of the last float4 read padding that is masked on the way out
+        if (absdiff_vec_ok(x, ldx, F) && F <= 256)
+            dx_gather_vec_kernel<<<g.B * g.N, 256, 0, st>>>(L.dD, ldd, x, dx, ldx, F, g.N, g.Rg);
+        else
+            dx_gather_kernel<<<g.B * g.N, 256, 0, st>>>(L.dD, ldd, x, dx, ldx, F, g.N, g.Rg);
         MFT_CHECK_LAUNCH();
         return MFT_OK;
     }

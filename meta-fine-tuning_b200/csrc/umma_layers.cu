@@ -84,6 +84,25 @@ __global__ void umma_weight_image_kernel(const float* __restrict__ W, int ldw, i
     }
 }
 
+// All weight images of one Wcompute direction in ONE launch (blockIdx.y = job).
+struct ImgJob { const float* W; float* img; int ldw, transpose, N, K, n0, N_TILE, KC; };
+struct ImgJobs { int n; ImgJob j[12]; };
+
+__global__ void umma_weight_images_kernel(ImgJobs jobs) {
+    const ImgJob& jb = jobs.j[blockIdx.y];
+    const int total = jb.KC * jb.N_TILE * UM_KB;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int kc = idx / (jb.N_TILE * UM_KB);
+        int rem = idx - kc * jb.N_TILE * UM_KB;
+        int n = rem / UM_KB, kk = rem - n * UM_KB;
+        int k = kc * UM_KB + kk;
+        float v = 0.f;
+        if (jb.n0 + n < jb.N && k < jb.K)
+            v = jb.transpose ? jb.W[(size_t)k * jb.ldw + jb.n0 + n] : jb.W[(size_t)(jb.n0 + n) * jb.ldw + k];
+        jb.img[(size_t)kc * jb.N_TILE * UM_KB + sw128_offset(n, kk)] = to_tf32(v);
+    }
+}
+
 // ------------------------------------------------------------------ producer functors
 // fetch(row, k, raw): issue the (read-only, non-coherent) global loads of four consecutive K
 // elements starting at k (k % 4 == 0); finish(raw, k, aux): turn them into operand values, zero
@@ -1072,7 +1091,7 @@ size_t umma_wimg_floats(int N, int K) {
 
 template <class AOp, class Epi>
 static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ldw, int transpose, int R, int N,
-                          int K, float* wimg, cudaStream_t st, int cat) {
+                          int K, float* wimg, cudaStream_t st, int cat, bool prebuilt = false) {
     int n0s[4], nts[4];
     int passes = plan_passes(N, K, n0s, nts);
     if (passes == 0) {
@@ -1089,7 +1108,7 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
         s.dbg = nullptr;
         if (g_umma_dbg && g_umma_dbg_skip-- == 0) { s.dbg = g_umma_dbg; g_umma_dbg = nullptr; }
         float* img = wimg + (size_t)p * s.N_TILE * s.KC * UM_KB;
-        {
+        if (!prebuilt) {
             ProfScope ps(PC_PREP, st);
             int total = s.KC * s.N_TILE * UM_KB;
             umma_weight_image_kernel<<<cdiv(total, 256), 256, 0, st>>>(W, ldw, transpose, N, K, s.n0, s.N_TILE,
@@ -1158,17 +1177,54 @@ bool umma_shape_supported(int F, int nf) {
            plan_passes((F + 15) & ~15, 2 * nf, n0s, nt) > 0;
 }
 
-size_t umma_workspace_floats(int F, int nf) {
-    // one weight image at a time (stream ordered): the largest of the forward / dgrad operands
-    size_t m = 0;
+// Region of layer k's weight image inside the workspace: all four layers of one direction are
+// resident at once (built by one launch); forward and backward reuse the same regions.
+static size_t img_region_floats(int F, int nf, int k) {
     int Cs[5] = {F, 2 * nf, 2 * nf, nf, nf};
+    size_t a = umma_wimg_floats(Cs[k + 1], Cs[k]);      // forward: N = C_out, K = C_in
+    size_t b = umma_wimg_floats(Cs[k], Cs[k + 1]);      // dgrad:   N = C_in,  K = C_out
+    return ((a > b ? a : b) + 255) & ~size_t(255);
+}
+static size_t img_offset(int F, int nf, int k) {
+    size_t off = 0;
+    for (int q = 0; q < k; ++q) off += img_region_floats(F, nf, q);
+    return off;
+}
+size_t umma_workspace_floats(int F, int nf) { return img_offset(F, nf, 4); }
+
+// Build the images of all four layers (forward: W[n][k]; backward: W^T for dgrad) with one launch.
+static int build_images(const mft_wcompute_params* p, float* wimg, int F, int nf, bool backward, cudaStream_t st) {
+    int Cs[5] = {F, 2 * nf, 2 * nf, nf, nf};
+    ImgJobs jobs{};
+    int max_total = 0;
     for (int k = 0; k < 4; ++k) {
-        size_t a = umma_wimg_floats(Cs[k + 1], Cs[k]);      // forward: N = C_out, K = C_in
-        size_t b = umma_wimg_floats(Cs[k], Cs[k + 1]);      // dgrad:   N = C_in,  K = C_out
-        m = m > a ? m : a;
-        m = m > b ? m : b;
+        const int N = backward ? Cs[k] : Cs[k + 1];
+        const int K = backward ? Cs[k + 1] : Cs[k];
+        int n0s[4], nts[4];
+        int passes = plan_passes(N, K, n0s, nts);
+        if (passes == 0) {
+            set_error(MFT_ERR_UNSUPPORTED, "tf32 path: no plan for N=%d K=%d", N, K);
+            return MFT_ERR_UNSUPPORTED;
+        }
+        const int KC = cdiv(K, UM_KB);
+        for (int q = 0; q < passes; ++q) {
+            ImgJob& jb = jobs.j[jobs.n++];
+            jb.W = p->conv_w[k];
+            jb.ldw = Cs[k];                               // conv2d_{k+1}.weight is [Cout, Cin]
+            jb.transpose = backward ? 1 : 0;
+            jb.N = N; jb.K = K; jb.n0 = n0s[q]; jb.N_TILE = nts[q]; jb.KC = KC;
+            jb.img = wimg + img_offset(F, nf, k) + (size_t)q * nts[q] * KC * UM_KB;
+            max_total = max(max_total, KC * nts[q] * UM_KB);
+        }
     }
-    return m;
+    ProfScope ps(PC_PREP, st);
+    umma_weight_images_kernel<<<dim3(cdiv(max_total, 256), jobs.n), 256, 0, st>>>(jobs);
+    MFT_CHECK_LAUNCH();
+    return MFT_OK;
+}
+
+int wcompute_bwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, cudaStream_t st) {
+    return build_images(p, L.wimg, F, nf, true, st);
 }
 
 int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_wcompute_params* p,
@@ -1177,21 +1233,26 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
         set_error(MFT_ERR_UNSUPPORTED, "tf32 path: unsupported shape F=%d nf=%d", F, nf);
         return MFT_ERR_UNSUPPORTED;
     }
+    {
+        int rc0 = build_images(p, L.wimg, F, nf, false, st);
+        if (rc0 != MFT_OK) return rc0;
+    }
     for (int k = 0; k < 4; ++k) {
         double* sums = L.fsums + (size_t)k * kStatSlot;
         EpiFwdStatsU epi{L.H[k], L.C[k + 1], sums, g};
+        float* img = L.wimg + img_offset(F, nf, k);
         int rc;
         if (k == 0) {
             AbsDiffU a{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
-            rc = umma_rows_gemm(a, epi, p->conv_w[0], F, 0, g.R, L.C[1], F, L.wimg, st, PC_FWD_L1);
+            rc = umma_rows_gemm(a, epi, p->conv_w[0], F, 0, g.R, L.C[1], F, img, st, PC_FWD_L1, true);
         } else {
             const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
             BnActT a{};
             rc = make_tmap_2d(&a.tmap, L.H[k - 1], g.R, L.C[k], L.C[k], UM_KB, UM_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
             if (rc != MFT_OK) return rc;
             a.C = L.C[k]; a.sums = ps; a.gamma = p->bn_g[k - 1]; a.beta = p->bn_b[k - 1]; a.inv_count = g.inv_pairs;
-            rc = umma_rows_gemm(a, epi, p->conv_w[k], L.C[k], 0, g.R, L.C[k + 1], L.C[k], L.wimg, st,
-                                PC_FWD_L1 + k);
+            rc = umma_rows_gemm(a, epi, p->conv_w[k], L.C[k], 0, g.R, L.C[k + 1], L.C[k], img, st,
+                                PC_FWD_L1 + k, true);
         }
         if (rc != MFT_OK) return rc;
     }
@@ -1269,14 +1330,15 @@ dx_gather_vec_kernel(const float* __restrict__ dD, int ldd, const float* __restr
 int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, int ldx, float* dx, int F, int nf,
                             const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                             const PairGeom& g, cudaStream_t st) {
-    (void)gr; (void)nf;
+    (void)gr;
     const int Cout = L.C[k + 1], Cin = L.C[k];
     DhU a{dh, L.H[k], Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
           g.inv_pairs, g};
     if (k == 0) {
         const int ldd = (F + 3) & ~3;
         EpiStoreU e{L.dD, ldd, 1};
-        int rc = umma_rows_gemm(a, e, p->conv_w[0], Cin, 1, g.R, Cin, Cout, L.wimg, st, PC_DGRAD_L1);
+        int rc = umma_rows_gemm(a, e, p->conv_w[0], Cin, 1, g.R, Cin, Cout, L.wimg + img_offset(F, nf, 0), st,
+                                PC_DGRAD_L1, true);
         if (rc != MFT_OK) return rc;
         ProfScope ps(PC_DGRAD_L1, st);
         // x rows 16-byte aligned and padded to a multiple of 4 floats (always true for the xcat of gnn_fwd):
@@ -1291,7 +1353,8 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
     const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
     double* pbs = L.bsums + (size_t)(k - 1) * kStatSlot;
     EpiDyU e{L.H[k - 1], dy_next, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
-    return umma_rows_gemm(a, e, p->conv_w[k], Cin, 1, g.R, Cin, Cout, L.wimg, st, PC_DGRAD_L1 + k);
+    return umma_rows_gemm(a, e, p->conv_w[k], Cin, 1, g.R, Cin, Cout, L.wimg + img_offset(F, nf, k), st,
+                          PC_DGRAD_L1 + k, true);
 }
 
 // wgrad of conv layer k: d conv2d_{k+1}.weight [Cout, Cin] += dH_k^T a_k (a_0 = |x_i - x_j|).

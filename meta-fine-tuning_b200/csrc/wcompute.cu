@@ -228,20 +228,36 @@ score_kernel(const float* __restrict__ H4, int C, const double* sums, const floa
     BnSmem s = bn_smem_at(aux);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float bias = last_b[0];
-    for (int r = blockIdx.x * kRowWarps + warp; r < g.R; r += gridDim.x * kRowWarps) {
+    // two rows per warp iteration: twice the loads in flight (the kernel is a pure HBM stream of H4)
+    const int stride = gridDim.x * kRowWarps;
+    for (int r = blockIdx.x * kRowWarps + warp; r < g.R; r += 2 * stride) {
+        const int r2 = r + stride;
+        const bool has2 = r2 < g.R;
         const float* row = H4 + (size_t)r * C;
-        float acc = 0.f;
+        const float* row2 = H4 + (size_t)(has2 ? r2 : r) * C;
+        float acc = 0.f, acc2 = 0.f;
         for (int c = lane; c < C; c += 32) {
-            float hh = (row[c] - s.mean[c]) * s.rstd[c];
+            float h1 = __ldg(row + c), h2 = __ldg(row2 + c);
+            float hh = (h1 - s.mean[c]) * s.rstd[c];
+            float hh2 = (h2 - s.mean[c]) * s.rstd[c];
             acc = fmaf(lrelu(fmaf(hh, s.gamma[c], s.beta[c])), wl[c], acc);
+            acc2 = fmaf(lrelu(fmaf(hh2, s.gamma[c], s.beta[c])), wl[c], acc2);
         }
         acc = warp_sum(acc);
+        acc2 = warp_sum(acc2);
         if (lane == 0) {
             PairRow p = decode_row(r, g);
             float v = acc + bias;
             size_t base = (size_t)p.b * g.N * g.N;
             S[base + (size_t)p.i * g.N + p.j] = v;
             S[base + (size_t)p.j * g.N + p.i] = v;
+            if (has2) {
+                PairRow q = decode_row(r2, g);
+                float v2 = acc2 + bias;
+                size_t base2 = (size_t)q.b * g.N * g.N;
+                S[base2 + (size_t)q.i * g.N + q.j] = v2;
+                S[base2 + (size_t)q.j * g.N + q.i] = v2;
+            }
         }
     }
 }
@@ -397,7 +413,7 @@ __global__ void finalize_grads_kernel(FinalizeArgs a) {
 
 // =========================== host orchestration ==============================
 
-static inline int row_grid(int R) { return min(cdiv(R, kRowWarps), 148 * 8); }
+static inline int row_grid(int R) { return min(cdiv(R, kRowWarps), 148 * 6); }
 
 WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     WcLayout L;
@@ -499,6 +515,10 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         MFT_CHECK_LAUNCH();
     }
 
+    if (precision == MFT_PREC_TF32) {
+        int rc = wcompute_bwd_prepare_tf32(p, L, F, nf, st);   // all four dgrad weight images, one launch
+        if (rc != MFT_OK) return rc;
+    }
     float* cur = L.dyA;
     float* nxt = L.dyB;
     for (int k = 3; k >= 0; --k) {   // layer k+1 of the reference (conv2d_{k+1}, bn_{k+1})

@@ -3,6 +3,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -153,6 +155,59 @@ __device__ __forceinline__ void bn_smem_fill(BnSmem s, const double* sums, const
         s.beta[c] = beta ? beta[c] : 0.f;
     }
 }
+
+// ---------------------------------------------------------------------------
+// Activation tape element types.  The fp32 path keeps everything in float.  The tensor-core path
+// stores the pre-BN activations H as fp16 (10-bit mantissa: the precision the TF32 operand
+// rounding applies to them anyway; values are clamped to the fp16 range on store) and the
+// gradients dy as bf16 (fp32 range -- gradients span many decades -- 8-bit mantissa).  Halving the
+// tape halves the HBM traffic of kernels that are all HBM bound.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 unpack_half4(uint2 u) {
+    float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 pack_half4(float4 v) {
+    uint2 u;   // round to nearest, saturate to +-65504 instead of overflowing to inf
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.x) : "f"(v.y), "f"(v.x));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.y) : "f"(v.w), "f"(v.z));
+    return u;
+}
+__device__ __forceinline__ float4 unpack_bf4(uint2 u) {
+    float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 pack_bf4(float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    return u;
+}
+// scalar tape accessors for the row-per-warp kernels shared by both paths
+template <bool Half> struct TapeH;
+template <> struct TapeH<false> {
+    typedef float T;
+    static __device__ __forceinline__ float ld(const void* p, size_t i) { return __ldg(static_cast<const float*>(p) + i); }
+};
+template <> struct TapeH<true> {
+    typedef __half T;
+    static __device__ __forceinline__ float ld(const void* p, size_t i) {
+        return __half2float(__ldg(static_cast<const __half*>(p) + i));
+    }
+};
+template <bool Half> struct TapeD;
+template <> struct TapeD<false> {
+    static __device__ __forceinline__ void st(void* p, size_t i, float v) { static_cast<float*>(p)[i] = v; }
+};
+template <> struct TapeD<true> {
+    static __device__ __forceinline__ void st(void* p, size_t i, float v) {
+        static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+    }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

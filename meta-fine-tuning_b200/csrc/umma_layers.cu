@@ -45,6 +45,8 @@ constexpr int UM_STAGE_LD = 36;           // padded row length of the epilogue s
 constexpr int UM_ACC_STRIDE = 256;        // TMEM columns between the two accumulators
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_MAX_STAGES = 4;
+constexpr int UM_MAX_RAW = 8;              // raw fp16 K blocks a TMA operand may have in flight
+constexpr int UM_RAW_BYTES = UM_ROWS * UM_KB * 2;   // [128 rows x 32 ch] fp16 = 8 KB
 constexpr int UM_MAX_CHUNKS = 8;          // 32-column epilogue chunks (N_TILE <= 256)
 constexpr int UM_STAT_CHUNKS = 6;         // chunks that can carry column statistics (N_TILE <= 192)
 constexpr int UM_MAX_NTILE = 240;
@@ -58,13 +60,14 @@ struct UmmaShape {
     int K;        // valid K
     int KC;       // K blocks (ceil(K/32))
     int stages;   // A ring depth
+    int raw_stages;   // fp16 raw-block ring depth (TMA operands only, else 0)
     long long* dbg;   // optional [gridDim.x][16] clock64 timeline (debug builds of the tests only)
     int reverse;      // walk the row tiles from the last to the first (see next_direction())
 };
 
 static inline size_t umma_smem_bytes(const UmmaShape& s) {
     return 1024 + (size_t)s.KC * s.N_TILE * 128 + (size_t)s.stages * UM_BLOCK_FLOATS * 4 +
-           (size_t)UM_ROWS * UM_STAGE_LD * 4 + (3 + 4) * kMaxC * 4 + UM_ROWS * 4 + 2 * 256 * 4 + 20 * 8 + 16;
+           (size_t)UM_ROWS * UM_STAGE_LD * 4 + (3 + 4) * kMaxC * 4 + (size_t)s.raw_stages * UM_RAW_BYTES + 32 * 8 + 16;
 }
 
 // ------------------------------------------------------------------ weight image
@@ -154,17 +157,19 @@ struct AbsDiffU {
 };
 
 // a = LeakyReLU(scale*h + shift), scale = gamma*rstd, shift = beta - mean*scale (C % 4 == 0)
+__device__ __forceinline__ uint2 ldg8(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+
 struct BnActU {
     static constexpr bool kTma = false;
     static constexpr int kAhead = 2;
-    const float* H;
+    const __half* H;                         // fp16 tape
     int C;
     const double* sums;
     const float* gamma;
     const float* beta;
     double inv_count;
-    struct Row { const float* h; };
-    struct Raw { float4 h; };
+    struct Row { const __half* h; };
+    struct Raw { uint2 h; };
     __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
         for (int c = tid; c < C; c += nthreads) {
             float m, r;
@@ -175,9 +180,10 @@ struct BnActU {
         }
     }
     __device__ __forceinline__ Row row(int r) const { return Row{H + (size_t)r * C}; }
-    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const { o.h = ldg4(rw.h + min(k, C - 4)); }
-    __device__ __forceinline__ float4 finish(const Raw& r, const Row&, int k, const float* aux) const {
+    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const { o.h = ldg8(rw.h + min(k, C - 4)); }
+    __device__ __forceinline__ float4 finish(const Raw& raw, const Row&, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        struct { float4 h; } r = {unpack_half4(raw.h)};
         float4 sc = *reinterpret_cast<const float4*>(aux + k);
         float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
         float4 y;
@@ -222,8 +228,8 @@ struct PlainU {
 struct DhU {
     static constexpr bool kTma = false;
     static constexpr int kAhead = 1;
-    const float* dy;
-    const float* H;
+    const float* dy;                         // fp32 (bf16 gradients cost 10% accuracy on small problems)
+    const __half* H;                         // fp16 tape
     int C;
     const double* fsums;
     const float* gamma;
@@ -231,7 +237,7 @@ struct DhU {
     double inv_count;
     PairGeom g;
     struct Row { int off; float w; };
-    struct Raw { float4 d, h; };
+    struct Raw { float4 d; uint2 h; };
     __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
         for (int c = tid; c < C; c += nthreads) {
             float m, r;
@@ -247,10 +253,11 @@ struct DhU {
     __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
         const int kk = min(k, C - 4);
         o.d = ldg4(dy + (size_t)rw.off + kk);
-        o.h = ldg4(H + (size_t)rw.off + kk);
+        o.h = ldg8(H + (size_t)rw.off + kk);
     }
-    __device__ __forceinline__ float4 finish(const Raw& r, const Row& rw, int k, const float* aux) const {
+    __device__ __forceinline__ float4 finish(const Raw& raw, const Row& rw, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        struct { float4 d, h; } r = {raw.d, unpack_half4(raw.h)};
         float4 P = *reinterpret_cast<const float4*>(aux + k);
         float4 Q = *reinterpret_cast<const float4*>(aux + kMaxC + k);
         float4 S = *reinterpret_cast<const float4*>(aux + 2 * kMaxC + k);
@@ -290,8 +297,9 @@ struct BnActT {
     __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
         return make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __device__ __forceinline__ float4 transform(float4 h, int k, const float* aux) const {
+    __device__ __forceinline__ float4 transform(uint2 raw, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 h = unpack_half4(raw);
         float4 sc = *reinterpret_cast<const float4*>(aux + k);
         float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
         float4 y;
@@ -315,10 +323,11 @@ struct EpiStoreU {
     int vec_ok;
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ float row_weight(int) const { return 1.f; }
-    __device__ __forceinline__ float4 prefetch(int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
-    __device__ __forceinline__ void apply(int r, float, int col, float4 v, float4, int nvalid, float*, float*,
-                                          const float*) const {
+    __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
+    __device__ __forceinline__ void apply(int r, bool ok, float, int col, float4 v, uint2, int nvalid, float*,
+                                          float*, const float*) const {
         float* o = out + (size_t)r * ld + col;
+        if (!ok) return;
         if (vec_ok && nvalid == 4) {
             *reinterpret_cast<float4*>(o) = v;
         } else {
@@ -336,16 +345,25 @@ struct EpiFwdStatsU {
     static constexpr bool kPrefetch = false;
     static constexpr bool kStats = true;
     static constexpr bool kRowWeight = true;
-    float* H;
+    __half* H;                               // fp16 tape
     int C;
     double* sums;
     PairGeom g;
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ float row_weight(int r) const { return decode_row(r, g).w; }
-    __device__ __forceinline__ float4 prefetch(int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
-    __device__ __forceinline__ void apply(int r, float w, int col, float4 v, float4, int, float* s0, float* s1,
-                                          const float*) const {
-        *reinterpret_cast<float4*>(H + (size_t)r * C + col) = v;
+    __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
+    __device__ __forceinline__ void apply(int r, bool ok, float w, int col, float4 v, uint2, int, float* s0,
+                                          float* s1, const float*) const {
+        const uint2 packed = pack_half4(v);
+#ifndef MFT_EXP_NOSTORE
+        if (ok) *reinterpret_cast<uint2*>(H + (size_t)r * C + col) = packed;
+#else
+        if (ok && w > 1e30f) *reinterpret_cast<uint2*>(H + (size_t)r * C + col) = packed;
+#endif
+        v = unpack_half4(packed);            // statistics of what the next layer will actually read
+#ifdef MFT_EXP_NOSTATS
+        if (w < 1e30f) return;
+#endif
         s0[0] = fmaf(w, v.x, s0[0]); s1[0] = fmaf(w * v.x, v.x, s1[0]);
         s0[1] = fmaf(w, v.y, s0[1]); s1[1] = fmaf(w * v.y, v.y, s1[1]);
         s0[2] = fmaf(w, v.z, s0[2]); s1[2] = fmaf(w * v.z, v.z, s1[2]);
@@ -363,8 +381,8 @@ struct EpiDyU {
     static constexpr bool kPrefetch = true;    // needs H_{k-1}(r, col): loaded one chunk ahead
     static constexpr bool kStats = true;
     static constexpr bool kRowWeight = false;
-    const float* H;
-    float* dy;
+    const __half* H;             // pre-BN activations of layer k-1 (fp16 tape)
+    float* dy;                   // gradient tape (fp32)
     int C;
     const double* fsums;
     const float* gamma;
@@ -383,9 +401,10 @@ struct EpiDyU {
         }
     }
     __device__ __forceinline__ float row_weight(int) const { return 1.f; }
-    __device__ __forceinline__ float4 prefetch(int r, int col) const { return ldg4(H + (size_t)r * C + col); }
-    __device__ __forceinline__ void apply(int r, float, int col, float4 v, float4 h, int, float* s0, float* s1,
-                                          const float* aux) const {
+    __device__ __forceinline__ uint2 prefetch(int r, int col) const { return ldg8(H + (size_t)r * C + col); }
+    __device__ __forceinline__ void apply(int r, bool ok, float, int col, float4 v, uint2 hraw, int, float* s0,
+                                          float* s1, const float* aux) const {
+        const float4 h = unpack_half4(hraw);
         float4 sc = *reinterpret_cast<const float4*>(aux + col);
         float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + col);
         float4 d;
@@ -393,7 +412,7 @@ struct EpiDyU {
         d.y = v.y * (fmaf(h.y, sc.y, sh.y) > 0.f ? 1.f : kSlope);
         d.z = v.z * (fmaf(h.z, sc.z, sh.z) > 0.f ? 1.f : kSlope);
         d.w = v.w * (fmaf(h.w, sc.w, sh.w) > 0.f ? 1.f : kSlope);
-        *reinterpret_cast<float4*>(dy + (size_t)r * C + col) = d;
+        if (ok) *reinterpret_cast<float4*>(dy + (size_t)r * C + col) = d;
         s0[0] += d.x; s1[0] = fmaf(d.x, h.x, s1[0]);
         s0[1] += d.y; s1[1] = fmaf(d.y, h.y, s1[1]);
         s0[2] += d.z; s1[2] = fmaf(d.z, h.z, s1[2]);
@@ -419,17 +438,16 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
     float* stage = Asm + (size_t)s.stages * UM_BLOCK_FLOATS;
     float* aux_a = stage + UM_ROWS * UM_STAGE_LD;
     float* aux_e = aux_a + 3 * kMaxC;
-    float* wrow = aux_e + 4 * kMaxC;
-    float* red0 = wrow + UM_ROWS;
-    float* red1 = red0 + 256;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red1 + 256);
+    uint8_t* rawring = reinterpret_cast<uint8_t*>(aux_e + 4 * kMaxC);   // [raw_stages][UM_RAW_BYTES], kTma only
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rawring + (size_t)s.raw_stages * UM_RAW_BYTES);
     uint64_t* full = bars;          // [UM_MAX_STAGES]
     uint64_t* empty = bars + 4;     // [UM_MAX_STAGES]
     uint64_t* tfull = bars + 8;     // [2]
     uint64_t* tempty = bars + 10;   // [2]
     uint64_t* wbar = bars + 12;
-    uint64_t* rawfull = bars + 13;  // [UM_MAX_STAGES]  (TMA operands: raw block landed)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* rawfull = bars + 13;   // [UM_MAX_RAW]  TMA operands: raw fp16 block landed
+    uint64_t* rawempty = bars + 21;  // [UM_MAX_RAW]  producers are done reading it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -442,7 +460,10 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
         for (int i = 0; i < UM_MAX_STAGES; ++i) {
             mbar_init(&full[i], UM_PROD_WARPS);     // one elected arrival per producer warp
             mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < UM_MAX_RAW; ++i) {
             mbar_init(&rawfull[i], 1);
+            mbar_init(&rawempty[i], UM_PROD_WARPS);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
@@ -454,7 +475,6 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
     if (warp == UM_MMA_WARP) tmem_alloc(tmem_slot, UM_TMEM_COLS);
     aop.init(aux_a, tid, UM_THREADS);
     epi.init(aux_e, tid, UM_THREADS);
-    for (int c = tid; c < 512; c += UM_THREADS) red0[c] = 0.f;   // red0 and red1 are contiguous
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -473,25 +493,35 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
         constexpr int RQ = UM_ROWS * 8 / UM_PROD_THREADS;      // rows per thread per K block (4)
         constexpr int RSTEP = UM_PROD_THREADS / 8;              // 32
         if constexpr (AOp::kTma) {
-            // in-place transform of the block the TMA warp landed in ring stage `st`
+            // The TMA warp lands raw fp16 blocks [128 rows x 32 ch] (row = 64 bytes, unswizzled) in the
+            // raw ring; each producer thread converts its (row, 4-channel) pieces, applies BN +
+            // LeakyReLU + TF32 rounding and writes the fp32 K block of the A ring, swizzled.
             const int rsub = tid >> 3, c16 = tid & 7;
             const int sw = rsub & 7;
-            int st = 0;
-            uint32_t ph = 0;
+            int st = 0, rs = 0;
+            uint32_t ph = 0, rph = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row0 = phys(tile) * UM_ROWS;
                 for (int kc = 0; kc < s.KC; ++kc) {
-                    mbar_wait(&rawfull[st], ph);
+                    mbar_wait(&rawfull[rs], rph);
+                    const uint8_t* rawb = rawring + (size_t)rs * UM_RAW_BYTES;
+                    uint2 raw[RQ];
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q)
+                        raw[q] = *reinterpret_cast<const uint2*>(rawb + (q * RSTEP + rsub) * 64 + c16 * 8);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&rawempty[rs]);      // the block is in registers: slot reusable
+                    if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
+                    mbar_wait(&empty[st], ph ^ 1);
                     float* blk = Asm + (size_t)st * UM_BLOCK_FLOATS;
                     const int k = kc * UM_KB + c16 * 4;
 #pragma unroll
                     for (int q = 0; q < RQ; ++q) {
                         const int rl = q * RSTEP + rsub;
-                        float4* ptr = reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2));
-                        float4 v = aop.transform(*ptr, k, aux_a);
+                        float4 v = aop.transform(raw[q], k, aux_a);
                         if (row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
                         v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-                        *ptr = v;
+                        *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -622,15 +652,15 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
         if constexpr (AOp::kTma) {
             if (lane == 0) {
                 tma_prefetch_desc(&aop.tmap);
-                int st = 0;
-                uint32_t ph = 0;
+                int rs = 0;
+                uint32_t rph = 0;
                 for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                     const int row0 = phys(tile) * UM_ROWS;
                     for (int kc = 0; kc < s.KC; ++kc) {
-                        mbar_wait(&empty[st], ph ^ 1);
-                        mbar_arrive_expect_tx(&rawfull[st], UM_BLOCK_FLOATS * 4);
-                        tma_load_2d(Asm + (size_t)st * UM_BLOCK_FLOATS, &aop.tmap, kc * UM_KB, row0, &rawfull[st]);
-                        if (++st == s.stages) { st = 0; ph ^= 1; }
+                        mbar_wait(&rawempty[rs], rph ^ 1);
+                        mbar_arrive_expect_tx(&rawfull[rs], UM_RAW_BYTES);
+                        tma_load_2d(rawring + (size_t)rs * UM_RAW_BYTES, &aop.tmap, kc * UM_KB, row0, &rawfull[rs]);
+                        if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
                     }
                 }
             }
@@ -671,9 +701,9 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
             // been copied to the slab, so they are in flight while chunk ch is written out.
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * UM_ACC_STRIDE;
             uint32_t v[32];
-            float4 pre[Epi::kPrefetch ? 2 : 1][8];
+            uint2 pre[Epi::kPrefetch ? 2 : 1][8];
             auto chunk_live = [&](int ch) { return ch * 32 + c4 < s.N_TILE && s.n0 + ch * 32 + c4 < s.N; };
-            auto load_pre = [&](int ch, float4 (&dst)[8]) {
+            auto load_pre = [&](int ch, uint2 (&dst)[8]) {
                 if (Epi::kPrefetch && chunk_live(ch)) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)       // pure loads, row clamped in bounds
@@ -682,16 +712,21 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
             };
             tmem_ld_32x32(tbase, v);
             load_pre(0, pre[0]);
+            long long t_ld = 0, t_sts = 0, t_apply = 0, tA = 0, tB = 0;
+            const bool timing = dbg != nullptr && warp == UM_EPI_WARP0 && lane == 0;
 #pragma unroll
             for (int ch = 0; ch < UM_MAX_CHUNKS; ++ch) {
                 if (ch < nchunks) {
+                    if (timing) tA = clock64();
                     tmem_ld_wait();
+                    if (timing) { tB = clock64(); t_ld += tB - tA; }
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         *reinterpret_cast<float4*>(slab + lane * UM_STAGE_LD + q * 4) =
                             make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
                     __syncwarp();
+                    if (timing) { tA = clock64(); t_sts += tA - tB; }
                     if (ch + 1 < nchunks) {
                         tmem_ld_32x32(tbase + (ch + 1) * 32, v);
                         load_pre(ch + 1, pre[Epi::kPrefetch ? ((ch + 1) & 1) : 0]);
@@ -701,19 +736,26 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                     if (cl < s.N_TILE && col < s.N) {
                         const int nvalid = min(4, s.N - col);
 #pragma unroll
+                        // straight-line over the 8 rows (no branch per row: rows past the end hold
+                        // exact zeros in TMEM and only their store is predicated off), so the eight
+                        // LDS / convert / store chains interleave
+                        float4 a[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            a[q] = *reinterpret_cast<const float4*>(slab + (q * 4 + rsub) * UM_STAGE_LD + c4);
+#pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const int rl = q * 4 + rsub;
-                            const int r = row0 + rl;
-                            if (r < s.R) {
-                                float4 a = *reinterpret_cast<const float4*>(slab + rl * UM_STAGE_LD + c4);
-                                epi.apply(r, wq[q], col, a, pre[Epi::kPrefetch ? (ch & 1) : 0][q], nvalid,
-                                          s0[ch < UM_STAT_CHUNKS ? ch : 0], s1[ch < UM_STAT_CHUNKS ? ch : 0], aux_e);
-                            }
+                            const int r = row0 + q * 4 + rsub;
+                            epi.apply(min(r, s.R - 1), r < s.R, wq[q], col, a[q], pre[Epi::kPrefetch ? (ch & 1) : 0][q],
+                                      nvalid, s0[ch < UM_STAT_CHUNKS ? ch : 0], s1[ch < UM_STAT_CHUNKS ? ch : 0],
+                                      aux_e);
                         }
                     }
                     __syncwarp();
+                    if (timing) { tB = clock64(); t_apply += tB - tA; }
                 }
             }
+            if (timing) { dbg[13] += t_ld; dbg[14] += t_sts; dbg[15] += t_apply; }
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -854,6 +896,9 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
         bool ok = false;
         typename POp::Row pr;
         typename QOp::Row qr;
+        // One chunk of loads in flight per thread (issued right after the previous chunk was handed
+        // to the MMA).  Deeper register prefetch was tried (two static buffers) and bought nothing:
+        // with six scoreboard slots the extra loads alias the slots of the ones being consumed.
         // Q operands with kAhead == 0 (|x_i - x_j| from the small L2-resident node matrix) are
         // fetched and consumed inside the step, after the P blocks have been stored, so that their
         // registers do not add to P's in-flight set.
@@ -1005,18 +1050,18 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // Row-major fp32 matrix [rows, cols] with leading dimension ld (elements): boxes of box_cols x box_rows.
-static int make_tmap_2d(CUtensorMap* out, const float* base, int rows, int cols, int ld, int box_cols, int box_rows,
-                        CUtensorMapSwizzle swz) {
+static int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int esize, int rows, int cols,
+                        int ld, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) {
         set_error(MFT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
         return MFT_ERR_CUDA;
     }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * esize};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+    CUresult r = fn(out, dtype, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1104,6 +1149,21 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
         const int dir = next_direction();
         UmmaShape s{};
         plan_pass(nts[p], K, s);
+        if (AOp::kTma) {
+            // two fp32 A stages are enough once the loads run ahead in the fp16 raw ring: give the
+            // rest of shared memory to raw blocks in flight
+            s.stages = 2;
+            s.raw_stages = 0;
+            for (int rs = UM_MAX_RAW; rs >= 2; --rs) {
+                s.raw_stages = rs;
+                if (umma_smem_bytes(s) <= kSmemLimit) break;
+                s.raw_stages = 0;
+            }
+            if (s.raw_stages == 0) {
+                set_error(MFT_ERR_UNSUPPORTED, "umma_rows_gemm: no room for the raw ring (N=%d K=%d)", N, K);
+                return MFT_ERR_UNSUPPORTED;
+            }
+        }
         s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.reverse = dir;
         s.dbg = nullptr;
         if (g_umma_dbg && g_umma_dbg_skip-- == 0) { s.dbg = g_umma_dbg; g_umma_dbg = nullptr; }
@@ -1239,7 +1299,7 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
     }
     for (int k = 0; k < 4; ++k) {
         double* sums = L.fsums + (size_t)k * kStatSlot;
-        EpiFwdStatsU epi{L.H[k], L.C[k + 1], sums, g};
+        EpiFwdStatsU epi{reinterpret_cast<__half*>(L.H[k]), L.C[k + 1], sums, g};
         float* img = L.wimg + img_offset(F, nf, k);
         int rc;
         if (k == 0) {
@@ -1248,7 +1308,8 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
         } else {
             const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
             BnActT a{};
-            rc = make_tmap_2d(&a.tmap, L.H[k - 1], g.R, L.C[k], L.C[k], UM_KB, UM_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+            rc = make_tmap_2d(&a.tmap, L.H[k - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g.R, L.C[k], L.C[k], UM_KB,
+                              UM_ROWS, CU_TENSOR_MAP_SWIZZLE_NONE);
             if (rc != MFT_OK) return rc;
             a.C = L.C[k]; a.sums = ps; a.gamma = p->bn_g[k - 1]; a.beta = p->bn_b[k - 1]; a.inv_count = g.inv_pairs;
             rc = umma_rows_gemm(a, epi, p->conv_w[k], L.C[k], 0, g.R, L.C[k + 1], L.C[k], img, st,
@@ -1332,7 +1393,7 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
                             const PairGeom& g, cudaStream_t st) {
     (void)gr;
     const int Cout = L.C[k + 1], Cin = L.C[k];
-    DhU a{dh, L.H[k], Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
+    DhU a{dh, reinterpret_cast<const __half*>(L.H[k]), Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
           g.inv_pairs, g};
     if (k == 0) {
         const int ldd = (F + 3) & ~3;
@@ -1352,7 +1413,7 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
     }
     const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
     double* pbs = L.bsums + (size_t)(k - 1) * kStatSlot;
-    EpiDyU e{L.H[k - 1], dy_next, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
+    EpiDyU e{reinterpret_cast<const __half*>(L.H[k - 1]), dy_next, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
     return umma_rows_gemm(a, e, p->conv_w[k], Cin, 1, g.R, Cin, Cout, L.wimg + img_offset(F, nf, k), st,
                           PC_DGRAD_L1 + k, true);
 }
@@ -1362,14 +1423,14 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
                               const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                               const PairGeom& g, cudaStream_t st) {
     const int Cout = L.C[k + 1], Cin = L.C[k];
-    DhU P{dh, L.H[k], Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
+    DhU P{dh, reinterpret_cast<const __half*>(L.H[k]), Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
           g.inv_pairs, g};
     if (k == 0) {
         AbsDiffU Q{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
         return umma_wgrad(P, Q, gr->conv_w[0], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1);
     }
     const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
-    BnActU Q{L.H[k - 1], Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
+    BnActU Q{reinterpret_cast<const __half*>(L.H[k - 1]), Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
     return umma_wgrad(P, Q, gr->conv_w[k], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1 + k);
 }
 

@@ -217,8 +217,9 @@ constexpr int kRowWarps = 8;   // warps per CTA in the warp-per-row kernels
 constexpr int kChPerLane = kMaxC / 32;
 
 // S[b,i,j] = S[b,j,i] = conv2d_last(LeakyReLU(BN4(H4[r])))   (gnn.py:99-103)
+template <bool HalfTape>
 __global__ void __launch_bounds__(kRowWarps * 32)
-score_kernel(const float* __restrict__ H4, int C, const double* sums, const float* gamma, const float* beta,
+score_kernel(const void* __restrict__ H4, int C, const double* sums, const float* gamma, const float* beta,
              const float* last_w, const float* last_b, PairGeom g, float* __restrict__ S) {
     __shared__ float aux[4 * kMaxC];
     __shared__ float wl[kMaxC];
@@ -233,11 +234,10 @@ score_kernel(const float* __restrict__ H4, int C, const double* sums, const floa
     for (int r = blockIdx.x * kRowWarps + warp; r < g.R; r += 2 * stride) {
         const int r2 = r + stride;
         const bool has2 = r2 < g.R;
-        const float* row = H4 + (size_t)r * C;
-        const float* row2 = H4 + (size_t)(has2 ? r2 : r) * C;
+        const size_t o1 = (size_t)r * C, o2 = (size_t)(has2 ? r2 : r) * C;
         float acc = 0.f, acc2 = 0.f;
         for (int c = lane; c < C; c += 32) {
-            float h1 = __ldg(row + c), h2 = __ldg(row2 + c);
+            float h1 = TapeH<HalfTape>::ld(H4, o1 + c), h2 = TapeH<HalfTape>::ld(H4, o2 + c);
             float hh = (h1 - s.mean[c]) * s.rstd[c];
             float hh2 = (h2 - s.mean[c]) * s.rstd[c];
             acc = fmaf(lrelu(fmaf(hh, s.gamma[c], s.beta[c])), wl[c], acc);
@@ -308,9 +308,10 @@ softmax_bwd_kernel(const float* __restrict__ adj, const float* __restrict__ d_ad
 // Backward through conv2d_last and the layer-4 LeakyReLU:
 //   G_r = dS_ij + dS_ji, dy4 = G_r * w_last * lrelu'(y4); reductions sum dy4, sum dy4*hhat4,
 //   sum G_r * a4 (= d conv2d_last.weight).  One warp per row, lanes over channels.
+template <bool HalfTape>
 __global__ void __launch_bounds__(kRowWarps * 32)
-dy4_kernel(const float* __restrict__ dS, const float* __restrict__ H4, int C, const double* fsums,
-           const float* gamma, const float* beta, const float* last_w, PairGeom g, float* __restrict__ dy4,
+dy4_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, const double* fsums,
+           const float* gamma, const float* beta, const float* last_w, PairGeom g, void* __restrict__ dy4,
            double* bsums, double* lastsum) {
     __shared__ float aux[4 * kMaxC];
     __shared__ float wl[kMaxC];
@@ -328,15 +329,14 @@ dy4_kernel(const float* __restrict__ dS, const float* __restrict__ H4, int C, co
         size_t base = (size_t)p.b * g.N * g.N;
         float G = dS[base + (size_t)p.i * g.N + p.j];
         if (p.i != p.j) G += dS[base + (size_t)p.j * g.N + p.i];
-        const float* row = H4 + (size_t)r * C;
 #pragma unroll
         for (int q = 0; q < kChPerLane; ++q) {
             int c = lane + 32 * q;
             if (c < C) {
-                float hh = (row[c] - s.mean[c]) * s.rstd[c];
+                float hh = (TapeH<HalfTape>::ld(H4, (size_t)r * C + c) - s.mean[c]) * s.rstd[c];
                 float y = fmaf(hh, s.gamma[c], s.beta[c]);
                 float d = G * wl[c] * dlrelu(y);
-                dy4[(size_t)r * C + c] = d;
+                TapeD<false>::st(dy4, (size_t)r * C + c, d);   // gradients stay fp32 on both paths
                 p0[q] += d;
                 p1[q] = fmaf(d, hh, p1[q]);
                 p2[q] = fmaf(G, lrelu(y), p2[q]);
@@ -473,8 +473,14 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     }
     {
         ProfScope ps(PC_SCORE, st);
-        score_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3],
-                                                                p->bn_b[3], p->last_w, p->last_b, g, L.S);
+        if (precision == MFT_PREC_TF32)
+            score_kernel<true><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * kStatSlot,
+                                                                          p->bn_g[3], p->bn_b[3], p->last_w,
+                                                                          p->last_b, g, L.S);
+        else
+            score_kernel<false><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * kStatSlot,
+                                                                           p->bn_g[3], p->bn_b[3], p->last_w,
+                                                                           p->last_b, g, L.S);
         MFT_CHECK_LAUNCH();
     }
     {
@@ -509,9 +515,14 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     double* lastsum = L.bsums + 4 * kStatSlot;
     {
         ProfScope ps(PC_DY4, st);
-        dy4_kernel<<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3],
-                                                              p->bn_b[3], p->last_w, g, L.dyA,
-                                                              L.bsums + 3 * kStatSlot, lastsum);
+        if (precision == MFT_PREC_TF32)
+            dy4_kernel<true><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * kStatSlot,
+                                                                        p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA,
+                                                                        L.bsums + 3 * kStatSlot, lastsum);
+        else
+            dy4_kernel<false><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * kStatSlot,
+                                                                         p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA,
+                                                                         L.bsums + 3 * kStatSlot, lastsum);
         MFT_CHECK_LAUNCH();
     }
 

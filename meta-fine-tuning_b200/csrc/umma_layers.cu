@@ -47,6 +47,7 @@ constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_MAX_STAGES = 4;
 constexpr int UM_MAX_RAW = 8;              // raw fp16 K blocks a TMA operand may have in flight
 constexpr int UM_RAW_BYTES = UM_ROWS * UM_KB * 2;   // [128 rows x 32 ch] fp16 = 8 KB
+constexpr unsigned WG_ROWS_C = 32;        // rows per wgrad K chunk (declared early for the TMA functors)
 constexpr int UM_MAX_CHUNKS = 8;          // 32-column epilogue chunks (N_TILE <= 256)
 constexpr int UM_STAT_CHUNKS = 6;         // chunks that can carry column statistics (N_TILE <= 192)
 constexpr int UM_MAX_NTILE = 240;
@@ -300,6 +301,89 @@ struct BnActT {
     __device__ __forceinline__ float4 transform(uint2 raw, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 h = unpack_half4(raw);
+        float4 sc = *reinterpret_cast<const float4*>(aux + k);
+        float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
+        float4 y;
+        y.x = fmaf(h.x, sc.x, sh.x); y.y = fmaf(h.y, sc.y, sh.y);
+        y.z = fmaf(h.z, sc.z, sh.z); y.w = fmaf(h.w, sc.w, sh.w);
+        return make_float4(fmaxf(y.x, kSlope * y.x), fmaxf(y.y, kSlope * y.y), fmaxf(y.z, kSlope * y.z),
+                           fmaxf(y.w, kSlope * y.w));
+    }
+};
+
+// Tensor-map operands of the wgrad kernel: whole [32 rows x C] row-major slabs land in a raw ring
+// (dy fp32, H fp16), producers convert them into the MN-major operand blocks.
+struct DhT {                                     // P = dH_k from (dy_k, H_k)
+    static constexpr bool kTma = true;
+    static constexpr int kAhead = 0;
+    alignas(64) CUtensorMap tmap_dy;             // fp32 [R, C], box {C, 32}
+    alignas(64) CUtensorMap tmap_h;              // fp16 [R, C], box {C, 32}
+    int C;
+    const double* fsums;
+    const float* gamma;
+    const double* bsums;
+    double inv_count;
+    PairGeom g;
+    struct Row { float w; };
+    struct Raw { int dummy; };
+    __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
+        for (int c = tid; c < C; c += nthreads) {
+            float m, r;
+            bn_mean_rstd(fsums, C, c, inv_count, m, r);
+            float P = gamma[c] * r;
+            float S = P * r * (float)(stat_get(bsums, C, c, 1) * inv_count);
+            aux[c] = P;
+            aux[kMaxC + c] = P * (float)(stat_get(bsums, C, c, 0) * inv_count) - S * m;
+            aux[2 * kMaxC + c] = S;
+        }
+    }
+    __device__ __forceinline__ Row row(int r) const { return Row{decode_row(r, g).w}; }
+    __device__ __forceinline__ void fetch(const Row&, int, Raw&) const {}
+    __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ uint32_t raw_bytes() const { return WG_ROWS_C * C * 6u; }   // fp32 + fp16 slab
+    __device__ __forceinline__ float4 transform(float4 d, uint2 hraw, float w, int k, const float* aux) const {
+        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 h = unpack_half4(hraw);
+        float4 P = *reinterpret_cast<const float4*>(aux + k);
+        float4 Q = *reinterpret_cast<const float4*>(aux + kMaxC + k);
+        float4 S = *reinterpret_cast<const float4*>(aux + 2 * kMaxC + k);
+        const float nw = -w;
+        return make_float4(fmaf(nw, fmaf(S.x, h.x, Q.x), P.x * d.x), fmaf(nw, fmaf(S.y, h.y, Q.y), P.y * d.y),
+                           fmaf(nw, fmaf(S.z, h.z, Q.z), P.z * d.z), fmaf(nw, fmaf(S.w, h.w, Q.w), P.w * d.w));
+    }
+};
+
+struct BnActQT {                                 // Q = LeakyReLU(BN(H_{k-1}))
+    static constexpr bool kTma = true;
+    static constexpr int kAhead = 1;             // (not a late-fetched operand)
+    alignas(64) CUtensorMap tmap_h;              // fp16 [R, C], box {C, 32}
+    int C;
+    const double* sums;
+    const float* gamma;
+    const float* beta;
+    double inv_count;
+    struct Row { int dummy; };
+    struct Raw { int dummy; };
+    __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
+        for (int c = tid; c < C; c += nthreads) {
+            float m, r;
+            bn_mean_rstd(sums, C, c, inv_count, m, r);
+            float sc = gamma[c] * r;
+            aux[c] = sc;
+            aux[kMaxC + c] = beta[c] - m * sc;
+        }
+    }
+    __device__ __forceinline__ Row row(int) const { return Row{0}; }
+    __device__ __forceinline__ void fetch(const Row&, int, Raw&) const {}
+    __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ uint32_t raw_bytes() const { return WG_ROWS_C * C * 2u; }
+    __device__ __forceinline__ float4 transform(uint2 hraw, int k, const float* aux) const {
+        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 h = unpack_half4(hraw);
         float4 sc = *reinterpret_cast<const float4*>(aux + k);
         float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
         float4 y;
@@ -822,7 +906,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 constexpr int WG_ROWS = 32;                       // rows per K chunk
 constexpr int WG_BLOCK_FLOATS = WG_ROWS * UM_KB;  // [32 rows x 32 ch] = 1024 floats = 4 KB
 constexpr int WG_PROD_THREADS = 256;
-constexpr int WG_THREADS = WG_PROD_THREADS + 32;   // 8 producer warps (0-3 also drain TMEM at the end) + 1 MMA warp
+constexpr int WG_THREADS = WG_PROD_THREADS + 64;   // 8 producer warps (0-3 also drain TMEM at the end) + MMA + TMA warp
 constexpr int WG_MAX_PB = 6;                      // Cout <= 192
 constexpr int WG_MAX_QB = 8;                      // Cin  <= 256
 
@@ -834,16 +918,21 @@ struct WgradShape {
     int stages;
     int chunks_per_cta;
     int reverse;
+    int raw_stages;    // raw slab ring depth (TMA operands), 0 = register path
+    int raw_bytes;     // bytes of one raw stage: [dy fp32 | H fp16 | Hq fp16] slabs of 32 rows
+    int copies;        // dW is `copies` partial accumulators `copy_stride` floats apart (CTA b -> b % copies)
+    int copy_stride;
 };
 
 static inline size_t wgrad_smem_bytes(const WgradShape& s) {
     return 1024 + (size_t)s.stages * (s.PB + s.QB) * WG_BLOCK_FLOATS * 4 + (size_t)UM_ROWS * UM_STAGE_LD * 4 +
-           (3 + 3) * kMaxC * 4 + 16 * 8 + 16;
+           (3 + 3) * kMaxC * 4 + (size_t)s.raw_stages * s.raw_bytes + 32 * 8 + 16;
 }
 
 template <class POp, class QOp>
 __global__ void __launch_bounds__(WG_THREADS, 1)
-umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape s) {
+umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp qop, float* __restrict__ dW, int ldw,
+                  const __grid_constant__ WgradShape s) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_floats = (s.PB + s.QB) * WG_BLOCK_FLOATS;
@@ -851,11 +940,14 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
     float* stage = ring + (size_t)s.stages * stage_floats;
     float* aux_p = stage + UM_ROWS * UM_STAGE_LD;
     float* aux_q = aux_p + 3 * kMaxC;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(aux_q + 3 * kMaxC);
+    uint8_t* rawring = reinterpret_cast<uint8_t*>(aux_q + 3 * kMaxC);   // [raw_stages][raw_bytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rawring + (size_t)s.raw_stages * s.raw_bytes);
     uint64_t* full = bars;        // [UM_MAX_STAGES]
     uint64_t* empty = bars + 4;   // [UM_MAX_STAGES]
     uint64_t* done = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* rawfull = bars + 9;     // [4]
+    uint64_t* rawempty = bars + 13;   // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -873,6 +965,10 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
             mbar_init(&empty[i], 1);
         }
         mbar_init(done, 1);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&rawfull[i], 1);
+            mbar_init(&rawempty[i], WG_PROD_THREADS / 32);
+        }
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, UM_TMEM_COLS);
@@ -891,6 +987,74 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
         const int off = (rl >> 2) * 128 + (rl & 3) * 32 + ((((c16 >> 1) ^ (rl & 3))) << 3) + ((c16 & 1) << 2);
         int st = 0;
         uint32_t ph = 0;
+        if constexpr (POp::kTma) {
+            // raw stage: [dy: 32 x Cout fp32][H_k: 32 x Cout fp16][H_{k-1}: 32 x Cin fp16], row-major
+            int rs = 0;
+            uint32_t rph = 0;
+            const uint32_t off_h = WG_ROWS * s.Cout * 4, off_q = off_h + WG_ROWS * s.Cout * 2;
+            typename QOp::Row qr;
+            typename QOp::Raw qraw[QOp::kTma ? 1 : WG_MAX_QB];
+            for (int c = c_begin; c < c_end; ++c) {
+                const int r = c * WG_ROWS + rl;
+                const bool ok = r < s.R;
+                const float w = ok ? pop.row(r).w : 0.f;
+                mbar_wait(&rawfull[rs], rph);
+                const uint8_t* rb = rawring + (size_t)rs * s.raw_bytes;
+                float4 dv[WG_MAX_PB];
+                uint2 hv[WG_MAX_PB];
+                uint2 qv[WG_MAX_QB];
+#pragma unroll
+                for (int b = 0; b < WG_MAX_PB; ++b) {
+                    if (b < s.PB) {
+                        const int k = min(b * UM_KB + c16 * 4, s.Cout - 4);
+                        dv[b] = *reinterpret_cast<const float4*>(rb + ((size_t)rl * s.Cout + k) * 4);
+                        hv[b] = *reinterpret_cast<const uint2*>(rb + off_h + ((size_t)rl * s.Cout + k) * 2);
+                    }
+                }
+                if constexpr (QOp::kTma) {
+#pragma unroll
+                    for (int b = 0; b < WG_MAX_QB; ++b)
+                        if (b < s.QB) {
+                            const int k = min(b * UM_KB + c16 * 4, s.Cin - 4);
+                            qv[b] = *reinterpret_cast<const uint2*>(rb + off_q + ((size_t)rl * s.Cin + k) * 2);
+                        }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rawempty[rs]);      // slab is in registers
+                if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
+                if constexpr (!QOp::kTma) {                       // |x_i - x_j| from the L2-resident node matrix
+                    qr = qop.row(ok ? r : 0);
+#pragma unroll
+                    for (int b = 0; b < WG_MAX_QB; ++b)
+                        if (b < s.QB) qop.fetch(qr, b * UM_KB + c16 * 4, qraw[b]);
+                }
+                mbar_wait(&empty[st], ph ^ 1);
+                float* dst = ring + (size_t)st * stage_floats + off;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int b = 0; b < WG_MAX_PB; ++b) {
+                    if (b < s.PB) {
+                        float4 v = ok ? pop.transform(dv[b], hv[b], w, b * UM_KB + c16 * 4, aux_p) : zero;
+                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                        *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < WG_MAX_QB; ++b) {
+                    if (b < s.QB) {
+                        float4 v;
+                        if constexpr (QOp::kTma) v = ok ? qop.transform(qv[b], b * UM_KB + c16 * 4, aux_q) : zero;
+                        else v = ok ? qop.finish(qraw[QOp::kTma ? 0 : b], qr, b * UM_KB + c16 * 4, aux_q) : zero;
+                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                        *reinterpret_cast<float4*>(dst + (s.PB + b) * WG_BLOCK_FLOATS) = v;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[st]);
+                if (++st == s.stages) { st = 0; ph ^= 1; }
+            }
+        } else {
         typename POp::Raw praw[WG_MAX_PB];
         typename QOp::Raw qraw[WG_MAX_QB];
         bool ok = false;
@@ -952,6 +1116,30 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
                 if (!kLateQ) fetch_q(c + 1);
             }
         }
+        }   // register path
+    } else if (warp == 9) {
+        // ===================== TMA loader (one thread): slabs of 32 rows, all operands of a chunk
+        if constexpr (POp::kTma) {
+            if (lane == 0 && my_chunks > 0) {
+                tma_prefetch_desc(&pop.tmap_dy);
+                tma_prefetch_desc(&pop.tmap_h);
+                const uint32_t off_h = WG_ROWS * s.Cout * 4, off_q = off_h + WG_ROWS * s.Cout * 2;
+                uint32_t bytes = WG_ROWS * s.Cout * 6;
+                if constexpr (QOp::kTma) bytes += WG_ROWS * s.Cin * 2;
+                int rs = 0;
+                uint32_t rph = 0;
+                for (int c = c_begin; c < c_end; ++c) {
+                    mbar_wait(&rawempty[rs], rph ^ 1);
+                    uint8_t* rb = rawring + (size_t)rs * s.raw_bytes;
+                    mbar_arrive_expect_tx(&rawfull[rs], bytes);
+                    tma_load_2d(rb, &pop.tmap_dy, 0, c * WG_ROWS, &rawfull[rs]);
+                    tma_load_2d(rb + off_h, &pop.tmap_h, 0, c * WG_ROWS, &rawfull[rs]);
+                    if constexpr (QOp::kTma) tma_load_2d(rb + off_q, &qop.tmap_h, 0, c * WG_ROWS, &rawfull[rs]);
+                    if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
     } else {
         // ===================== MMA issuer
         if (lane == 0 && my_chunks > 0) {
@@ -1013,7 +1201,7 @@ umma_wgrad_kernel(POp pop, QOp qop, float* __restrict__ dW, int ldw, WgradShape 
                     const int co = co_base + l;
                     if (l >= lane_lo && co < s.Cout && col < s.Cin) {
                         const float* sp = stage + l * UM_STAGE_LD + c4;
-                        float* gp = dW + (size_t)co * ldw + col;
+                        float* gp = dW + (size_t)(blockIdx.x % s.copies) * s.copy_stride + (size_t)co * ldw + col;
                         const int nv = min(4, s.Cin - col);
                         for (int e = 0; e < nv; ++e) atomicAdd(gp + e, sp[e]);
                     }
@@ -1188,9 +1376,10 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
 
 template <class POp, class QOp>
 static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R, int Cout, int Cin,
-                      cudaStream_t st, int cat) {
+                      cudaStream_t st, int cat, int copies = 1) {
     WgradShape s{};
     s.R = R; s.Cout = Cout; s.Cin = Cin;
+    s.copies = copies; s.copy_stride = Cout * Cin;
     s.PB = cdiv(Cout, UM_KB);
     s.QB = cdiv(Cin, UM_KB);
     s.N_TILE = (Cin + 15) & ~15;
@@ -1199,6 +1388,21 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
         return MFT_ERR_UNSUPPORTED;
     }
     s.stages = 0;
+    s.raw_stages = 0;
+    s.raw_bytes = 0;
+    if (POp::kTma) {
+        // raw slabs of one chunk: dy fp32 + H_k fp16 (+ H_{k-1} fp16); two operand stages, and as
+        // many raw stages in flight as shared memory allows (at least two)
+        s.raw_bytes = WG_ROWS * Cout * 6 + (QOp::kTma ? WG_ROWS * Cin * 2 : 0);
+        s.raw_bytes = (s.raw_bytes + 127) & ~127;
+        s.stages = 2;
+        for (int rs = 4; rs >= 2; --rs) {
+            s.raw_stages = rs;
+            if (wgrad_smem_bytes(s) <= kSmemLimit) break;
+            s.raw_stages = 0;
+        }
+        if (s.raw_stages == 0) s.stages = 0;
+    } else
     for (int stg = UM_MAX_STAGES; stg >= 2; --stg) {
         s.stages = stg;
         if (wgrad_smem_bytes(s) <= kSmemLimit) break;
@@ -1423,15 +1627,26 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
                               const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                               const PairGeom& g, cudaStream_t st) {
     const int Cout = L.C[k + 1], Cin = L.C[k];
-    DhU P{dh, reinterpret_cast<const __half*>(L.H[k]), Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
-          g.inv_pairs, g};
+    DhT P{};
+    int rc = make_tmap_2d(&P.tmap_dy, dh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.R, Cout, Cout, Cout, WG_ROWS,
+                          CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != MFT_OK) return rc;
+    rc = make_tmap_2d(&P.tmap_h, L.H[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g.R, Cout, Cout, Cout, WG_ROWS,
+                      CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != MFT_OK) return rc;
+    P.C = Cout; P.fsums = L.fsums + (size_t)k * kStatSlot; P.gamma = p->bn_g[k];
+    P.bsums = L.bsums + (size_t)k * kStatSlot; P.inv_count = g.inv_pairs; P.g = g;
     if (k == 0) {
         AbsDiffU Q{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
-        return umma_wgrad(P, Q, gr->conv_w[0], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1);
+        return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[0], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1, kWgCopies);
     }
-    const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
-    BnActU Q{reinterpret_cast<const __half*>(L.H[k - 1]), Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs};
-    return umma_wgrad(P, Q, gr->conv_w[k], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1 + k);
+    BnActQT Q{};
+    rc = make_tmap_2d(&Q.tmap_h, L.H[k - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g.R, Cin, Cin, Cin, WG_ROWS,
+                      CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != MFT_OK) return rc;
+    Q.C = Cin; Q.sums = L.fsums + (size_t)(k - 1) * kStatSlot; Q.gamma = p->bn_g[k - 1]; Q.beta = p->bn_b[k - 1];
+    Q.inv_count = g.inv_pairs;
+    return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[k], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1 + k, kWgCopies);
 }
 
 // Debug / test entry: C[M, N] = A[M, K] * op(W)^T through the tcgen05 rows kernel with plain

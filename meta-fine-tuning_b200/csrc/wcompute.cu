@@ -387,6 +387,9 @@ dh_kernel(float* __restrict__ dy, const float* __restrict__ H, int C, const doub
 }
 
 struct FinalizeArgs {
+    const float* wgpart[4];   // tcgen05 path: kWgCopies partial weight gradients per layer (else null)
+    float* conv_w[4];
+    int wsize[4];
     const double* bsums[4];
     const double* lastsum;
     float* bn_g[4];
@@ -409,6 +412,16 @@ __global__ void finalize_grads_kernel(FinalizeArgs a) {
     }
     if (t < a.nf && a.last_w) a.last_w[t] = (float)stat_get(a.lastsum, a.nf, t, 0);
     if (t == 0 && a.last_b) a.last_b[0] = 0.f;         // softmax shift invariance: exactly zero
+    // conv weight gradients: add up the partial copies the wgrad CTAs accumulated into
+    for (int k = 0; k < 4; ++k) {
+        if (a.wgpart[k] == nullptr) continue;
+        for (int i = t; i < a.wsize[k]; i += gridDim.x * blockDim.x) {
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < kWgCopies; ++q) v += a.wgpart[k][(size_t)q * a.wsize[k] + i];
+            a.conv_w[k][i] = v;
+        }
+    }
 }
 
 // =========================== host orchestration ==============================
@@ -432,6 +445,15 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     L.bsums = ws.take<double>(5 * kStatSlot);
     L.wimg = ws.take<float>(umma_workspace_floats(F, nf) + 64);
     L.dD = ws.take<float>(umma_shape_supported(F, nf) ? R * (size_t)((F + 3) & ~3) : 0);
+    {
+        size_t tot = 0;
+        for (int k = 0; k < 4; ++k) {
+            L.wgpart_off[k] = tot;
+            tot += (size_t)kWgCopies * L.C[k + 1] * L.C[k];
+        }
+        L.wgpart = ws.take<float>(umma_shape_supported(F, nf) ? tot : 0);
+        L.wgpart_floats = tot;
+    }
     L.workspace_bytes = ws.used();
     return L;
 }
@@ -500,8 +522,12 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     PairGeom g = make_geom(B, N, L.tri);
 
     MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * kStatSlot, st));
-    for (int k = 0; k < 4; ++k)
-        MFT_CHECK_CUDA(cudaMemsetAsync(gr->conv_w[k], 0, sizeof(float) * (size_t)L.C[k + 1] * L.C[k], st));
+    if (precision == MFT_PREC_TF32) {
+        MFT_CHECK_CUDA(cudaMemsetAsync(L.wgpart, 0, sizeof(float) * L.wgpart_floats, st));
+    } else {
+        for (int k = 0; k < 4; ++k)
+            MFT_CHECK_CUDA(cudaMemsetAsync(gr->conv_w[k], 0, sizeof(float) * (size_t)L.C[k + 1] * L.C[k], st));
+    }
     {
         ProfScope ps(PC_PREP, st);
         tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
@@ -585,6 +611,9 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         fa.bn_b[k] = gr->bn_b[k];
         fa.conv_b[k] = gr->conv_b[k];
         fa.C[k] = L.C[k + 1];
+        fa.wgpart[k] = precision == MFT_PREC_TF32 ? L.wgpart + L.wgpart_off[k] : nullptr;
+        fa.conv_w[k] = gr->conv_w[k];
+        fa.wsize[k] = L.C[k + 1] * L.C[k];
     }
     fa.lastsum = lastsum;
     fa.last_w = gr->last_w;
@@ -592,7 +621,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     fa.nf = nf;
     {
         ProfScope ps(PC_FINALIZE, st);
-        finalize_grads_kernel<<<1, kMaxC, 0, st>>>(fa);
+        finalize_grads_kernel<<<precision == MFT_PREC_TF32 ? 64 : 1, kMaxC, 0, st>>>(fa);
         MFT_CHECK_LAUNCH();
     }
     return MFT_OK;

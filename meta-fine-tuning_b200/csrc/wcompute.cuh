@@ -6,6 +6,8 @@
 namespace mft {
 
 // Carved views of the Wcompute `saved` / `workspace` blobs.
+constexpr int kWgCopies = 8;   // same-address fp32 atomics from 148 CTAs serialise in L2; 8 copies -> ~18 per address
+
 struct WcLayout {
     int C[5];            // channel widths: F, 2nf, 2nf, nf, nf
     float* H[4];         // saved: pre-BN activations of the four conv layers, [R, C[k+1]]
@@ -17,6 +19,9 @@ struct WcLayout {
     double* bsums;       // workspace: backward reductions, 5 x [2*kMaxC] (last = d conv2d_last.weight)
     float* wimg;         // workspace: swizzled TF32 weight image of the tcgen05 path
     float* dD;           // workspace (tcgen05 path): dL/d|x_i-x_j| per unordered pair, [R, roundup4(F)]
+    float* wgpart;       // workspace (tcgen05 path): kWgCopies partial copies of the four conv-weight gradients
+    size_t wgpart_off[4];  // float offset of layer k's copies inside wgpart (copy stride = C[k+1]*C[k])
+    size_t wgpart_floats;
     size_t saved_bytes, workspace_bytes;
 };
 

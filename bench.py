@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -345,6 +345,7 @@ def run_ours(args):
                 "workload": f"GnnNet head fwd+bwd, {args.shape}: GNN_nl on B={n_query} graphs x N={n} nodes, F=133, "
                             f"nf=96, n_way={n_way}; CE on the query nodes; input + 64 parameter gradients",
                 "shape": args.shape, "precision": prec,
+                "tape": "fp16 pre-BN activations, fp32 gradients (tensor-core path)" if prec == "tf32" else "fp32",
                 "parallelism": f"episode-dp{world}" + (" + nccl allreduce(gnn grads, 1.34 MB)" if world > 1 else ""),
                 "l2": "256 MiB fill between timed steps (L2 flushed); activation tape per step is 620 MB > L2",
                 "timing": "CUDA events per step on torch's current stream, summed over K steps, max over ranks",
@@ -390,7 +391,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="5w20s", choices=sorted(SHAPES))

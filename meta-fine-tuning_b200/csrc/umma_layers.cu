@@ -424,6 +424,25 @@ struct EpiStoreU {
     __device__ __forceinline__ void commit(int, float, float, const float*) const {}
 };
 
+// dD (gradient of |x_i - x_j|, consumed only by the dx gather) is stored as bf16: fp32 range, and its
+// 2^-9 rounding is far below what TF32 leaves in the gradients anyway (ld % 4 == 0, padded columns
+// hold exact zeros because the padded weight-image rows are zero).
+struct EpiStoreBf16U {
+    static constexpr bool kPrefetch = false;
+    static constexpr bool kStats = false;
+    static constexpr bool kRowWeight = false;
+    __nv_bfloat16* out;
+    int ld;
+    __device__ __forceinline__ void init(float*, int, int) const {}
+    __device__ __forceinline__ float row_weight(int) const { return 1.f; }
+    __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
+    __device__ __forceinline__ void apply(int r, bool ok, float, int col, float4 v, uint2, int, float*, float*,
+                                          const float*) const {
+        if (ok && col < ld) *reinterpret_cast<uint2*>(out + (size_t)r * ld + col) = pack_bf4(v);
+    }
+    __device__ __forceinline__ void commit(int, float, float, const float*) const {}
+};
+
 // forward: store pre-BN H, accumulate sum w*h and sum w*h^2 (C % 4 == 0)
 struct EpiFwdStatsU {
     static constexpr bool kPrefetch = false;
@@ -1528,12 +1547,12 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
 // broadcast subtraction (gnn.py:79-81) as a gather: one CTA per node, no atomics.  dD holds the
 // twin-summed gradient of each unordered pair, so the same formula serves both ends of a pair.
 __global__ void __launch_bounds__(256)
-dx_gather_kernel(const float* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
+dx_gather_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
                  int ldx, int F, int N, int Rg) {
     const int node = blockIdx.x;            // b*N + n
     const int b = node / N, n = node - b * N;
     const float* xn = x + (size_t)node * ldx;
-    const float* Db = dD + (size_t)b * Rg * ldd;
+    const __nv_bfloat16* Db = dD + (size_t)b * Rg * ldd;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
         const float xv = xn[f];
         float acc = 0.f;
@@ -1542,7 +1561,7 @@ dx_gather_kernel(const float* __restrict__ dD, int ldd, const float* __restrict_
             const int i = min(n, m), j = max(n, m);
             const int r = tri_start(i, N) + (j - i);
             const float df = xv - __ldg(x + (size_t)(b * N + m) * ldx + f);
-            const float d = __ldg(Db + (size_t)r * ldd + f);
+            const float d = __bfloat162float(__ldg(Db + (size_t)r * ldd + f));
             acc += (df > 0.f) ? d : ((df < 0.f) ? -d : 0.f);
         }
         dx[(size_t)node * ldx + f] += acc;
@@ -1552,7 +1571,7 @@ dx_gather_kernel(const float* __restrict__ dD, int ldd, const float* __restrict_
 // Vector form for 16-byte aligned rows: 64 lanes x float4 over the features, 4 slices over the
 // partner nodes m (four independent load streams per thread, combined through shared memory).
 __global__ void __launch_bounds__(256)
-dx_gather_vec_kernel(const float* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
+dx_gather_vec_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
                      int ldx, int F, int N, int Rg) {
     __shared__ float4 part[4][64];
     const int node = blockIdx.x;
@@ -1562,7 +1581,7 @@ dx_gather_vec_kernel(const float* __restrict__ dD, int ldd, const float* __restr
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f < F) {
         const float4 xv = ldg4(x + (size_t)node * ldx + f);
-        const float* Db = dD + (size_t)b * Rg * ldd + f;
+        const __nv_bfloat16* Db = dD + (size_t)b * Rg * ldd + f;
         const float* xb = x + (size_t)b * N * ldx + f;
 #pragma unroll 4
         for (int m = ty; m < N; m += 4) {
@@ -1570,7 +1589,7 @@ dx_gather_vec_kernel(const float* __restrict__ dD, int ldd, const float* __restr
             const int i = min(n, m), j = max(n, m);
             const int r = tri_start(i, N) + (j - i);
             const float4 xm = ldg4(xb + (size_t)m * ldx);
-            const float4 d = ldg4(Db + (size_t)r * ldd);
+            const float4 d = unpack_bf4(ldg8(Db + (size_t)r * ldd));
             acc.x += (xv.x > xm.x) ? d.x : ((xv.x < xm.x) ? -d.x : 0.f);
             acc.y += (xv.y > xm.y) ? d.y : ((xv.y < xm.y) ? -d.y : 0.f);
             acc.z += (xv.z > xm.z) ? d.z : ((xv.z < xm.z) ? -d.z : 0.f);
@@ -1601,7 +1620,7 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
           g.inv_pairs, g};
     if (k == 0) {
         const int ldd = (F + 3) & ~3;
-        EpiStoreU e{L.dD, ldd, 1};
+        EpiStoreBf16U e{reinterpret_cast<__nv_bfloat16*>(L.dD), ldd};
         int rc = umma_rows_gemm(a, e, p->conv_w[0], Cin, 1, g.R, Cin, Cout, L.wimg + img_offset(F, nf, 0), st,
                                 PC_DGRAD_L1, true);
         if (rc != MFT_OK) return rc;
@@ -1609,9 +1628,11 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
         // x rows 16-byte aligned and padded to a multiple of 4 floats (always true for the xcat of gnn_fwd):
         // beyond-F lanes of the last float4 read padding that is masked on the way out
         if (absdiff_vec_ok(x, ldx, F) && F <= 256)
-            dx_gather_vec_kernel<<<g.B * g.N, 256, 0, st>>>(L.dD, ldd, x, dx, ldx, F, g.N, g.Rg);
+            dx_gather_vec_kernel<<<g.B * g.N, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(L.dD), ldd, x, dx,
+                                                            ldx, F, g.N, g.Rg);
         else
-            dx_gather_kernel<<<g.B * g.N, 256, 0, st>>>(L.dD, ldd, x, dx, ldx, F, g.N, g.Rg);
+            dx_gather_kernel<<<g.B * g.N, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(L.dD), ldd, x, dx,
+                                                        ldx, F, g.N, g.Rg);
         MFT_CHECK_LAUNCH();
         return MFT_OK;
     }

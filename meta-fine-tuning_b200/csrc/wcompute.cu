@@ -324,22 +324,42 @@ dy4_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, con
     float p0[kChPerLane], p1[kChPerLane], p2[kChPerLane];
 #pragma unroll
     for (int q = 0; q < kChPerLane; ++q) { p0[q] = 0.f; p1[q] = 0.f; p2[q] = 0.f; }
-    for (int r = blockIdx.x * kRowWarps + warp; r < g.R; r += gridDim.x * kRowWarps) {
-        PairRow p = decode_row(r, g);
-        size_t base = (size_t)p.b * g.N * g.N;
-        float G = dS[base + (size_t)p.i * g.N + p.j];
-        if (p.i != p.j) G += dS[base + (size_t)p.j * g.N + p.i];
+    // four rows per warp iteration: all their H4 / dS loads are issued before any is consumed
+    constexpr int RU = 4;
+    const int stride = gridDim.x * kRowWarps;
+    for (int r0 = blockIdx.x * kRowWarps + warp; r0 < g.R; r0 += RU * stride) {
+        float G[RU];
+        float hraw[RU][kChPerLane];
 #pragma unroll
-        for (int q = 0; q < kChPerLane; ++q) {
-            int c = lane + 32 * q;
-            if (c < C) {
-                float hh = (TapeH<HalfTape>::ld(H4, (size_t)r * C + c) - s.mean[c]) * s.rstd[c];
-                float y = fmaf(hh, s.gamma[c], s.beta[c]);
-                float d = G * wl[c] * dlrelu(y);
-                TapeD<false>::st(dy4, (size_t)r * C + c, d);   // gradients stay fp32 on both paths
-                p0[q] += d;
-                p1[q] = fmaf(d, hh, p1[q]);
-                p2[q] = fmaf(G, lrelu(y), p2[q]);
+        for (int u = 0; u < RU; ++u) {
+            const int r = min(r0 + u * stride, g.R - 1);
+            PairRow p = decode_row(r, g);
+            size_t base = (size_t)p.b * g.N * g.N;
+            float a = __ldg(dS + base + (size_t)p.i * g.N + p.j);
+            float b2 = __ldg(dS + base + (size_t)p.j * g.N + p.i);
+            G[u] = (p.i != p.j) ? a + b2 : a;
+#pragma unroll
+            for (int q = 0; q < kChPerLane; ++q) {
+                int c = lane + 32 * q;
+                hraw[u][q] = (c < C) ? TapeH<HalfTape>::ld(H4, (size_t)r * C + c) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * stride;
+            if (r >= g.R) break;
+#pragma unroll
+            for (int q = 0; q < kChPerLane; ++q) {
+                int c = lane + 32 * q;
+                if (c < C) {
+                    float hh = (hraw[u][q] - s.mean[c]) * s.rstd[c];
+                    float y = fmaf(hh, s.gamma[c], s.beta[c]);
+                    float d = G[u] * wl[c] * dlrelu(y);
+                    TapeD<false>::st(dy4, (size_t)r * C + c, d);   // gradients stay fp32 on both paths
+                    p0[q] += d;
+                    p1[q] = fmaf(d, hh, p1[q]);
+                    p2[q] = fmaf(G[u], lrelu(y), p2[q]);
+                }
             }
         }
     }

@@ -40,6 +40,8 @@ class GraphedStep:
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager()
         torch.cuda.synchronize()
+        # the graph writes gradients at these addresses on every replay
+        self.static_grads = [p.grad for p in self.params]
 
     def _eager(self) -> torch.Tensor:
         for p in self.params:
@@ -60,4 +62,7 @@ class GraphedStep:
         for dst, src in zip(self.static_inputs, inputs):
             dst.detach().copy_(src, non_blocking=True)
         self.graph.replay()
+        for p, g in zip(self.params, self.static_grads):
+            if p.grad is not g:         # someone cleared or replaced .grad between replays
+                p.grad = g
         return self.static_loss

@@ -1,0 +1,134 @@
+"""GPU tests of the module surface beyond GNN_nl: Wcompute and Gconv called on their own (as the
+reference API allows), inference under no_grad, eval()/train() equivalence, deepcopy, state_dict
+round trip, the GnnHead mirror against the oracle (5-shot and compressed 50-shot), and CUDA-graph
+replay of a training step."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gnn_oracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(fin, nf, n_way, seed):
+    return {k: v.float() for k, v in O.random_params(fin, nf, n_way, seed, torch.float64).items()}
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-6), ("tf32", 2e-3)])
+def test_wcompute_module_alone(prec, tol):
+    import mft_b200
+    mft_b200.set_precision(prec)
+    fin, nf, bsz, n = 133, 96, 3, 11
+    p = _params(fin, nf, 5, 21)
+    m = mft_b200.Wcompute(fin, nf).cuda()
+    m.load_state_dict({k[len("layer_w0."):]: v for k, v in p.items() if k.startswith("layer_w0.")})
+    x = torch.randn(bsz, n, fin, generator=torch.Generator().manual_seed(1))
+    eye = torch.eye(n).unsqueeze(0).repeat(bsz, 1, 1).unsqueeze(3)
+    with torch.no_grad():
+        out = m(x.cuda(), eye.cuda()).cpu()
+        ref = O.wcompute(x.double(), {k: v.double() for k, v in p.items()}, "layer_w0.")
+    assert out.shape == (bsz, n, n, 2)
+    assert torch.equal(out[..., 0], eye[..., 0])
+    assert U.rel(out[..., 1].numpy(), ref[..., 1].numpy()) < tol
+    mft_b200.set_precision("auto")
+
+
+def test_gconv_module_alone_forward_backward():
+    import mft_b200
+    fin, nout, bsz, n = 37, 12, 3, 9
+    g = torch.Generator().manual_seed(3)
+    adj = torch.softmax(torch.randn(bsz, n, n, generator=g, dtype=torch.float64), dim=2)
+    eye = torch.eye(n, dtype=torch.float64).expand(bsz, n, n)
+    W = torch.stack([eye, adj], dim=3)
+    x = torch.randn(bsz, n, fin, generator=g, dtype=torch.float64)
+    m = mft_b200.Gconv(fin, nout, 2).cuda()
+    p = {"l.fc.weight": m.fc.weight.detach().double().cpu(), "l.fc.bias": m.fc.bias.detach().double().cpu(),
+         "l.bn.weight": m.bn.weight.detach().double().cpu(), "l.bn.bias": m.bn.bias.detach().double().cpu()}
+    xr = x.clone().requires_grad_(True)
+    Wr = W.clone().requires_grad_(True)
+    ref = O.gconv(Wr, xr, p, "l.")
+    proj = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * proj).sum().backward()
+    xg = x.float().cuda().requires_grad_(True)
+    Wg = W.float().cuda().requires_grad_(True)
+    W_out, out = m([Wg, xg])
+    assert W_out is Wg
+    (out * proj.float().cuda()).sum().backward()
+    assert U.rel(out.detach().cpu().numpy(), ref.detach().numpy()) < 5e-6
+    assert U.rel(xg.grad.cpu().numpy(), xr.grad.numpy()) < 5e-5
+    assert U.rel(Wg.grad[..., 1].cpu().numpy(), Wr.grad[..., 1].numpy()) < 5e-5
+
+
+def test_inference_modes_and_copies_agree():
+    import mft_b200
+    mft_b200.set_precision("fp32")
+    torch.manual_seed(0)
+    net = mft_b200.GNN_nl(133, 96, 5).cuda()
+    x = torch.randn(4, 30, 133, device="cuda")
+    with torch.no_grad():
+        a = net(x)
+        net.eval()
+        b = net(x)                    # no running statistics anywhere: eval() changes nothing
+        net.train()
+        c = copy.deepcopy(net)(x)
+        d = mft_b200.GNN_nl(133, 96, 5).cuda()
+        d.load_state_dict(net.state_dict())
+        dd = d(x)
+        net.fused = False
+        e = net(x)
+    assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, dd)
+    assert torch.allclose(a, e, rtol=0, atol=1e-5)
+    mft_b200.set_precision("auto")
+
+
+@pytest.mark.parametrize("n_support,compress,fixture", [(5, False, "head_5w5s.npz"), (50, True, "head_50c.npz")])
+def test_gnn_head_matches_reference_scores(golden_dir, n_support, compress, fixture):
+    """GnnHead (fc -> graphs -> GNN -> select) against scores the reference GnnNet / gnnnet_copy
+    produced on the same features and parameters (tests/golden, is_feature path of finetune.py)."""
+    import mft_b200
+    rec = dict(np.load(os.path.join(golden_dir, fixture)))
+    prm = dict(np.load(os.path.join(golden_dir, "head_5w5s.npz")))
+    head = mft_b200.GnnHead(5, n_support, compress=compress)
+    head.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in prm.items() if k.startswith("p.")})
+    head = head.cuda()
+    head.n_query = 15
+    feat = torch.from_numpy(rec["feat15"] if "feat15" in rec else rec["feat"]).cuda()
+    want = rec["scores15"] if "scores15" in rec else rec["scores"]
+    for prec, tol in (("fp32", 2e-5), ("tf32", 2e-3)):
+        mft_b200.set_precision(prec)
+        with torch.no_grad():
+            got = head.set_forward(feat).cpu().numpy()
+        assert got.shape == want.shape
+        assert U.rel(got, want) < tol, (prec, U.rel(got, want))
+    mft_b200.set_precision("auto")
+
+
+def test_cuda_graph_replay_equals_eager():
+    import mft_b200
+    mft_b200.set_precision("tf32")
+    torch.manual_seed(1)
+    head = mft_b200.GnnHead(5, 5).cuda()
+    head.n_query = 16
+    params = list(head.parameters())
+    feats = [torch.randn(5, 21, 512, device="cuda") for _ in range(3)]
+    step = mft_b200.GraphedStep(lambda f: head.set_forward_loss(f), [feats[0]], params, inputs_require_grad=False)
+    for f in feats:
+        loss_g = float(step(f))
+        grads_g = [p.grad.clone() for p in params]
+        for p in params:
+            p.grad = None
+        loss_e = head.set_forward_loss(f)
+        loss_e.backward()
+        assert abs(loss_g - float(loss_e.detach())) < 1e-5
+        for a, p in zip(grads_g, params):
+            den = float(p.grad.norm())
+            if den > 1e-6:      # atomics reorder sums between runs: tiny differences only
+                assert float((a - p.grad).norm()) / den < 5e-3
+        for p in params:
+            p.grad = None
+    mft_b200.set_precision("auto")

@@ -115,14 +115,16 @@ size_t mft_wcompute_workspace_bytes(int B, int N, int F, int nf);
  * [B,N,N,2] is stack(identity, adj); the identity half is built by the host. */
 int mft_wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf,
                      const mft_wcompute_params* p, float* adj,
-                     void* saved, void* workspace, int precision, void* stream);
+                     void* saved, void* workspace, int precision,
+                     const unsigned char* shared_nodes, void* stream);
 
 /* Backward: d_adj [B,N,N] -> dx (ACCUMULATED into dx[(b*N+n)*ldx + f], f < F)
  * and parameter gradients (overwritten). */
 int mft_wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf,
                      const mft_wcompute_params* p, const float* adj, const float* d_adj,
                      float* dx, const mft_wcompute_grads* g,
-                     void* saved, void* workspace, int precision, void* stream);
+                     void* saved, void* workspace, int precision,
+                     const unsigned char* shared_nodes, void* stream);
 
 /* ---- Gconv: replaces gmul + Gconv.forward (gnn.py:16-28, 43-56) ------------- */
 
@@ -150,12 +152,14 @@ size_t mft_gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way);
 /* x [B,N,F0] contiguous -> out [B,N,n_way] contiguous. */
 int mft_gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way,
                 const mft_gnn_params* p, float* out,
-                void* saved, void* workspace, int precision, void* stream);
+                void* saved, void* workspace, int precision,
+                const unsigned char* shared_nodes, void* stream);
 
 /* d_out [B,N,n_way] -> dx [B,N,F0] (overwritten) + every parameter gradient. */
 int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way,
                 const mft_gnn_params* p, float* dx, const mft_gnn_grads* g,
-                void* saved, void* workspace, int precision, void* stream);
+                void* saved, void* workspace, int precision,
+                const unsigned char* shared_nodes, void* stream);
 
 /* ---- measurement hooks (new; the reference has no profiler) ---- */
 

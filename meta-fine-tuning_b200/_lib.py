@@ -58,9 +58,10 @@ SIGNATURES = {
     "mft_tf32_supported": (_i, [_i, _i]),
     "mft_wcompute_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "mft_wcompute_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "mft_wcompute_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(WcomputeParams), _vp, _vp, _vp, _i, _vp]),
+    "mft_wcompute_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(WcomputeParams), _vp, _vp, _vp, _i, C.c_char_p,
+                              _vp]),
     "mft_wcompute_bwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(WcomputeParams), _vp, _vp, _vp,
-                              C.POINTER(WcomputeGrads), _vp, _vp, _i, _vp]),
+                              C.POINTER(WcomputeGrads), _vp, _vp, _i, C.c_char_p, _vp]),
     "mft_gconv_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "mft_gconv_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mft_gconv_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(GconvParams), _i, _vp, _i, _vp, _vp, _vp]),
@@ -68,9 +69,9 @@ SIGNATURES = {
                            C.POINTER(GconvGrads), _vp, _vp, _vp]),
     "mft_gnn_saved_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mft_gnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "mft_gnn_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, _vp, _vp, _i, _vp]),
+    "mft_gnn_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, _vp, _vp, _i, C.c_char_p, _vp]),
     "mft_gnn_bwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, C.POINTER(GnnGrads), _vp, _vp,
-                         _i, _vp]),
+                         _i, C.c_char_p, _vp]),
     "mft_debug_umma_gemm_workspace_bytes": (_sz, [_i, _i]),
     "mft_debug_umma_gemm": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mft_debug_umma_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),

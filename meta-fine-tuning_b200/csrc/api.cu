@@ -23,9 +23,10 @@ int last_code() { return g_code; }
 size_t gnn_saved_bytes(int B, int N, int F0, int nf, int n_way);
 size_t gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way);
 int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
-            void* saved, void* workspace, int precision, cudaStream_t st);
+            void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st);
 int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* dx,
-            const mft_gnn_grads* g, void* saved, void* workspace, int precision, cudaStream_t st);
+            const mft_gnn_grads* g, void* saved, void* workspace, int precision, const unsigned char* shared_nodes,
+            cudaStream_t st);
 
 // The kernels are compiled for sm_100a only; refuse anything else up front instead of
 // failing with "no kernel image" somewhere in the middle of a call.
@@ -86,18 +87,20 @@ size_t mft_wcompute_workspace_bytes(int B, int N, int F, int nf) {
 }
 
 int mft_wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
-                     float* adj, void* saved, void* workspace, int precision, void* stream) {
+                     float* adj, void* saved, void* workspace, int precision, const unsigned char* shared_nodes,
+                     void* stream) {
     MFT_ENTER();
     MFT_REQUIRE(x && p && adj && saved && workspace, "mft_wcompute_fwd: null pointer");
-    return wcompute_fwd(x, ldx, B, N, F, nf, p, adj, saved, workspace, precision, (cudaStream_t)stream);
+    return wcompute_fwd(x, ldx, B, N, F, nf, p, adj, saved, workspace, precision, shared_nodes,
+                        (cudaStream_t)stream);
 }
 
 int mft_wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
                      const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* g, void* saved,
-                     void* workspace, int precision, void* stream) {
+                     void* workspace, int precision, const unsigned char* shared_nodes, void* stream) {
     MFT_ENTER();
     MFT_REQUIRE(x && p && adj && d_adj && dx && g && saved && workspace, "mft_wcompute_bwd: null pointer");
-    return wcompute_bwd(x, ldx, B, N, F, nf, p, adj, d_adj, dx, g, saved, workspace, precision,
+    return wcompute_bwd(x, ldx, B, N, F, nf, p, adj, d_adj, dx, g, saved, workspace, precision, shared_nodes,
                         (cudaStream_t)stream);
 }
 
@@ -131,17 +134,20 @@ size_t mft_gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way) {
 }
 
 int mft_gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
-                void* saved, void* workspace, int precision, void* stream) {
+                void* saved, void* workspace, int precision, const unsigned char* shared_nodes, void* stream) {
     MFT_ENTER();
     MFT_REQUIRE(x && p && out && saved && workspace, "mft_gnn_fwd: null pointer");
-    return gnn_fwd(x, B, N, F0, nf, n_way, p, out, saved, workspace, precision, (cudaStream_t)stream);
+    return gnn_fwd(x, B, N, F0, nf, n_way, p, out, saved, workspace, precision, shared_nodes,
+                   (cudaStream_t)stream);
 }
 
 int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* dx,
-                const mft_gnn_grads* g, void* saved, void* workspace, int precision, void* stream) {
+                const mft_gnn_grads* g, void* saved, void* workspace, int precision,
+                const unsigned char* shared_nodes, void* stream) {
     MFT_ENTER();
     MFT_REQUIRE(d_out && p && dx && g && saved && workspace, "mft_gnn_bwd: null pointer");
-    return gnn_bwd(d_out, B, N, F0, nf, n_way, p, dx, g, saved, workspace, precision, (cudaStream_t)stream);
+    return gnn_bwd(d_out, B, N, F0, nf, n_way, p, dx, g, saved, workspace, precision, shared_nodes,
+                   (cudaStream_t)stream);
 }
 
 size_t mft_debug_umma_gemm_workspace_bytes(int N, int K) { return (umma_wimg_floats(N, K) + 64) * sizeof(float); }

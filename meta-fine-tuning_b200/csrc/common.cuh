@@ -50,18 +50,45 @@ int last_code();
 // ---------------------------------------------------------------------------
 struct PairGeom {
     int B, N, Rg, R;
+    int Rs, Rq;       // shared rows (one for all B graphs) / per-graph rows; Rs = 0, Rq = Rg without sharing
     double inv_pairs;
-    const int* tri;   // [Rg] packed (j << 16) | i, filled by tri_table_kernel
+    const int* tri;   // [Rg] packed (j << 16) | i: the Rs shared pairs first, then the Rq per-graph ones
+    const int* inv;   // [N*N] (i <= j): index into the per-graph part, or -1 - index into the shared part
 };
 
-inline PairGeom make_geom(int B, int N, const int* tri) {
+// Shared nodes (include/mft_gnn.h, `shared_nodes`): node n is "shared" when x[b, n, :] is the same
+// row for every graph b -- the support nodes of GnnNet's graphs (gnnnet.py:79-80 replicates them
+// into each query's graph).  A pair of two shared nodes has the same edge features in all B graphs,
+// so it gets ONE row standing for B (diagonal) or 2B (off-diagonal) ordered pairs of the reference's
+// dense tensor.  The mask travels by value (kernel parameter), one bit per node.
+constexpr int kMaxMaskNodes = 1024;
+struct NodeMask {
+    uint32_t w[kMaxMaskNodes / 32];
+};
+
+inline int mask_from_host(const unsigned char* shared_nodes, int B, int N, NodeMask& m) {
+    for (int q = 0; q < kMaxMaskNodes / 32; ++q) m.w[q] = 0u;
+    if (shared_nodes == nullptr || B < 2 || N > kMaxMaskNodes) return 0;
+    int S = 0;
+    for (int n = 0; n < N; ++n)
+        if (shared_nodes[n]) {
+            m.w[n >> 5] |= 1u << (n & 31);
+            ++S;
+        }
+    return S;
+}
+
+inline PairGeom make_geom(int B, int N, const int* tri, const int* inv = nullptr, int n_shared = 0) {
     PairGeom g;
     g.B = B;
     g.N = N;
     g.Rg = N * (N + 1) / 2;
-    g.R = B * g.Rg;
+    g.Rs = n_shared * (n_shared + 1) / 2;
+    g.Rq = g.Rg - g.Rs;
+    g.R = g.Rs + B * g.Rq;
     g.inv_pairs = 1.0 / ((double)B * (double)N * (double)N);
     g.tri = tri;
+    g.inv = inv;
     return g;
 }
 
@@ -79,21 +106,39 @@ __device__ __forceinline__ void decode_local(int rl, int N, int& i, int& j) {
 
 struct PairRow {
     int b, i, j;
-    float w;   // multiplicity: 1 diagonal, 2 off-diagonal, 0 past the end
+    int nb;    // graphs the row stands for: 1, or B for a shared pair (then b = 0)
+    float w;   // multiplicity in the reference's dense tensor: nb (diagonal) or 2*nb; 0 past the end
 };
 
 __device__ __forceinline__ PairRow decode_row(int r, const PairGeom& g) {
     PairRow p;
     if (r >= g.R) {
-        p.b = 0; p.i = 0; p.j = 0; p.w = 0.f;
+        p.b = 0; p.i = 0; p.j = 0; p.nb = 0; p.w = 0.f;
         return p;
     }
-    p.b = r / g.Rg;
-    int packed = __ldg(g.tri + (r - p.b * g.Rg));
+    int t;
+    if (r < g.Rs) {
+        p.b = 0; p.nb = g.B; t = r;
+    } else {
+        int rr = r - g.Rs;
+        p.b = rr / g.Rq; p.nb = 1; t = g.Rs + (rr - p.b * g.Rq);
+    }
+    int packed = __ldg(g.tri + t);
     p.i = packed & 0xffff;
     p.j = packed >> 16;
-    p.w = (p.i == p.j) ? 1.f : 2.f;
+    p.w = (float)((p.i == p.j) ? p.nb : 2 * p.nb);
     return p;
+}
+
+// Row of the unordered pair {i <= j} of graph b; `shared` tells whether it is a shared row.
+__device__ __forceinline__ int pair_row(const PairGeom& g, int b, int i, int j, bool& shared) {
+    if (g.Rs == 0) {
+        shared = false;
+        return b * g.Rg + tri_start(i, g.N) + (j - i);
+    }
+    int q = __ldg(g.inv + i * g.N + j);
+    shared = q < 0;
+    return shared ? (-1 - q) : (g.Rs + b * g.Rq + q);
 }
 
 __device__ __forceinline__ float lrelu(float y) { return y > 0.f ? y : y * kSlope; }

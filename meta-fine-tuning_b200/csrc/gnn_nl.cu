@@ -64,7 +64,7 @@ size_t gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way) {
 }
 
 int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
-            void* saved, void* workspace, int precision, cudaStream_t st) {
+            void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st) {
     MFT_REQUIRE(B > 0 && N > 0 && F0 > 0 && nf >= 2 && (nf % 2) == 0 && n_way > 0, "gnn_fwd: bad shape");
     GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace);
     const int rows = B * N;
@@ -72,7 +72,7 @@ int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_g
                                      rows, cudaMemcpyDeviceToDevice, st));
     for (int l = 0; l < G.L; ++l) {
         int rc = wcompute_fwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.wc_saved[l], G.sub_ws,
-                              precision, st);
+                              precision, l == 0 ? shared_nodes : nullptr, st);   // later layers see per-graph features
         if (rc != MFT_OK) return rc;
         const bool last = (l == G.L - 1);
         float* dst = last ? out : G.xcat + G.F[l];
@@ -85,7 +85,8 @@ int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_g
 }
 
 int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* dx,
-            const mft_gnn_grads* g, void* saved, void* workspace, int precision, cudaStream_t st) {
+            const mft_gnn_grads* g, void* saved, void* workspace, int precision, const unsigned char* shared_nodes,
+            cudaStream_t st) {
     MFT_REQUIRE(B > 0 && N > 0 && F0 > 0 && nf >= 2 && (nf % 2) == 0 && n_way > 0, "gnn_bwd: bad shape");
     GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace);
     const int rows = B * N;
@@ -100,7 +101,7 @@ int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const m
                            G.dxcat, G.d_adj, &g->l[l], G.gc_saved[l], G.sub_ws, st);
         if (rc != MFT_OK) return rc;
         rc = wcompute_bwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.d_adj, G.dxcat, &g->w[l],
-                          G.wc_saved[l], G.sub_ws, precision, st);
+                          G.wc_saved[l], G.sub_ws, precision, l == 0 ? shared_nodes : nullptr, st);
         if (rc != MFT_OK) return rc;
     }
     MFT_CHECK_CUDA(cudaMemcpy2DAsync(dx, sizeof(float) * F0, G.dxcat, sizeof(float) * G.ldx, sizeof(float) * F0,

@@ -939,8 +939,8 @@ struct WgradShape {
     int reverse;
     int raw_stages;    // raw slab ring depth (TMA operands), 0 = register path
     int raw_bytes;     // bytes of one raw stage: [dy fp32 | H fp16 | Hq fp16] slabs of 32 rows
-    int copies;        // dW is `copies` partial accumulators `copy_stride` floats apart (CTA b -> b % copies)
-    int copy_stride;
+    int copies;        // > 1: every CTA stores its partial dW into its own copy, `copy_stride` floats apart
+    int copy_stride;   //      (dW 16-byte aligned, ldw % 4 == 0); 1: atomic accumulation into dW
 };
 
 static inline size_t wgrad_smem_bytes(const WgradShape& s) {
@@ -1220,9 +1220,16 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                     const int co = co_base + l;
                     if (l >= lane_lo && co < s.Cout && col < s.Cin) {
                         const float* sp = stage + l * UM_STAGE_LD + c4;
-                        float* gp = dW + (size_t)(blockIdx.x % s.copies) * s.copy_stride + (size_t)co * ldw + col;
-                        const int nv = min(4, s.Cin - col);
-                        for (int e = 0; e < nv; ++e) atomicAdd(gp + e, sp[e]);
+                        if (s.copies > 1) {
+                            // private partial per CTA, plain 16-byte stores (rows padded to 4 floats);
+                            // finalize_grads_kernel adds the copies up in a fixed order
+                            float* gp = dW + (size_t)blockIdx.x * s.copy_stride + (size_t)co * ldw + col;
+                            *reinterpret_cast<float4*>(gp) = *reinterpret_cast<const float4*>(sp);
+                        } else {
+                            float* gp = dW + (size_t)co * ldw + col;
+                            const int nv = min(4, s.Cin - col);
+                            for (int e = 0; e < nv; ++e) atomicAdd(gp + e, sp[e]);
+                        }
                     }
                 }
                 named_bar_sync(1, 128);
@@ -1395,10 +1402,14 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
 
 template <class POp, class QOp>
 static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R, int Cout, int Cin,
-                      cudaStream_t st, int cat, int copies = 1) {
+                      cudaStream_t st, int cat, int* copies_out = nullptr) {
     WgradShape s{};
     s.R = R; s.Cout = Cout; s.Cin = Cin;
-    s.copies = copies; s.copy_stride = Cout * Cin;
+    s.copy_stride = Cout * ldw;
+    if (copies_out && (ldw % 4 != 0 || (reinterpret_cast<uintptr_t>(dW) & 15) != 0)) {
+        set_error(MFT_ERR_ARG, "umma_wgrad: partial copies need 16-byte aligned rows (ldw=%d)", ldw);
+        return MFT_ERR_ARG;
+    }
     s.PB = cdiv(Cout, UM_KB);
     s.QB = cdiv(Cin, UM_KB);
     s.N_TILE = (Cin + 15) & ~15;
@@ -1432,8 +1443,10 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
         return MFT_ERR_UNSUPPORTED;
     }
     const int nchunks = cdiv(R, WG_ROWS);
-    const int grid = min(nchunks, num_sms());
+    const int grid = min(nchunks, min(num_sms(), kWgMaxCopies));
     s.chunks_per_cta = cdiv(nchunks, grid);
+    s.copies = copies_out ? max(2, cdiv(nchunks, s.chunks_per_cta)) : 1;   // (a one-CTA launch still stores)
+    if (copies_out) *copies_out = cdiv(nchunks, s.chunks_per_cta);
     s.reverse = next_direction();
     size_t smem = wgrad_smem_bytes(s);
     MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<POp, QOp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1548,20 +1561,21 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
 // twin-summed gradient of each unordered pair, so the same formula serves both ends of a pair.
 __global__ void __launch_bounds__(256)
 dx_gather_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
-                 int ldx, int F, int N, int Rg) {
+                 int ldx, int F, PairGeom g) {
+    const int N = g.N;
     const int node = blockIdx.x;            // b*N + n
     const int b = node / N, n = node - b * N;
     const float* xn = x + (size_t)node * ldx;
-    const __nv_bfloat16* Db = dD + (size_t)b * Rg * ldd;
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
         const float xv = xn[f];
         float acc = 0.f;
         for (int m = 0; m < N; ++m) {
             if (m == n) continue;
-            const int i = min(n, m), j = max(n, m);
-            const int r = tri_start(i, N) + (j - i);
+            bool shared;
+            const int r = pair_row(g, b, min(n, m), max(n, m), shared);
+            if (shared && b != 0) continue;   // a shared pair's (graph-summed) gradient lands in graph 0's copy
             const float df = xv - __ldg(x + (size_t)(b * N + m) * ldx + f);
-            const float d = __bfloat162float(__ldg(Db + (size_t)r * ldd + f));
+            const float d = __bfloat162float(__ldg(dD + (size_t)r * ldd + f));
             acc += (df > 0.f) ? d : ((df < 0.f) ? -d : 0.f);
         }
         dx[(size_t)node * ldx + f] += acc;
@@ -1572,8 +1586,9 @@ dx_gather_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __r
 // partner nodes m (four independent load streams per thread, combined through shared memory).
 __global__ void __launch_bounds__(256)
 dx_gather_vec_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
-                     int ldx, int F, int N, int Rg) {
+                     int ldx, int F, PairGeom g) {
     __shared__ float4 part[4][64];
+    const int N = g.N;
     const int node = blockIdx.x;
     const int b = node / N, n = node - b * N;
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
@@ -1581,15 +1596,16 @@ dx_gather_vec_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float*
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f < F) {
         const float4 xv = ldg4(x + (size_t)node * ldx + f);
-        const __nv_bfloat16* Db = dD + (size_t)b * Rg * ldd + f;
+        const __nv_bfloat16* Df = dD + f;
         const float* xb = x + (size_t)b * N * ldx + f;
 #pragma unroll 4
         for (int m = ty; m < N; m += 4) {
             if (m == n) continue;
-            const int i = min(n, m), j = max(n, m);
-            const int r = tri_start(i, N) + (j - i);
+            bool shared;
+            const int r = pair_row(g, b, min(n, m), max(n, m), shared);
+            if (shared && b != 0) continue;
             const float4 xm = ldg4(xb + (size_t)m * ldx);
-            const float4 d = unpack_bf4(ldg8(Db + (size_t)r * ldd));
+            const float4 d = unpack_bf4(ldg8(Df + (size_t)r * ldd));
             acc.x += (xv.x > xm.x) ? d.x : ((xv.x < xm.x) ? -d.x : 0.f);
             acc.y += (xv.y > xm.y) ? d.y : ((xv.y < xm.y) ? -d.y : 0.f);
             acc.z += (xv.z > xm.z) ? d.z : ((xv.z < xm.z) ? -d.z : 0.f);
@@ -1629,10 +1645,10 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
         // beyond-F lanes of the last float4 read padding that is masked on the way out
         if (absdiff_vec_ok(x, ldx, F) && F <= 256)
             dx_gather_vec_kernel<<<g.B * g.N, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(L.dD), ldd, x, dx,
-                                                            ldx, F, g.N, g.Rg);
+                                                            ldx, F, g);
         else
             dx_gather_kernel<<<g.B * g.N, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(L.dD), ldd, x, dx,
-                                                        ldx, F, g.N, g.Rg);
+                                                        ldx, F, g);
         MFT_CHECK_LAUNCH();
         return MFT_OK;
     }
@@ -1646,7 +1662,7 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
 // wgrad of conv layer k: d conv2d_{k+1}.weight [Cout, Cin] += dH_k^T a_k (a_0 = |x_i - x_j|).
 int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, int F,
                               const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
-                              const PairGeom& g, cudaStream_t st) {
+                              const PairGeom& g, int* copies, cudaStream_t st) {
     const int Cout = L.C[k + 1], Cin = L.C[k];
     DhT P{};
     int rc = make_tmap_2d(&P.tmap_dy, dh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.R, Cout, Cout, Cout, WG_ROWS,
@@ -1659,7 +1675,7 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
     P.bsums = L.bsums + (size_t)k * kStatSlot; P.inv_count = g.inv_pairs; P.g = g;
     if (k == 0) {
         AbsDiffU Q{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
-        return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[0], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1, kWgCopies);
+        return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[0], (Cin + 3) & ~3, g.R, Cout, Cin, st, PC_WGRAD_L1, copies);
     }
     BnActQT Q{};
     rc = make_tmap_2d(&Q.tmap_h, L.H[k - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g.R, Cin, Cin, Cin, WG_ROWS,
@@ -1667,7 +1683,7 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
     if (rc != MFT_OK) return rc;
     Q.C = Cin; Q.sums = L.fsums + (size_t)(k - 1) * kStatSlot; Q.gamma = p->bn_g[k - 1]; Q.beta = p->bn_b[k - 1];
     Q.inv_count = g.inv_pairs;
-    return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[k], Cin, g.R, Cout, Cin, st, PC_WGRAD_L1 + k, kWgCopies);
+    return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[k], (Cin + 3) & ~3, g.R, Cout, Cin, st, PC_WGRAD_L1 + k, copies);
 }
 
 // Debug / test entry: C[M, N] = A[M, K] * op(W)^T through the tcgen05 rows kernel with plain

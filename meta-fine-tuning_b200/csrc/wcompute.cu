@@ -205,19 +205,44 @@ struct EpiDx {
 
 // =========================== small kernels ===================================
 
-__global__ void tri_table_kernel(int* tri, int N, int Rg) {
+// Pair tables (common.cuh): tri lists the Rs shared pairs first, then the Rq per-graph pairs, each
+// in row-major (i, j >= i) order; inv maps (i, j) back.  With no shared node this is the plain
+// triangular enumeration.  The rank of a pair among the shared (or the other) pairs is a closed form
+// of s(n) = number of shared nodes below n.
+__device__ __forceinline__ int shared_below(const NodeMask& m, int n) {
+    int c = 0;
+    for (int q = 0; q < (n >> 5); ++q) c += __popc(m.w[q]);
+    return c + __popc(m.w[n >> 5] & ((1u << (n & 31)) - 1u));
+}
+
+__global__ void tri_table_kernel(int* tri, int* inv, int N, int Rg, int Rs, int n_shared, NodeMask mask) {
     int rl = blockIdx.x * blockDim.x + threadIdx.x;
     if (rl >= Rg) return;
     int i, j;
     decode_local(rl, N, i, j);
-    tri[rl] = (j << 16) | i;
+    const int packed = (j << 16) | i;
+    if (Rs == 0) {
+        tri[rl] = packed;
+        inv[i * N + j] = rl;
+        return;
+    }
+    const bool mi = (mask.w[i >> 5] >> (i & 31)) & 1u, mj = (mask.w[j >> 5] >> (j & 31)) & 1u;
+    const int si = shared_below(mask, i), sj = shared_below(mask, j);
+    const int before = si * n_shared - (si * (si - 1)) / 2 + (mi ? (sj - si) : 0);   // shared pairs ahead of (i,j)
+    if (mi && mj) {
+        tri[before] = packed;
+        inv[i * N + j] = -1 - before;
+    } else {
+        tri[Rs + rl - before] = packed;
+        inv[i * N + j] = rl - before;
+    }
 }
 
 constexpr int kRowWarps = 8;   // warps per CTA in the warp-per-row kernels
 constexpr int kChPerLane = kMaxC / 32;
 
 // S[b,i,j] = S[b,j,i] = conv2d_last(LeakyReLU(BN4(H4[r])))   (gnn.py:99-103)
-template <bool HalfTape>
+template <bool HalfTape, bool Shared>
 __global__ void __launch_bounds__(kRowWarps * 32)
 score_kernel(const void* __restrict__ H4, int C, const double* sums, const float* gamma, const float* beta,
              const float* last_w, const float* last_b, PairGeom g, float* __restrict__ S) {
@@ -245,18 +270,22 @@ score_kernel(const void* __restrict__ H4, int C, const double* sums, const float
         }
         acc = warp_sum(acc);
         acc2 = warp_sum(acc2);
-        if (lane == 0) {
+        if (Shared || lane == 0) {   // a shared pair's score goes to every graph (lanes over the graphs)
             PairRow p = decode_row(r, g);
             float v = acc + bias;
-            size_t base = (size_t)p.b * g.N * g.N;
-            S[base + (size_t)p.i * g.N + p.j] = v;
-            S[base + (size_t)p.j * g.N + p.i] = v;
+            for (int b = p.b + lane; b < p.b + p.nb; b += 32) {
+                size_t base = (size_t)b * g.N * g.N;
+                S[base + (size_t)p.i * g.N + p.j] = v;
+                S[base + (size_t)p.j * g.N + p.i] = v;
+            }
             if (has2) {
                 PairRow q = decode_row(r2, g);
                 float v2 = acc2 + bias;
-                size_t base2 = (size_t)q.b * g.N * g.N;
-                S[base2 + (size_t)q.i * g.N + q.j] = v2;
-                S[base2 + (size_t)q.j * g.N + q.i] = v2;
+                for (int b = q.b + lane; b < q.b + q.nb; b += 32) {
+                    size_t base2 = (size_t)b * g.N * g.N;
+                    S[base2 + (size_t)q.i * g.N + q.j] = v2;
+                    S[base2 + (size_t)q.j * g.N + q.i] = v2;
+                }
             }
         }
     }
@@ -308,7 +337,7 @@ softmax_bwd_kernel(const float* __restrict__ adj, const float* __restrict__ d_ad
 // Backward through conv2d_last and the layer-4 LeakyReLU:
 //   G_r = dS_ij + dS_ji, dy4 = G_r * w_last * lrelu'(y4); reductions sum dy4, sum dy4*hhat4,
 //   sum G_r * a4 (= d conv2d_last.weight).  One warp per row, lanes over channels.
-template <bool HalfTape>
+template <bool HalfTape, bool Shared>
 __global__ void __launch_bounds__(kRowWarps * 32)
 dy4_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, const double* fsums,
            const float* gamma, const float* beta, const float* last_w, PairGeom g, void* __restrict__ dy4,
@@ -334,10 +363,20 @@ dy4_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, con
         for (int u = 0; u < RU; ++u) {
             const int r = min(r0 + u * stride, g.R - 1);
             PairRow p = decode_row(r, g);
-            size_t base = (size_t)p.b * g.N * g.N;
-            float a = __ldg(dS + base + (size_t)p.i * g.N + p.j);
-            float b2 = __ldg(dS + base + (size_t)p.j * g.N + p.i);
-            G[u] = (p.i != p.j) ? a + b2 : a;
+            if (!Shared || p.nb == 1) {   // (Shared is a template switch: the branch would serialise the loads)
+                size_t base = (size_t)p.b * g.N * g.N;
+                float a = __ldg(dS + base + (size_t)p.i * g.N + p.j);
+                float b2 = __ldg(dS + base + (size_t)p.j * g.N + p.i);
+                G[u] = (p.i != p.j) ? a + b2 : a;
+            } else {   // shared pair: the row's gradient is the sum over the graphs it stands for
+                float a = 0.f;
+                for (int b = lane; b < p.nb; b += 32) {
+                    size_t base = (size_t)b * g.N * g.N;
+                    a += __ldg(dS + base + (size_t)p.i * g.N + p.j);
+                    if (p.i != p.j) a += __ldg(dS + base + (size_t)p.j * g.N + p.i);
+                }
+                G[u] = warp_sum(a);
+            }
 #pragma unroll
             for (int q = 0; q < kChPerLane; ++q) {
                 int c = lane + 32 * q;
@@ -407,9 +446,11 @@ dh_kernel(float* __restrict__ dy, const float* __restrict__ H, int C, const doub
 }
 
 struct FinalizeArgs {
-    const float* wgpart[4];   // tcgen05 path: kWgCopies partial weight gradients per layer (else null)
+    const float* wgpart[4];   // tcgen05 path: ncopies[k] partial weight gradients per layer (else null)
+    int ncopies[4];
     float* conv_w[4];
     int wsize[4];
+    int cin[4];
     const double* bsums[4];
     const double* lastsum;
     float* bn_g[4];
@@ -432,15 +473,53 @@ __global__ void finalize_grads_kernel(FinalizeArgs a) {
     }
     if (t < a.nf && a.last_w) a.last_w[t] = (float)stat_get(a.lastsum, a.nf, t, 0);
     if (t == 0 && a.last_b) a.last_b[0] = 0.f;         // softmax shift invariance: exactly zero
-    // conv weight gradients: add up the partial copies the wgrad CTAs accumulated into
-    for (int k = 0; k < 4; ++k) {
-        if (a.wgpart[k] == nullptr) continue;
-        for (int i = t; i < a.wsize[k]; i += gridDim.x * blockDim.x) {
-            float v = 0.f;
-#pragma unroll
-            for (int q = 0; q < kWgCopies; ++q) v += a.wgpart[k][(size_t)q * a.wsize[k] + i];
-            a.conv_w[k][i] = v;
+}
+
+// Conv weight gradients of the tcgen05 path: add up the partial copies the wgrad CTAs stored.  One CTA
+// per (layer, output channel) row; thread (cx, cy) sums copies cy, cy+S, ... of float4 column cx, the
+// S slices are combined through shared memory in a fixed order (bitwise reproducible result).
+constexpr int kRedThreads = 256;
+__global__ void __launch_bounds__(kRedThreads)
+wgrad_reduce_kernel(FinalizeArgs a) {
+    __shared__ float4 part[kRedThreads];
+    int k = 0, co = blockIdx.x;
+    while (k < 4 && co >= a.wsize[k] / a.cin[k]) { co -= a.wsize[k] / a.cin[k]; ++k; }
+    if (k == 4 || a.wgpart[k] == nullptr) return;
+    const int cin = a.cin[k], ldp = (cin + 3) & ~3, cout = a.wsize[k] / cin, nc = a.ncopies[k];
+    const int ncol4 = ldp / 4;                       // <= 64
+    const int slices = kRedThreads / ncol4;
+    const int cx = threadIdx.x % ncol4, cy = threadIdx.x / ncol4;
+    const size_t cstride = (size_t)cout * ldp;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cy < slices) {
+        const float* src = a.wgpart[k] + (size_t)co * ldp + cx * 4;
+        int q = cy;
+        for (; q + 3 * slices < nc; q += 4 * slices) {   // four independent 16-byte loads in flight
+            float4 v0 = __ldcs(reinterpret_cast<const float4*>(src + (size_t)q * cstride));
+            float4 v1 = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(q + slices) * cstride));
+            float4 v2 = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(q + 2 * slices) * cstride));
+            float4 v3 = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(q + 3 * slices) * cstride));
+            acc.x += (v0.x + v1.x) + (v2.x + v3.x);
+            acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+            acc.z += (v0.z + v1.z) + (v2.z + v3.z);
+            acc.w += (v0.w + v1.w) + (v2.w + v3.w);
         }
+        for (; q < nc; q += slices) {
+            float4 v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)q * cstride));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (cy == 0) {
+        for (int sl = 1; sl < slices; ++sl) {
+            float4 v = part[sl * ncol4 + cx];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float* dst = a.conv_w[k] + (size_t)co * cin + cx * 4;
+        const float o[4] = {acc.x, acc.y, acc.z, acc.w};
+        for (int e = 0; e < 4; ++e)
+            if (cx * 4 + e < cin) dst[e] = o[e];
     }
 }
 
@@ -459,6 +538,7 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     L.saved_bytes = sv.used();
     Carver ws(workspace);
     L.tri = ws.take<int>(Rg);
+    L.inv = ws.take<int>((size_t)N * N);
     L.S = ws.take<float>((size_t)B * N * N);
     L.dyA = ws.take<float>(R * 2 * nf);
     L.dyB = ws.take<float>(R * 2 * nf);
@@ -469,7 +549,7 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
         size_t tot = 0;
         for (int k = 0; k < 4; ++k) {
             L.wgpart_off[k] = tot;
-            tot += (size_t)kWgCopies * L.C[k + 1] * L.C[k];
+            tot += (size_t)kWgMaxCopies * L.C[k + 1] * ((L.C[k] + 3) & ~3);   // rows padded to 4 floats
         }
         L.wgpart = ws.take<float>(umma_shape_supported(F, nf) ? tot : 0);
         L.wgpart_floats = tot;
@@ -479,18 +559,20 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
 }
 
 int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p, float* adj,
-                 void* saved, void* workspace, int precision, cudaStream_t st) {
+                 void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st) {
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_fwd: bad shape B=%d N=%d F=%d nf=%d", B, N, F, nf);
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_fwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
     MFT_REQUIRE(N < 32768, "wcompute_fwd: N=%d too large", N);
     MFT_REQUIRE(ldx >= F, "wcompute_fwd: ldx=%d < F=%d", ldx, F);
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
-    PairGeom g = make_geom(B, N, L.tri);
+    NodeMask mask;
+    const int n_shared = mask_from_host(shared_nodes, B, N, mask);
+    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared);
 
     MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 4 * kStatSlot, st));
     {
         ProfScope ps(PC_PREP, st);
-        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
+        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, N, g.Rg, g.Rs, n_shared, mask);
         MFT_CHECK_LAUNCH();
     }
 
@@ -515,14 +597,16 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     }
     {
         ProfScope ps(PC_SCORE, st);
-        if (precision == MFT_PREC_TF32)
-            score_kernel<true><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * kStatSlot,
-                                                                          p->bn_g[3], p->bn_b[3], p->last_w,
-                                                                          p->last_b, g, L.S);
-        else
-            score_kernel<false><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * kStatSlot,
-                                                                           p->bn_g[3], p->bn_b[3], p->last_w,
-                                                                           p->last_b, g, L.S);
+#define MFT_SCORE(HALF, SHARED)                                                                                   \
+    score_kernel<HALF, SHARED><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * kStatSlot,         \
+                                                                         p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, \
+                                                                         g, L.S)
+        if (precision == MFT_PREC_TF32) {
+            if (g.Rs > 0) MFT_SCORE(true, true); else MFT_SCORE(true, false);
+        } else {
+            if (g.Rs > 0) MFT_SCORE(false, true); else MFT_SCORE(false, false);
+        }
+#undef MFT_SCORE
         MFT_CHECK_LAUNCH();
     }
     {
@@ -535,22 +619,23 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
 
 int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
                  const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* gr, void* saved,
-                 void* workspace, int precision, cudaStream_t st) {
+                 void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st) {
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_bwd: bad shape");
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_bwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
-    PairGeom g = make_geom(B, N, L.tri);
+    NodeMask mask;
+    const int n_shared = mask_from_host(shared_nodes, B, N, mask);
+    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared);
 
     MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * kStatSlot, st));
-    if (precision == MFT_PREC_TF32) {
-        MFT_CHECK_CUDA(cudaMemsetAsync(L.wgpart, 0, sizeof(float) * L.wgpart_floats, st));
-    } else {
+    int wg_copies[4] = {0, 0, 0, 0};
+    if (precision != MFT_PREC_TF32) {
         for (int k = 0; k < 4; ++k)
             MFT_CHECK_CUDA(cudaMemsetAsync(gr->conv_w[k], 0, sizeof(float) * (size_t)L.C[k + 1] * L.C[k], st));
     }
     {
         ProfScope ps(PC_PREP, st);
-        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, N, g.Rg);
+        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, N, g.Rg, g.Rs, n_shared, mask);
         MFT_CHECK_LAUNCH();
     }
     {
@@ -561,14 +646,16 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     double* lastsum = L.bsums + 4 * kStatSlot;
     {
         ProfScope ps(PC_DY4, st);
-        if (precision == MFT_PREC_TF32)
-            dy4_kernel<true><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * kStatSlot,
-                                                                        p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA,
-                                                                        L.bsums + 3 * kStatSlot, lastsum);
-        else
-            dy4_kernel<false><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * kStatSlot,
-                                                                         p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA,
-                                                                         L.bsums + 3 * kStatSlot, lastsum);
+#define MFT_DY4(HALF, SHARED)                                                                                  \
+    dy4_kernel<HALF, SHARED><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * kStatSlot,  \
+                                                                       p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA, \
+                                                                       L.bsums + 3 * kStatSlot, lastsum)
+        if (precision == MFT_PREC_TF32) {
+            if (g.Rs > 0) MFT_DY4(true, true); else MFT_DY4(true, false);
+        } else {
+            if (g.Rs > 0) MFT_DY4(false, true); else MFT_DY4(false, false);
+        }
+#undef MFT_DY4
         MFT_CHECK_LAUNCH();
     }
 
@@ -591,7 +678,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             PlainA dh{cur, Cout};
             // wgrad: d conv2d_{k+1}.weight [Cout, Cin] = dH^T a_k
             if (precision == MFT_PREC_TF32) {
-                int rc = wcompute_wgrad_layer_tf32(k, cur, x, ldx, F, p, gr, L, g, st);
+                int rc = wcompute_wgrad_layer_tf32(k, cur, x, ldx, F, p, gr, L, g, &wg_copies[k], st);
                 if (rc != MFT_OK) return rc;
             } else if (k == 0) {
                 ProfScope ps(PC_WGRAD_L1, st);
@@ -634,6 +721,8 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         fa.wgpart[k] = precision == MFT_PREC_TF32 ? L.wgpart + L.wgpart_off[k] : nullptr;
         fa.conv_w[k] = gr->conv_w[k];
         fa.wsize[k] = L.C[k + 1] * L.C[k];
+        fa.cin[k] = L.C[k];
+        fa.ncopies[k] = wg_copies[k];
     }
     fa.lastsum = lastsum;
     fa.last_w = gr->last_w;
@@ -641,8 +730,12 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     fa.nf = nf;
     {
         ProfScope ps(PC_FINALIZE, st);
-        finalize_grads_kernel<<<precision == MFT_PREC_TF32 ? 64 : 1, kMaxC, 0, st>>>(fa);
+        finalize_grads_kernel<<<1, kMaxC, 0, st>>>(fa);
         MFT_CHECK_LAUNCH();
+        if (precision == MFT_PREC_TF32) {
+            wgrad_reduce_kernel<<<L.C[1] + L.C[2] + L.C[3] + L.C[4], kRedThreads, 0, st>>>(fa);
+            MFT_CHECK_LAUNCH();
+        }
     }
     return MFT_OK;
 }

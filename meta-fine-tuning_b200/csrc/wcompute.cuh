@@ -6,21 +6,24 @@
 namespace mft {
 
 // Carved views of the Wcompute `saved` / `workspace` blobs.
-constexpr int kWgCopies = 8;   // same-address fp32 atomics from 148 CTAs serialise in L2; 8 copies -> ~18 per address
+// The tcgen05 wgrad CTAs each store their partial dW into a private copy (plain stores; atomics from
+// 148 CTAs onto one 147 KB matrix cost more than the GEMM); finalize_grads_kernel sums the copies.
+constexpr int kWgMaxCopies = 160;   // >= number of SMs
 
 struct WcLayout {
     int C[5];            // channel widths: F, 2nf, 2nf, nf, nf
     float* H[4];         // saved: pre-BN activations of the four conv layers, [R, C[k+1]]
     double* fsums;       // saved: forward batch statistics, 4 x [2*kMaxC]
     int* tri;            // workspace: unordered-pair table [Rg]
+    int* inv;            // workspace: (i, j) -> table index [N*N]
     float* S;            // workspace: scores / dS, [B,N,N]
     float* dyA;          // workspace: ping-pong gradient buffers [R, 2nf]
     float* dyB;
     double* bsums;       // workspace: backward reductions, 5 x [2*kMaxC] (last = d conv2d_last.weight)
     float* wimg;         // workspace: swizzled TF32 weight image of the tcgen05 path
     float* dD;           // workspace (tcgen05 path): dL/d|x_i-x_j| per unordered pair, [R, roundup4(F)]
-    float* wgpart;       // workspace (tcgen05 path): kWgCopies partial copies of the four conv-weight gradients
-    size_t wgpart_off[4];  // float offset of layer k's copies inside wgpart (copy stride = C[k+1]*C[k])
+    float* wgpart;       // workspace (tcgen05 path): per-CTA partial copies of the four conv-weight gradients
+    size_t wgpart_off[4];  // float offset of layer k's copies inside wgpart (copy stride = C[k+1]*roundup4(C[k]))
     size_t wgpart_floats;
     size_t saved_bytes, workspace_bytes;
 };
@@ -36,10 +39,10 @@ int umma_debug_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW
 WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace);
 
 int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p, float* adj,
-                 void* saved, void* workspace, int precision, cudaStream_t st);
+                 void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st);
 int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
                  const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* gr, void* saved,
-                 void* workspace, int precision, cudaStream_t st);
+                 void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st);
 
 // tcgen05 (MFT_PREC_TF32) replacements for the four forward layer GEMMs and for the
 // dgrad + wgrad pair of one backward layer; same buffers in and out as the fp32 path.
@@ -52,7 +55,7 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
 int wcompute_bwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, cudaStream_t st);
 int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, int F,
                               const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
-                              const PairGeom& g, cudaStream_t st);
+                              const PairGeom& g, int* copies, cudaStream_t st);
 
 struct GcLayout {
     float* Y;            // saved: pre-BN Gconv output [B*N, n_out]

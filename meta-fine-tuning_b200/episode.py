@@ -67,8 +67,12 @@ class GnnHead(nn.Module):
     ``set_forward(feat)`` is ``GnnNet.set_forward(x, is_feature=True)`` (gnnnet.py:71-87);
     ``set_forward_loss(feat)`` adds the cross-entropy of gnnnet.py:219-224."""
 
-    def __init__(self, n_way: int, n_support: int, feat_dim: int = 512, compress: bool = False):
+    def __init__(self, n_way: int, n_support: int, feat_dim: int = 512, compress: bool = False,
+                 share_support: bool = True):
         super().__init__()
+        # The graphs build_graphs makes differ only in their query nodes: tell GNN_nl so that
+        # layer_w0 evaluates the support-support pairs once (GNN_nl.shared_nodes).
+        self.share_support = share_support
         self.n_way = n_way
         self.n_support_in = n_support
         self.compress = compress
@@ -85,7 +89,14 @@ class GnnHead(nn.Module):
         z = z.view(self.n_way, -1, z.size(1))
         return build_graphs(z, self.support_label, self.n_way, self.n_support_in, self.n_query, self.compress)
 
+    def shared_mask(self):
+        """True for the support nodes of a graph (node order of build_graphs: per class, the
+        supports then the one query)."""
+        return ([True] * self.n_support + [False]) * self.n_way
+
     def forward_gnn_nodes(self, nodes: torch.Tensor) -> torch.Tensor:
+        """``nodes`` must come from ``self.nodes`` / ``build_graphs`` (supports replicated)."""
+        self.gnn.shared_nodes = self.shared_mask() if self.share_support else None
         return select_scores(self.gnn(nodes), self.n_way, self.n_support, self.n_query)
 
     def set_forward(self, feat: torch.Tensor) -> torch.Tensor:

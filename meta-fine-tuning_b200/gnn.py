@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -144,6 +144,18 @@ def _alloc_like_flat(ts: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     return [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, ts)]
 
 
+def _shared_mask(shared_nodes, x) -> Optional[bytes]:
+    """Length-N byte mask for the C ABI (host memory), or None."""
+    if shared_nodes is None:
+        return None
+    if isinstance(shared_nodes, torch.Tensor):
+        shared_nodes = shared_nodes.detach().cpu().tolist()
+    mask = bytes(1 if v else 0 for v in shared_nodes)
+    if len(mask) != x.size(1):
+        raise ValueError("shared_nodes has %d entries for %d nodes" % (len(mask), x.size(1)))
+    return mask if any(mask) else None
+
+
 # ---------------------------------------------------------------------------------
 # autograd functions
 # ---------------------------------------------------------------------------------
@@ -152,7 +164,7 @@ class _WcomputeFn(torch.autograd.Function):
     """adj = softmax_j(edge_mlp(|x_i - x_j|) - 1e8 [i==j])  -- mft_wcompute_fwd / _bwd."""
 
     @staticmethod
-    def forward(ctx, x, nf, prec, *params):
+    def forward(ctx, x, nf, prec, shared, *params):
         lib = _lib.load_library()
         _require_cuda(x, "Wcompute")
         x = x.contiguous()
@@ -165,16 +177,17 @@ class _WcomputeFn(torch.autograd.Function):
         ws = _blob(lib.mft_wcompute_workspace_bytes(B, N, F, nf), x.device)
         with torch.cuda.device(x.device):
             _lib.check(lib.mft_wcompute_fwd(x.data_ptr(), F, B, N, F, nf, C.byref(p), adj.data_ptr(),
-                                            saved.data_ptr(), ws.data_ptr(), prec, _stream()), "mft_wcompute_fwd")
+                                            saved.data_ptr(), ws.data_ptr(), prec, shared, _stream()),
+                       "mft_wcompute_fwd")
         ctx.save_for_backward(x, adj, saved, *params)
-        ctx.meta = (nf, prec)
+        ctx.meta = (nf, prec, shared)
         return adj
 
     @staticmethod
     def backward(ctx, d_adj):
         lib = _lib.load_library()
         x, adj, saved, *params = ctx.saved_tensors
-        nf, prec = ctx.meta
+        nf, prec, shared = ctx.meta
         B, N, F = x.shape
         d_adj = d_adj.contiguous()
         p = _lib.WcomputeParams()
@@ -187,8 +200,8 @@ class _WcomputeFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             _lib.check(lib.mft_wcompute_bwd(x.data_ptr(), F, B, N, F, nf, C.byref(p), adj.data_ptr(),
                                             d_adj.data_ptr(), dx.data_ptr(), C.byref(g), saved.data_ptr(),
-                                            ws.data_ptr(), prec, _stream()), "mft_wcompute_bwd")
-        return (dx, None, None, *grads)
+                                            ws.data_ptr(), prec, shared, _stream()), "mft_wcompute_bwd")
+        return (dx, None, None, None, *grads)
 
 
 class _GconvFn(torch.autograd.Function):
@@ -243,7 +256,7 @@ class _GnnFn(torch.autograd.Function):
     """Whole GNN_nl stack in one library call per direction -- mft_gnn_fwd / _bwd."""
 
     @staticmethod
-    def forward(ctx, x, nf, n_way, prec, *params):
+    def forward(ctx, x, nf, n_way, prec, shared, *params):
         lib = _lib.load_library()
         _require_cuda(x, "GNN_nl")
         x = x.contiguous()
@@ -256,16 +269,16 @@ class _GnnFn(torch.autograd.Function):
         ws = _blob(lib.mft_gnn_workspace_bytes(B, N, F0, nf, n_way), x.device)
         with torch.cuda.device(x.device):
             _lib.check(lib.mft_gnn_fwd(x.data_ptr(), B, N, F0, nf, n_way, C.byref(p), out.data_ptr(),
-                                       saved.data_ptr(), ws.data_ptr(), prec, _stream()), "mft_gnn_fwd")
+                                       saved.data_ptr(), ws.data_ptr(), prec, shared, _stream()), "mft_gnn_fwd")
         ctx.save_for_backward(saved, *params)
-        ctx.meta = (B, N, F0, nf, n_way, prec)
+        ctx.meta = (B, N, F0, nf, n_way, prec, shared)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load_library()
         saved, *params = ctx.saved_tensors
-        B, N, F0, nf, n_way, prec = ctx.meta
+        B, N, F0, nf, n_way, prec, shared = ctx.meta
         d_out = d_out.contiguous()
         p = _lib.GnnParams()
         _pack_gnn(p, params, grads=False)
@@ -276,8 +289,9 @@ class _GnnFn(torch.autograd.Function):
         ws = _blob(lib.mft_gnn_workspace_bytes(B, N, F0, nf, n_way), d_out.device)
         with torch.cuda.device(d_out.device):
             _lib.check(lib.mft_gnn_bwd(d_out.data_ptr(), B, N, F0, nf, n_way, C.byref(p), dx.data_ptr(),
-                                       C.byref(g), saved.data_ptr(), ws.data_ptr(), prec, _stream()), "mft_gnn_bwd")
-        return (dx, None, None, None, *grads)
+                                       C.byref(g), saved.data_ptr(), ws.data_ptr(), prec, shared, _stream()),
+                       "mft_gnn_bwd")
+        return (dx, None, None, None, None, *grads)
 
 
 def _pack_gnn(dst, t: Sequence[torch.Tensor], grads: bool) -> None:
@@ -413,18 +427,18 @@ class Wcompute(nn.Module):
                 "Wcompute: the CUDA path implements the configuration the reference uses everywhere "
                 "(operator='J2', activation='softmax', ratio=[2,2,1,1], num_operators=1, drop=False)")
 
-    def adjacency(self, x):
+    def adjacency(self, x, shared_nodes=None):
         self._check_supported()
         nf = self.num_features
         prec = _resolve_precision([x.size(2)], nf)
-        return _WcomputeFn.apply(x, nf, prec, *_wc_tensors(self))
+        return _WcomputeFn.apply(x, nf, prec, _shared_mask(shared_nodes, x), *_wc_tensors(self))
 
-    def forward(self, x, W_id):
+    def forward(self, x, W_id, shared_nodes=None):
         """x [B,N,F], W_id [B,N,N,1] (identity) -> [B,N,N,2] = cat(W_id, adjacency).
 
         The -1e8 mask of gnn.py:106 is applied on the diagonal, i.e. W_id is taken to
-        be the identity GNN_nl builds (gnn.py:155)."""
-        adj = self.adjacency(x)
+        be the identity GNN_nl builds (gnn.py:155).  ``shared_nodes``: see GNN_nl.shared_nodes."""
+        adj = self.adjacency(x, shared_nodes)
         return torch.cat([W_id, adj.unsqueeze(3)], 3)
 
 
@@ -447,6 +461,15 @@ class GNN_nl(nn.Module):
         self.w_comp_last = Wcompute(fin, nf, operator='J2', activation='softmax', ratio=[2, 2, 1, 1])
         self.layer_last = Gconv(fin, train_N_way, 2, bn_bool=False)
         self.fused = True   # one library call per direction; False = module-by-module
+        # Optional promise from the caller (new; the reference recomputes everything): a length-N
+        # boolean sequence, True where x[b, n, :] is the SAME row in every graph b -- GnnNet's support
+        # nodes (gnnnet.py:79-80 copies them into each query's graph).  layer_w0 then evaluates each
+        # support-support pair once instead of B times: same adjacency, same parameter gradients;
+        # the input gradient of a shared node is delivered SUMMED over the graphs in graph 0's row
+        # (zero contribution from those pairs in the other graphs' rows), which is what the backward
+        # of the caller's replication adds up anyway.  None (default) = no assumption.
+        self.shared_nodes = None
+        self.check_shared = False   # debug: verify the promise on every call (device sync)
 
     def _all_tensors(self) -> List[torch.Tensor]:
         t: List[torch.Tensor] = []
@@ -457,15 +480,23 @@ class GNN_nl(nn.Module):
         t += _gc_tensors(self.layer_last)
         return t
 
+    def _shared(self, x):
+        mask = _shared_mask(self.shared_nodes, x)
+        if mask is not None and self.check_shared:
+            sel = torch.tensor([bool(v) for v in mask], device=x.device)
+            if not torch.equal(x[:, sel], x[:1, sel].expand(x.size(0), -1, -1)):
+                raise ValueError("GNN_nl.shared_nodes marks nodes whose features differ between graphs")
+        return mask
+
     def forward(self, x):
         if self.fused and self.nf % 2 == 0:
             fins = [self.input_features + (self.nf // 2) * i for i in range(self.num_layers + 1)]
             prec = _resolve_precision(fins, self.nf)
-            return _GnnFn.apply(x, self.nf, self.train_N_way, prec, *self._all_tensors())
+            return _GnnFn.apply(x, self.nf, self.train_N_way, prec, self._shared(x), *self._all_tensors())
         # module-by-module (same kernels, one autograd node per module)
         W_init = torch.eye(x.size(1), device=x.device).unsqueeze(0).repeat(x.size(0), 1, 1).unsqueeze(3)
         for i in range(self.num_layers):
-            Wi = self._modules['layer_w{}'.format(i)](x, W_init)
+            Wi = self._modules['layer_w{}'.format(i)](x, W_init, self._shared(x) if i == 0 else None)
             x_new = self._modules['layer_l{}'.format(i)]([Wi, x], _lrelu=True)[1]
             x = torch.cat([x, x_new], 2)
         Wl = self.w_comp_last(x, W_init)

@@ -220,8 +220,14 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     BView X{x, 0, ldx, 1};                           // (m = row, k = f)
     BView Wa{p->fc_w, 0, 1, 2 * F};                  // (k = f, n = c) -> fc_w[c*2F + f]
     BView Wb{p->fc_w + F, 0, 1, 2 * F};
-    { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wa, Y, 0, ldy, 1, rows, n_out, F, 0.f, st)); }
-    { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wb, L.UV, 0, n_out, 1, rows, n_out, F, 0.f, st)); }
+    {
+        Branches br(st);                             // the two products with x are independent
+        cudaStream_t s1 = br.fork(0);
+        { ProfScope ps(PC_GCONV_FWD, s1); MFT_CHECK_CUDA(launch_bgemm(X, Wb, L.UV, 0, n_out, 1, rows, n_out, F, 0.f, s1)); }
+        { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wa, Y, 0, ldy, 1, rows, n_out, F, 0.f, st)); }
+        br.join(0);
+        MFT_REQUIRE(br.ok(), "gconv_fwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     {
         BView Am{adj, (long)N * N, N, 1};            // (m = i, k = j)
         BView Um{L.UV, (long)N * n_out, n_out, 1};   // (k = j, n = c)
@@ -269,17 +275,25 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     { ProfScope ps(PC_GCONV_BWD, st); gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, st>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
     MFT_CHECK_LAUNCH(); }
 
-    // AX = adj x   [B*N, F]
-    BView A{adj, (long)N * N, N, 1};
-    BView X{x, (long)N * ldx, ldx, 1};
-    { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(A, X, L.AX, (long)N * F, F, B, N, F, N, 0.f, st)); }
-
-    // d fc.weight [n_out, 2F] = [dY^T x | dY^T AX]
+    // Three independent chains from here (all read dY):
+    //   side 0:  AX = adj x  ->  d fc.weight[:, F:] = dY^T AX
+    //   side 1:  d fc.weight[:, :F] = dY^T x ; then (after DU) d_adj = DU2 x^T
+    //   main  :  DU = dY W  ->  dx += DU1  ->  dx += adj^T DU2
+    Branches br(st);
+    cudaStream_t s0 = br.fork(0), s1 = br.fork(1);
     PlainOp dy{L.dY, n_out};
-    PlainOp qx{x, ldx};
-    PlainOp qax{L.AX, F};
-    { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, st))); }
-    { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA((launch_gemm_tn(dy, qax, g->fc_w + F, 2 * F, n_out, F, rows, st))); }
+    {
+        // AX = adj x   [B*N, F]
+        BView A{adj, (long)N * N, N, 1};
+        BView X{x, (long)N * ldx, ldx, 1};
+        { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA(launch_bgemm(A, X, L.AX, (long)N * F, F, B, N, F, N, 0.f, s0)); }
+        PlainOp qax{L.AX, F};
+        { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA((launch_gemm_tn(dy, qax, g->fc_w + F, 2 * F, n_out, F, rows, s0))); }
+    }
+    {
+        PlainOp qx{x, ldx};
+        { ProfScope ps(PC_GCONV_BWD, s1); MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, s1))); }
+    }
 
     // DU = dY W  [B*N, 2F]: first half feeds the identity operator, second half the adjacency
     {
@@ -288,7 +302,13 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
         ProfScope ps(PC_GCONV_BWD, st);
         MFT_CHECK_CUDA(launch_bgemm(Dy, Wf, L.DU, 0, 2 * F, 1, rows, 2 * F, n_out, 0.f, st));
     }
-
+    br.sync_to_main(1);                              // side 1 continues once DU exists
+    // d_adj[b,i,j] = sum_f DU2[b,i,f] x[b,j,f]
+    {
+        BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (m=i, k=f)
+        BView Xt{x, (long)N * ldx, 1, ldx};                     // (k=f, n=j) -> x[b, j, f]
+        { ProfScope ps(PC_GCONV_BWD, s1); MFT_CHECK_CUDA(launch_bgemm(D2, Xt, d_adj, (long)N * N, N, B, N, N, F, 0.f, s1)); }
+    }
     // dx += DU1 + adj^T DU2
     {
         int total = rows * F;
@@ -298,12 +318,9 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
         BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (k=i, n=f)
         { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st)); }
     }
-    // d_adj[b,i,j] = sum_f DU2[b,i,f] x[b,j,f]
-    {
-        BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (m=i, k=f)
-        BView Xt{x, (long)N * ldx, 1, ldx};                     // (k=f, n=j) -> x[b, j, f]
-        { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(D2, Xt, d_adj, (long)N * N, N, B, N, N, F, 0.f, st)); }
-    }
+    br.join(0);
+    br.join(1);
+    MFT_REQUIRE(br.ok(), "gconv_bwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
     return MFT_OK;
 }
 

@@ -85,3 +85,67 @@ int mft_prof_collect(float* ms, int* counts, int n) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------- side branches
+namespace mft {
+
+namespace {
+struct SidePool {
+    bool ready = false;
+    cudaStream_t s[kSideStreams];
+    cudaEvent_t main_ev[kSideStreams];   // recorded on the main stream, waited on by side i
+    cudaEvent_t side_ev[kSideStreams];   // recorded on side i, waited on by the main stream
+};
+SidePool g_pools[64];
+std::mutex g_pool_mu;
+
+SidePool* pool_for_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    SidePool& p = g_pools[dev];
+    if (!p.ready) {
+        for (int i = 0; i < kSideStreams; ++i) {
+            if (cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.main_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&p.side_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        p.ready = true;
+    }
+    return &p;
+}
+}  // namespace
+
+Branches::Branches(cudaStream_t main) : main_(main), pool_(pool_for_current_device()), ok_(true) {
+    for (int i = 0; i < kSideStreams; ++i) forked_[i] = false;
+    if (pool_ == nullptr) ok_ = false;
+}
+
+void Branches::sync_to_main(int i) {
+    SidePool* p = static_cast<SidePool*>(pool_);
+    if (!p) return;
+    if (cudaEventRecord(p->main_ev[i], main_) != cudaSuccess) ok_ = false;
+    if (cudaStreamWaitEvent(p->s[i], p->main_ev[i], 0) != cudaSuccess) ok_ = false;
+}
+
+cudaStream_t Branches::fork(int i) {
+    SidePool* p = static_cast<SidePool*>(pool_);
+    if (!p) return main_;               // no pool: everything stays on the caller's stream
+    sync_to_main(i);
+    forked_[i] = true;
+    return p->s[i];
+}
+
+void Branches::join(int i) {
+    SidePool* p = static_cast<SidePool*>(pool_);
+    if (!p || !forked_[i]) return;
+    if (cudaEventRecord(p->side_ev[i], p->s[i]) != cudaSuccess) ok_ = false;
+    if (cudaStreamWaitEvent(main_, p->side_ev[i], 0) != cudaSuccess) ok_ = false;
+    forked_[i] = false;
+}
+
+Branches::~Branches() {
+    for (int i = 0; i < kSideStreams; ++i) join(i);
+}
+
+}  // namespace mft

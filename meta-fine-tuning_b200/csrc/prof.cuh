@@ -33,3 +33,36 @@ struct ProfScope {
 };
 
 }  // namespace mft
+
+// ---------------------------------------------------------------------------------------------
+// Side branches for independent small kernels (the Gconv products run on 16-60 CTAs each; issued
+// back to back on one stream they leave most of the 148 SMs idle).  A Branches object forks up to
+// kSideStreams library-owned non-blocking streams off the caller's stream with events and joins
+// them back before the library call returns, so the caller still sees plain stream order.  Works
+// the same eagerly and under stream capture (the event edges become graph dependencies).  The
+// streams and events are created once per device on first use; nothing is allocated per call.
+// ---------------------------------------------------------------------------------------------
+namespace mft {
+
+constexpr int kSideStreams = 2;
+
+class Branches {
+public:
+    explicit Branches(cudaStream_t main);
+    bool ok() const { return ok_; }
+    // side stream i, ordered after everything enqueued on the main stream so far
+    cudaStream_t fork(int i);
+    // make side stream i wait for the main stream's work enqueued so far
+    void sync_to_main(int i);
+    // main stream waits for side stream i
+    void join(int i);
+    ~Branches();   // joins whatever is still forked
+
+private:
+    cudaStream_t main_;
+    void* pool_;
+    bool forked_[kSideStreams];
+    bool ok_;
+};
+
+}  // namespace mft

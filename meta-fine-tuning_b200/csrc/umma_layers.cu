@@ -275,6 +275,7 @@ struct DhU {
 // 16 KB load in flight.
 struct BnActT {
     static constexpr bool kTma = true;
+    static constexpr bool kInPlace = false;
     static constexpr int kAhead = 0;
     alignas(64) CUtensorMap tmap;
     int C;
@@ -308,6 +309,55 @@ struct BnActT {
         y.z = fmaf(h.z, sc.z, sh.z); y.w = fmaf(h.w, sc.w, sh.w);
         return make_float4(fmaxf(y.x, kSlope * y.x), fmaxf(y.y, kSlope * y.y), fmaxf(y.z, kSlope * y.z),
                            fmaxf(y.w, kSlope * y.w));
+    }
+};
+
+// Tensor-map variant of DhU for the rows kernel (dgrad A operand).  The fp32 [128 rows x 32 ch] block
+// of dy lands by TMA (SWIZZLE_128B) DIRECTLY in the ring stage -- the K-major swizzled arrangement
+// the MMA reads -- and the matching fp16 block of H in a raw slot of the same index; the producer
+// threads then turn dy into dH = P*dy - w*(Q + S*h) in place.  No register staging: every stage the
+// MMA has released has 24 KB of loads in flight.
+struct DhInPlaceT {
+    static constexpr bool kTma = true;
+    static constexpr bool kInPlace = true;
+    static constexpr int kAhead = 0;
+    alignas(64) CUtensorMap tmap_dy;         // fp32 [R, C], box {32, 128}, SWIZZLE_128B
+    alignas(64) CUtensorMap tmap;            // fp16 [R, C], box {32, 128}, unswizzled (64-byte rows)
+    int C;
+    const double* fsums;
+    const float* gamma;
+    const double* bsums;
+    double inv_count;
+    PairGeom g;
+    struct Row { int dummy; };
+    struct Raw { int dummy; };
+    __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
+        for (int c = tid; c < C; c += nthreads) {
+            float m, r;
+            bn_mean_rstd(fsums, C, c, inv_count, m, r);
+            float P = gamma[c] * r;
+            float S = P * r * (float)(stat_get(bsums, C, c, 1) * inv_count);
+            aux[c] = P;
+            aux[kMaxC + c] = P * (float)(stat_get(bsums, C, c, 0) * inv_count) - S * m;
+            aux[2 * kMaxC + c] = S;
+        }
+    }
+    __device__ __forceinline__ Row row(int) const { return Row{0}; }
+    __device__ __forceinline__ void fetch(const Row&, int, Raw&) const {}
+    __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ float4 transform(uint2, int, const float*) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ float row_weight(int r) const { return decode_row(r, g).w; }
+    __device__ __forceinline__ float4 transform2(float4 d, uint2 hraw, float w, int k, const float* aux) const {
+        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 h = unpack_half4(hraw);
+        float4 P = *reinterpret_cast<const float4*>(aux + k);
+        float4 Q = *reinterpret_cast<const float4*>(aux + kMaxC + k);
+        float4 S = *reinterpret_cast<const float4*>(aux + 2 * kMaxC + k);
+        const float nw = -w;
+        return make_float4(fmaf(nw, fmaf(S.x, h.x, Q.x), P.x * d.x), fmaf(nw, fmaf(S.y, h.y, Q.y), P.y * d.y),
+                           fmaf(nw, fmaf(S.z, h.z, Q.z), P.z * d.z), fmaf(nw, fmaf(S.w, h.w, Q.w), P.w * d.w));
     }
 };
 
@@ -529,6 +579,10 @@ struct EpiDyU {
 };
 
 // ------------------------------------------------------------------ the kernel
+template <class AOp> __host__ __device__ constexpr bool tma_in_place() {
+    if constexpr (AOp::kTma) return AOp::kInPlace; else return false;
+}
+
 template <class AOp, class Epi>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi epi, const float* __restrict__ wimg,
@@ -595,7 +649,50 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
         reg_dec<96>();   // 8 warps x 32 regs released ...
         constexpr int RQ = UM_ROWS * 8 / UM_PROD_THREADS;      // rows per thread per K block (4)
         constexpr int RSTEP = UM_PROD_THREADS / 8;              // 32
-        if constexpr (AOp::kTma) {
+        if constexpr (tma_in_place<AOp>()) {
+            // In-place operands (DhInPlaceT): stage st holds the fp32 block the TMA warp landed (already
+            // swizzled), raw slot st the fp16 companion; transform own elements and hand over to the MMA.
+            const int rsub = tid >> 3, c16 = tid & 7;
+            const int sw = rsub & 7;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int row0 = phys(tile) * UM_ROWS;
+                float wq[RQ];
+#pragma unroll
+                for (int q = 0; q < RQ; ++q) {
+                    const int r = row0 + q * RSTEP + rsub;
+                    wq[q] = r < s.R ? aop.row_weight(r) : 0.f;
+                }
+                for (int kc = 0; kc < s.KC; ++kc) {
+                    mbar_wait(&rawfull[st], ph);
+                    const uint8_t* rawb = rawring + (size_t)st * UM_RAW_BYTES;
+                    float* blk = Asm + (size_t)st * UM_BLOCK_FLOATS;
+                    const int k = kc * UM_KB + c16 * 4;
+                    uint2 hraw[RQ];
+                    float4 d[RQ];
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q) {
+                        const int rl = q * RSTEP + rsub;
+                        hraw[q] = *reinterpret_cast<const uint2*>(rawb + rl * 64 + c16 * 8);
+                        d[q] = *reinterpret_cast<const float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2));
+                    }
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q) {
+                        const int rl = q * RSTEP + rsub;
+                        float4 v = aop.transform2(d[q], hraw[q], wq[q], k, aux_a);
+                        if (row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                        *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[st]);
+                    if (++st == s.stages) { st = 0; ph ^= 1; }
+                }
+                if (warp == 0 && tile == (int)blockIdx.x) MFT_MARK(2);
+            }
+        } else if constexpr (AOp::kTma) {
             // The TMA warp lands raw fp16 blocks [128 rows x 32 ch] (row = 64 bytes, unswizzled) in the
             // raw ring; each producer thread converts its (row, 4-channel) pieces, applies BN +
             // LeakyReLU + TF32 rounding and writes the fp32 K block of the A ring, swizzled.
@@ -752,7 +849,24 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
         __syncwarp();
     } else if (warp == UM_TMA_WARP) {
         // ===================== TMA loader (one thread; kTma operands only) =====================
-        if constexpr (AOp::kTma) {
+        if constexpr (tma_in_place<AOp>()) {
+            if (lane == 0) {
+                tma_prefetch_desc(&aop.tmap);
+                tma_prefetch_desc(&aop.tmap_dy);
+                int st = 0;
+                uint32_t ph = 0;
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                    const int row0 = phys(tile) * UM_ROWS;
+                    for (int kc = 0; kc < s.KC; ++kc) {
+                        mbar_wait(&empty[st], ph ^ 1);           // the MMA has consumed the stage
+                        mbar_arrive_expect_tx(&rawfull[st], UM_RAW_BYTES + UM_BLOCK_FLOATS * 4);
+                        tma_load_2d(Asm + (size_t)st * UM_BLOCK_FLOATS, &aop.tmap_dy, kc * UM_KB, row0, &rawfull[st]);
+                        tma_load_2d(rawring + (size_t)st * UM_RAW_BYTES, &aop.tmap, kc * UM_KB, row0, &rawfull[st]);
+                        if (++st == s.stages) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+        } else if constexpr (AOp::kTma) {
             if (lane == 0) {
                 tma_prefetch_desc(&aop.tmap);
                 int rs = 0;
@@ -1363,7 +1477,19 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
         const int dir = next_direction();
         UmmaShape s{};
         plan_pass(nts[p], K, s);
-        if (AOp::kTma) {
+        if (tma_in_place<AOp>()) {
+            // stage st and raw slot st travel together: as many as fit
+            bool fit = false;
+            for (int stg = UM_MAX_STAGES; stg >= 2 && !fit; --stg) {
+                s.stages = stg;
+                s.raw_stages = stg;
+                fit = umma_smem_bytes(s) <= kSmemLimit;
+            }
+            if (!fit) {
+                set_error(MFT_ERR_UNSUPPORTED, "umma_rows_gemm: no room for in-place TMA stages (N=%d K=%d)", N, K);
+                return MFT_ERR_UNSUPPORTED;
+            }
+        } else if (AOp::kTma) {
             // two fp32 A stages are enough once the loads run ahead in the fp16 raw ring: give the
             // rest of shared memory to raw blocks in flight
             s.stages = 2;
@@ -1582,24 +1708,26 @@ dx_gather_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __r
     }
 }
 
-// Vector form for 16-byte aligned rows: 64 lanes x float4 over the features, 4 slices over the
-// partner nodes m (four independent load streams per thread, combined through shared memory).
+// Vector form for 16-byte aligned rows: QF = ceil(F/4) lanes x float4 over the features, 256/QF
+// slices over the partner nodes m (independent load streams, combined through shared memory).
 __global__ void __launch_bounds__(256)
 dx_gather_vec_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
                      int ldx, int F, PairGeom g) {
-    __shared__ float4 part[4][64];
+    __shared__ float4 part[256];
     const int N = g.N;
     const int node = blockIdx.x;
     const int b = node / N, n = node - b * N;
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int QF = (F + 3) >> 2;                 // <= 64
+    const int slices = 256 / QF;
+    const int tx = threadIdx.x % QF, ty = threadIdx.x / QF;
     const int f = tx * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (f < F) {
+    if (ty < slices) {
         const float4 xv = ldg4(x + (size_t)node * ldx + f);
         const __nv_bfloat16* Df = dD + f;
         const float* xb = x + (size_t)b * N * ldx + f;
 #pragma unroll 4
-        for (int m = ty; m < N; m += 4) {
+        for (int m = ty; m < N; m += slices) {
             if (m == n) continue;
             bool shared;
             const int r = pair_row(g, b, min(n, m), max(n, m), shared);
@@ -1612,13 +1740,15 @@ dx_gather_vec_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float*
             acc.w += (xv.w > xm.w) ? d.w : ((xv.w < xm.w) ? -d.w : 0.f);
         }
     }
-    part[ty][tx] = acc;
+    part[threadIdx.x] = acc;
     __syncthreads();
-    if (ty == 0 && f < F) {
-        float4 a = part[0][tx], b1 = part[1][tx], c = part[2][tx], d = part[3][tx];
+    if (ty == 0) {
+        for (int sl = 1; sl < slices; ++sl) {
+            const float4 v = part[sl * QF + tx];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
         float* o = dx + (size_t)node * ldx + f;
-        float v[4] = {a.x + b1.x + c.x + d.x, a.y + b1.y + c.y + d.y, a.z + b1.z + c.z + d.z,
-                      a.w + b1.w + c.w + d.w};
+        const float v[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (f + e < F) o[e] += v[e];
@@ -1632,8 +1762,17 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
                             const PairGeom& g, cudaStream_t st) {
     (void)gr;
     const int Cout = L.C[k + 1], Cin = L.C[k];
-    DhU a{dh, reinterpret_cast<const __half*>(L.H[k]), Cout, L.fsums + (size_t)k * kStatSlot, p->bn_g[k], L.bsums + (size_t)k * kStatSlot,
-          g.inv_pairs, g};
+    DhInPlaceT a{};
+    {
+        int rc = make_tmap_2d(&a.tmap_dy, dh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.R, Cout, Cout, UM_KB, UM_ROWS,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != MFT_OK) return rc;
+        rc = make_tmap_2d(&a.tmap, L.H[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g.R, Cout, Cout, UM_KB, UM_ROWS,
+                          CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != MFT_OK) return rc;
+        a.C = Cout; a.fsums = L.fsums + (size_t)k * kStatSlot; a.gamma = p->bn_g[k];
+        a.bsums = L.bsums + (size_t)k * kStatSlot; a.inv_count = g.inv_pairs; a.g = g;
+    }
     if (k == 0) {
         const int ldd = (F + 3) & ~3;
         EpiStoreBf16U e{reinterpret_cast<__nv_bfloat16*>(L.dD), ldd};

@@ -153,9 +153,105 @@ bgemm64_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int 
     }
 }
 
+// One-shot variant for K <= 256 (every Gconv product except the weight gradients): a 32x32 output
+// tile whose complete A and B panels are brought into shared memory by cp.async in ONE round of
+// loads (the looped kernels above pay one L2 round trip per 16-32 columns of K with nothing to
+// overlap it: 27-CTA launches that took 12-17 us), then multiplied from shared memory.
+constexpr int OS_T = 32;
+constexpr int OS_MAXK = 256;
+
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+    const int sz = valid ? 4 : 0;      // src-size 0: the destination is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int M, int N, int K, float beta) {
+    extern __shared__ float os_smem[];
+    const int lda = K | 1;                       // odd row stride: conflict-free column walks
+    float* As = os_smem;                         // [32][lda]  (m, k)
+    float* Bs = os_smem + OS_T * lda;            // [K][32]    (k, n)
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.y * OS_T, n0 = blockIdx.x * OS_T;
+    const int t = threadIdx.x;
+    const float* Ab = A.p + (size_t)b * A.sb;
+    const float* Bb = Bm.p + (size_t)b * Bm.sb;
+    const int total = OS_T * K;
+    if (A.s1 == 1) {                             // k contiguous in memory
+        for (int idx = t; idx < total; idx += 256) {
+            const int m = idx / K, k = idx - m * K;
+            const bool ok = m0 + m < M;
+            cp_async4(As + m * lda + k, Ab + (size_t)(ok ? m0 + m : 0) * A.s0 + k, ok);
+        }
+    } else {                                     // m contiguous (or general strides)
+        for (int idx = t; idx < total; idx += 256) {
+            const int k = idx >> 5, m = idx & 31;
+            const bool ok = m0 + m < M;
+            cp_async4(As + m * lda + k, Ab + (size_t)(ok ? m0 + m : 0) * A.s0 + (size_t)k * A.s1, ok);
+        }
+    }
+    if (Bm.s1 == 1) {                            // n contiguous
+        for (int idx = t; idx < total; idx += 256) {
+            const int k = idx >> 5, n = idx & 31;
+            const bool ok = n0 + n < N;
+            cp_async4(Bs + k * OS_T + n, Bb + (size_t)k * Bm.s0 + (ok ? n0 + n : 0), ok);
+        }
+    } else {                                     // k contiguous (or general strides)
+        for (int idx = t; idx < total; idx += 256) {
+            const int n = idx / K, k = idx - n * K;
+            const bool ok = n0 + n < N;
+            cp_async4(Bs + k * OS_T + n, Bb + (size_t)k * Bm.s0 + (size_t)(ok ? n0 + n : 0) * Bm.s1, ok);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int tx = t & 15, ty = t >> 4;          // thread -> outputs (2*ty + {0,1}, 2*tx + {0,1})
+    const float* a0 = As + (2 * ty) * lda;
+    const float* a1 = a0 + lda;
+    const float* bp = Bs + 2 * tx;
+    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+        const float x0 = a0[k], x1 = a1[k];
+        const float2 y = *reinterpret_cast<const float2*>(bp + k * OS_T);
+        c00 = fmaf(x0, y.x, c00); c01 = fmaf(x0, y.y, c01);
+        c10 = fmaf(x1, y.x, c10); c11 = fmaf(x1, y.y, c11);
+    }
+    const float acc[2][2] = {{c00, c01}, {c10, c11}};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + 2 * ty + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = n0 + 2 * tx + j;
+            if (n < N) {
+                float* c = C + (size_t)b * scb + (size_t)m * ldc + n;
+                *c = (beta == 0.f) ? acc[i][j] : fmaf(beta, *c, acc[i][j]);
+            }
+        }
+    }
+}
+
 cudaError_t launch_bgemm(BView A, BView Bm, float* C, long scb, int ldc, int batch, int M, int N, int K,
                          float beta, cudaStream_t st) {
     if (batch <= 0 || M <= 0 || N <= 0) return cudaSuccess;
+    if (K >= 1 && K <= OS_MAXK) {
+        static bool attr_set = false;
+        const size_t max_smem = (size_t)(OS_T * (OS_MAXK | 1) + OS_MAXK * OS_T) * sizeof(float);
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(bgemm_oneshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)max_smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        const size_t smem = (size_t)(OS_T * (K | 1) + K * OS_T) * sizeof(float);
+        dim3 grid(cdiv(N, OS_T), cdiv(M, OS_T), batch);
+        bgemm_oneshot_kernel<<<grid, 256, smem, st>>>(A, Bm, C, scb, ldc, M, N, K, beta);
+        return cudaGetLastError();
+    }
     if (M >= 48 && N >= 40) {
         dim3 grid(cdiv(N, BG2_T), cdiv(M, BG2_T), batch);
         bgemm64_kernel<<<grid, 256, 0, st>>>(A, Bm, C, scb, ldc, M, N, K, beta);

@@ -291,6 +291,384 @@ score_kernel(const void* __restrict__ H4, int C, const double* sums, const float
     }
 }
 
+// ---- vector forms of score / dy4 (C % 4 == 0): lane l owns channels 4l..4l+3 (+128 per extra group), its
+// BN constants live in registers, H4 is read with one 8-byte (fp16 tape) or 16-byte (fp32) load per
+// group and dy4 written with one 16-byte store.  The scalar kernels above/below stay as the fallback.
+template <bool HalfTape>
+__device__ __forceinline__ float4 tape_ld4(const void* p, size_t i) {
+    if constexpr (HalfTape) return unpack_half4(__ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p) + i)));
+    else return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p) + i));
+}
+
+template <int NG>
+struct LaneConsts {
+    float4 sc[NG], sh[NG], wl[NG], mean[NG], rstd[NG];
+    bool on[NG];
+};
+
+template <int NG>
+__device__ __forceinline__ void lane_consts(LaneConsts<NG>& k, const float* aux, const float* wl, int C, int lane) {
+    BnSmem s = bn_smem_at(const_cast<float*>(aux));
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+        const int c = 4 * (lane + 32 * q);
+        k.on[q] = c < C;
+        const int cc = k.on[q] ? c : 0;
+        float sc[4], sh[4], w[4], m[4], r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            sc[e] = s.gamma[cc + e] * s.rstd[cc + e];
+            sh[e] = s.beta[cc + e] - s.mean[cc + e] * sc[e];
+            w[e] = wl[cc + e];
+            m[e] = s.mean[cc + e];
+            r[e] = s.rstd[cc + e];
+        }
+        k.sc[q] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+        k.sh[q] = make_float4(sh[0], sh[1], sh[2], sh[3]);
+        k.wl[q] = make_float4(w[0], w[1], w[2], w[3]);
+        k.mean[q] = make_float4(m[0], m[1], m[2], m[3]);
+        k.rstd[q] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+template <bool HalfTape, bool Shared, int NG>
+__global__ void __launch_bounds__(kRowWarps * 32)
+score_vec_kernel(const void* __restrict__ H4, int C, const double* sums, const float* gamma, const float* beta,
+                 const float* last_w, const float* last_b, PairGeom g, float* __restrict__ S) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float wls[kMaxC];
+    bn_smem_fill(bn_smem_at(aux), sums, gamma, beta, C, g.inv_pairs);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) wls[c] = last_w[c];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LaneConsts<NG> k;
+    lane_consts<NG>(k, aux, wls, C, lane);
+    const float bias = last_b[0];
+    constexpr int RU = 4;                      // rows in flight per warp
+    const int stride = gridDim.x * kRowWarps;
+    for (int r0 = blockIdx.x * kRowWarps + warp; r0 < g.R; r0 += RU * stride) {
+        float4 h[RU][NG];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = min(r0 + u * stride, g.R - 1);
+#pragma unroll
+            for (int q = 0; q < NG; ++q)
+                h[u][q] = k.on[q] ? tape_ld4<HalfTape>(H4, (size_t)r * C + 4 * (lane + 32 * q))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * stride;
+            if (r >= g.R) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+                if (!k.on[q]) continue;
+                acc = fmaf(lrelu(fmaf(h[u][q].x, k.sc[q].x, k.sh[q].x)), k.wl[q].x, acc);
+                acc = fmaf(lrelu(fmaf(h[u][q].y, k.sc[q].y, k.sh[q].y)), k.wl[q].y, acc);
+                acc = fmaf(lrelu(fmaf(h[u][q].z, k.sc[q].z, k.sh[q].z)), k.wl[q].z, acc);
+                acc = fmaf(lrelu(fmaf(h[u][q].w, k.sc[q].w, k.sh[q].w)), k.wl[q].w, acc);
+            }
+            acc = warp_sum(acc);
+            if (Shared || lane == 0) {
+                PairRow p = decode_row(r, g);
+                const float v = acc + bias;
+                for (int b = p.b + lane; b < p.b + p.nb; b += 32) {
+                    size_t base = (size_t)b * g.N * g.N;
+                    S[base + (size_t)p.i * g.N + p.j] = v;
+                    S[base + (size_t)p.j * g.N + p.i] = v;
+                }
+            }
+        }
+    }
+}
+
+template <bool HalfTape, bool Shared, int NG>
+__global__ void __launch_bounds__(kRowWarps * 32)
+dy4_vec_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, const double* fsums,
+               const float* gamma, const float* beta, const float* last_w, PairGeom g, float* __restrict__ dy4,
+               double* bsums, double* lastsum) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float wls[kMaxC];
+    __shared__ float red[3][kRowWarps][kMaxC];
+    bn_smem_fill(bn_smem_at(aux), fsums, gamma, beta, C, g.inv_pairs);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) wls[c] = last_w[c];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LaneConsts<NG> k;
+    lane_consts<NG>(k, aux, wls, C, lane);
+    float4 p0[NG], p1[NG], p2[NG];             // sum d, sum d*h (turned into sum d*hhat at the end), sum G*a4
+#pragma unroll
+    for (int q = 0; q < NG; ++q) p0[q] = p1[q] = p2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int RU = 4;
+    const int stride = gridDim.x * kRowWarps;
+    for (int r0 = blockIdx.x * kRowWarps + warp; r0 < g.R; r0 += RU * stride) {
+        float G[RU];
+        float4 h[RU][NG];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = min(r0 + u * stride, g.R - 1);
+            PairRow p = decode_row(r, g);
+            if (!Shared || p.nb == 1) {
+                size_t base = (size_t)p.b * g.N * g.N;
+                float a = __ldg(dS + base + (size_t)p.i * g.N + p.j);
+                float b2 = __ldg(dS + base + (size_t)p.j * g.N + p.i);
+                G[u] = (p.i != p.j) ? a + b2 : a;
+            } else {
+                float a = 0.f;
+                for (int b = lane; b < p.nb; b += 32) {
+                    size_t base = (size_t)b * g.N * g.N;
+                    a += __ldg(dS + base + (size_t)p.i * g.N + p.j);
+                    if (p.i != p.j) a += __ldg(dS + base + (size_t)p.j * g.N + p.i);
+                }
+                G[u] = warp_sum(a);
+            }
+#pragma unroll
+            for (int q = 0; q < NG; ++q)
+                h[u][q] = k.on[q] ? tape_ld4<HalfTape>(H4, (size_t)r * C + 4 * (lane + 32 * q))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * stride;
+            if (r >= g.R) break;
+#pragma unroll
+            for (int q = 0; q < NG; ++q) {
+                if (!k.on[q]) continue;
+                const float4 hv = h[u][q];
+                float4 y, d;
+                y.x = fmaf(hv.x, k.sc[q].x, k.sh[q].x); y.y = fmaf(hv.y, k.sc[q].y, k.sh[q].y);
+                y.z = fmaf(hv.z, k.sc[q].z, k.sh[q].z); y.w = fmaf(hv.w, k.sc[q].w, k.sh[q].w);
+                d.x = G[u] * k.wl[q].x * dlrelu(y.x); d.y = G[u] * k.wl[q].y * dlrelu(y.y);
+                d.z = G[u] * k.wl[q].z * dlrelu(y.z); d.w = G[u] * k.wl[q].w * dlrelu(y.w);
+                *reinterpret_cast<float4*>(dy4 + (size_t)r * C + 4 * (lane + 32 * q)) = d;
+                p0[q].x += d.x; p0[q].y += d.y; p0[q].z += d.z; p0[q].w += d.w;
+                p1[q].x = fmaf(d.x, hv.x, p1[q].x); p1[q].y = fmaf(d.y, hv.y, p1[q].y);
+                p1[q].z = fmaf(d.z, hv.z, p1[q].z); p1[q].w = fmaf(d.w, hv.w, p1[q].w);
+                p2[q].x = fmaf(G[u], lrelu(y.x), p2[q].x); p2[q].y = fmaf(G[u], lrelu(y.y), p2[q].y);
+                p2[q].z = fmaf(G[u], lrelu(y.z), p2[q].z); p2[q].w = fmaf(G[u], lrelu(y.w), p2[q].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+        if (!k.on[q]) continue;
+        const int c = 4 * (lane + 32 * q);
+        // sum d*hhat = rstd * (sum d*h - mean * sum d)
+        const float4 hh = make_float4(k.rstd[q].x * (p1[q].x - k.mean[q].x * p0[q].x),
+                                      k.rstd[q].y * (p1[q].y - k.mean[q].y * p0[q].y),
+                                      k.rstd[q].z * (p1[q].z - k.mean[q].z * p0[q].z),
+                                      k.rstd[q].w * (p1[q].w - k.mean[q].w * p0[q].w));
+        *reinterpret_cast<float4*>(&red[0][warp][c]) = p0[q];
+        *reinterpret_cast<float4*>(&red[1][warp][c]) = hh;
+        *reinterpret_cast<float4*>(&red[2][warp][c]) = p2[q];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRowWarps; ++w) { v0 += red[0][w][c]; v1 += red[1][w][c]; v2 += red[2][w][c]; }
+        stat_add(bsums, C, c, 0, v0);
+        stat_add(bsums, C, c, 1, v1);
+        stat_add(lastsum, C, c, 0, v2);
+    }
+}
+
+// ---- eight lanes per row (C % 4 == 0, C <= 32*NGL): a warp works on four rows at a time, lane (l & 7)
+// owns the 4-channel groups (l & 7) + 8q.  Compared with one warp per row this divides the per-row
+// overhead (row decode, reduction shuffles, address arithmetic, scatter) by four, which is what
+// bounds these kernels once the loads are vectorised (ncu: issue-bound at ~1 TB/s).
+template <int NGL>
+struct Lane8Consts {
+    float4 sc[NGL], sh[NGL], wl[NGL];
+    bool on[NGL];
+};
+template <int NGL>
+__device__ __forceinline__ void lane8_consts(Lane8Consts<NGL>& k, const float* aux, const float* wl, int C, int sl) {
+    BnSmem s = bn_smem_at(const_cast<float*>(aux));
+#pragma unroll
+    for (int q = 0; q < NGL; ++q) {
+        const int c = 4 * (sl + 8 * q);
+        k.on[q] = c < C;
+        const int cc = k.on[q] ? c : 0;
+        float sc[4], sh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            sc[e] = s.gamma[cc + e] * s.rstd[cc + e];
+            sh[e] = s.beta[cc + e] - s.mean[cc + e] * sc[e];
+        }
+        k.sc[q] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+        k.sh[q] = make_float4(sh[0], sh[1], sh[2], sh[3]);
+        k.wl[q] = make_float4(wl[cc], wl[cc + 1], wl[cc + 2], wl[cc + 3]);
+    }
+}
+__device__ __forceinline__ float sum8(float v) {   // over the 8 lanes of a row group
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+template <bool HalfTape, bool Shared, int NGL>
+__global__ void __launch_bounds__(kRowWarps * 32)
+score8_kernel(const void* __restrict__ H4, int C, const double* sums, const float* gamma, const float* beta,
+              const float* last_w, const float* last_b, PairGeom g, float* __restrict__ S) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float wls[kMaxC];
+    bn_smem_fill(bn_smem_at(aux), sums, gamma, beta, C, g.inv_pairs);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) wls[c] = last_w[c];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = lane & 7, rg = lane >> 3;
+    Lane8Consts<NGL> k;
+    lane8_consts<NGL>(k, aux, wls, C, sl);
+    const float bias = last_b[0];
+    constexpr int RU = 2;                          // row quads in flight per warp
+    const int stride = gridDim.x * kRowWarps * 4;  // rows per grid sweep
+    for (int rb = (blockIdx.x * kRowWarps + warp) * 4; rb < g.R; rb += RU * stride) {   // warp-uniform trip count
+        const int r0 = rb + rg;
+        float4 h[RU][NGL];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = min(r0 + u * stride, g.R - 1);
+#pragma unroll
+            for (int q = 0; q < NGL; ++q)
+                h[u][q] = k.on[q] ? tape_ld4<HalfTape>(H4, (size_t)r * C + 4 * (sl + 8 * q))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * stride;
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < NGL; ++q) {
+                if (!k.on[q]) continue;
+                acc = fmaf(lrelu(fmaf(h[u][q].x, k.sc[q].x, k.sh[q].x)), k.wl[q].x, acc);
+                acc = fmaf(lrelu(fmaf(h[u][q].y, k.sc[q].y, k.sh[q].y)), k.wl[q].y, acc);
+                acc = fmaf(lrelu(fmaf(h[u][q].z, k.sc[q].z, k.sh[q].z)), k.wl[q].z, acc);
+                acc = fmaf(lrelu(fmaf(h[u][q].w, k.sc[q].w, k.sh[q].w)), k.wl[q].w, acc);
+            }
+            acc = sum8(acc);                       // (all lanes take part; rows past the end are dropped below)
+            if (r < g.R && (Shared || sl == 0)) {
+                PairRow p = decode_row(r, g);
+                const float v = acc + bias;
+                for (int b = p.b + sl; b < p.b + p.nb; b += 8) {
+                    size_t base = (size_t)b * g.N * g.N;
+                    S[base + (size_t)p.i * g.N + p.j] = v;
+                    S[base + (size_t)p.j * g.N + p.i] = v;
+                }
+            }
+        }
+    }
+}
+
+template <bool HalfTape, bool Shared, int NGL>
+__global__ void __launch_bounds__(kRowWarps * 32, 2)
+dy8_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, const double* fsums,
+           const float* gamma, const float* beta, const float* last_w, PairGeom g, float* __restrict__ dy4,
+           double* bsums, double* lastsum) {
+    __shared__ float aux[4 * kMaxC];
+    __shared__ float wls[kMaxC];
+    __shared__ float red[3][kRowWarps][32 * NGL];
+    bn_smem_fill(bn_smem_at(aux), fsums, gamma, beta, C, g.inv_pairs);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) wls[c] = last_w[c];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sl = lane & 7, rg = lane >> 3;
+    Lane8Consts<NGL> k;
+    lane8_consts<NGL>(k, aux, wls, C, sl);
+    float4 p0[NGL], p1[NGL], p2[NGL];
+#pragma unroll
+    for (int q = 0; q < NGL; ++q) p0[q] = p1[q] = p2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int RU = 2;
+    const int stride = gridDim.x * kRowWarps * 4;
+    for (int rb = (blockIdx.x * kRowWarps + warp) * 4; rb < g.R; rb += RU * stride) {   // warp-uniform trip count
+        const int r0 = rb + rg;
+        float G[RU];
+        float4 h[RU][NGL];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = min(r0 + u * stride, g.R - 1);
+            PairRow p = decode_row(r, g);
+            float a = 0.f;
+            if (!Shared || p.nb == 1) {
+                if (sl == 0) {
+                    size_t base = (size_t)p.b * g.N * g.N;
+                    a = __ldg(dS + base + (size_t)p.i * g.N + p.j);
+                    if (p.i != p.j) a += __ldg(dS + base + (size_t)p.j * g.N + p.i);
+                }
+            } else {   // shared pair: sum over the graphs it stands for (8 lanes over b)
+                for (int b = sl; b < p.nb; b += 8) {
+                    size_t base = (size_t)b * g.N * g.N;
+                    a += __ldg(dS + base + (size_t)p.i * g.N + p.j);
+                    if (p.i != p.j) a += __ldg(dS + base + (size_t)p.j * g.N + p.i);
+                }
+            }
+            G[u] = a;
+#pragma unroll
+            for (int q = 0; q < NGL; ++q)
+                h[u][q] = k.on[q] ? tape_ld4<HalfTape>(H4, (size_t)r * C + 4 * (sl + 8 * q))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * stride;
+            const float Gr = sum8(G[u]);
+            if (r >= g.R) continue;
+#pragma unroll
+            for (int q = 0; q < NGL; ++q) {
+                if (!k.on[q]) continue;
+                const float4 hv = h[u][q];
+                float4 y, d;
+                y.x = fmaf(hv.x, k.sc[q].x, k.sh[q].x); y.y = fmaf(hv.y, k.sc[q].y, k.sh[q].y);
+                y.z = fmaf(hv.z, k.sc[q].z, k.sh[q].z); y.w = fmaf(hv.w, k.sc[q].w, k.sh[q].w);
+                d.x = Gr * k.wl[q].x * dlrelu(y.x); d.y = Gr * k.wl[q].y * dlrelu(y.y);
+                d.z = Gr * k.wl[q].z * dlrelu(y.z); d.w = Gr * k.wl[q].w * dlrelu(y.w);
+                *reinterpret_cast<float4*>(dy4 + (size_t)r * C + 4 * (sl + 8 * q)) = d;
+                p0[q].x += d.x; p0[q].y += d.y; p0[q].z += d.z; p0[q].w += d.w;
+                p1[q].x = fmaf(d.x, hv.x, p1[q].x); p1[q].y = fmaf(d.y, hv.y, p1[q].y);
+                p1[q].z = fmaf(d.z, hv.z, p1[q].z); p1[q].w = fmaf(d.w, hv.w, p1[q].w);
+                p2[q].x = fmaf(Gr, lrelu(y.x), p2[q].x); p2[q].y = fmaf(Gr, lrelu(y.y), p2[q].y);
+                p2[q].z = fmaf(Gr, lrelu(y.z), p2[q].z); p2[q].w = fmaf(Gr, lrelu(y.w), p2[q].w);
+            }
+        }
+    }
+    // combine the four row groups of the warp (lanes with equal sl), then the warps through shared memory
+#pragma unroll
+    for (int q = 0; q < NGL; ++q) {
+        float* ps[3] = {&p0[q].x, &p1[q].x, &p2[q].x};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float v = ps[a][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                ps[a][e] = v;
+            }
+        if (rg == 0) {
+            const int c = 4 * (sl + 8 * q);
+            const float* mean = aux, *rstd = aux + kMaxC;           // (bn_smem_at layout)
+            const float4 hh = make_float4(rstd[c] * (p1[q].x - mean[c] * p0[q].x),
+                                          rstd[c + 1] * (p1[q].y - mean[c + 1] * p0[q].y),
+                                          rstd[c + 2] * (p1[q].z - mean[c + 2] * p0[q].z),
+                                          rstd[c + 3] * (p1[q].w - mean[c + 3] * p0[q].w));
+            *reinterpret_cast<float4*>(&red[0][warp][c]) = p0[q];
+            *reinterpret_cast<float4*>(&red[1][warp][c]) = hh;      // sum d*hhat = rstd*(sum d*h - mean*sum d)
+            *reinterpret_cast<float4*>(&red[2][warp][c]) = p2[q];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRowWarps; ++w) { v0 += red[0][w][c]; v1 += red[1][w][c]; v2 += red[2][w][c]; }
+        stat_add(bsums, C, c, 0, v0);
+        stat_add(bsums, C, c, 1, v1);
+        stat_add(lastsum, C, c, 0, v2);
+    }
+}
+
 // adj[b,i,:] = softmax_j(S[b,i,j] - 1e8 [i==j])   (gnn.py:105-115), one warp per row
 __global__ void __launch_bounds__(kRowWarps * 32)
 softmax_rows_kernel(const float* __restrict__ S, float* __restrict__ adj, int rows, int N) {
@@ -462,14 +840,15 @@ struct FinalizeArgs {
     int nf;
 };
 
-__global__ void finalize_grads_kernel(FinalizeArgs a) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int k = 0; k < 4; ++k) {
+__global__ void finalize_grads_kernel(FinalizeArgs a) {   // grid = 5: one CTA per BN layer + one for conv2d_last
+    const int t = threadIdx.x, k = blockIdx.x;
+    if (k < 4) {
         if (t < a.C[k]) {
             if (a.bn_b[k]) a.bn_b[k][t] = (float)stat_get(a.bsums[k], a.C[k], t, 0);
             if (a.bn_g[k]) a.bn_g[k][t] = (float)stat_get(a.bsums[k], a.C[k], t, 1);
             if (a.conv_b[k]) a.conv_b[k][t] = 0.f;   // BN removes the mean: exactly zero
         }
+        return;
     }
     if (t < a.nf && a.last_w) a.last_w[t] = (float)stat_get(a.lastsum, a.nf, t, 0);
     if (t == 0 && a.last_b) a.last_b[0] = 0.f;         // softmax shift invariance: exactly zero
@@ -526,6 +905,7 @@ wgrad_reduce_kernel(FinalizeArgs a) {
 // =========================== host orchestration ==============================
 
 static inline int row_grid(int R) { return min(cdiv(R, kRowWarps), 148 * 6); }
+static inline int row_grid8(int R) { return min(cdiv(R, kRowWarps * 4), 148 * 4); }   // four rows per warp
 
 WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     WcLayout L;
@@ -598,9 +978,17 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     {
         ProfScope ps(PC_SCORE, st);
 #define MFT_SCORE(HALF, SHARED)                                                                                   \
-    score_kernel<HALF, SHARED><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.H[3], nf, L.fsums + 3 * kStatSlot,         \
-                                                                         p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, \
-                                                                         g, L.S)
+    do {                                                                                                          \
+        if (nf % 4 == 0 && nf <= 96)                                                                              \
+            score8_kernel<HALF, SHARED, 3><<<row_grid8(g.R), kRowWarps * 32, 0, st>>>(                             \
+                L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, g, L.S);        \
+        else if (nf % 4 == 0 && nf <= 128)                                                                        \
+            score_vec_kernel<HALF, SHARED, 1><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(                           \
+                L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, g, L.S);        \
+        else                                                                                                      \
+            score_kernel<HALF, SHARED><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(                                  \
+                L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, g, L.S);        \
+    } while (0)
         if (precision == MFT_PREC_TF32) {
             if (g.Rs > 0) MFT_SCORE(true, true); else MFT_SCORE(true, false);
         } else {
@@ -634,22 +1022,45 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             MFT_CHECK_CUDA(cudaMemsetAsync(gr->conv_w[k], 0, sizeof(float) * (size_t)L.C[k + 1] * L.C[k], st));
     }
     {
-        ProfScope ps(PC_PREP, st);
-        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, N, g.Rg, g.Rs, n_shared, mask);
-        MFT_CHECK_LAUNCH();
-    }
-    {
-        ProfScope ps(PC_SOFTMAX_BWD, st);
-        softmax_bwd_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(adj, d_adj, L.S, B * N, N);
-        MFT_CHECK_LAUNCH();
+        // the pair tables and (tensor-core path) the four dgrad weight images do not depend on the
+        // upstream gradient: build them on a side branch while the softmax backward runs
+        Branches br(st);
+        cudaStream_t s0 = br.fork(0);
+        {
+            ProfScope ps(PC_PREP, s0);
+            tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, s0>>>(L.tri, L.inv, N, g.Rg, g.Rs, n_shared, mask);
+            MFT_CHECK_LAUNCH();
+        }
+        if (precision == MFT_PREC_TF32) {
+            int rc = wcompute_bwd_prepare_tf32(p, L, F, nf, s0);   // all four dgrad weight images, one launch
+            if (rc != MFT_OK) return rc;
+        }
+        {
+            ProfScope ps(PC_SOFTMAX_BWD, st);
+            softmax_bwd_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(adj, d_adj, L.S, B * N, N);
+            MFT_CHECK_LAUNCH();
+        }
+        br.join(0);
+        MFT_REQUIRE(br.ok(), "wcompute_bwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     double* lastsum = L.bsums + 4 * kStatSlot;
     {
         ProfScope ps(PC_DY4, st);
-#define MFT_DY4(HALF, SHARED)                                                                                  \
-    dy4_kernel<HALF, SHARED><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(L.S, L.H[3], nf, L.fsums + 3 * kStatSlot,  \
-                                                                       p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA, \
-                                                                       L.bsums + 3 * kStatSlot, lastsum)
+#define MFT_DY4(HALF, SHARED)                                                                                     \
+    do {                                                                                                          \
+        if (nf % 4 == 0 && nf <= 96)                                                                              \
+            dy8_kernel<HALF, SHARED, 3><<<row_grid8(g.R), kRowWarps * 32, 0, st>>>(                                \
+                L.S, L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA,             \
+                L.bsums + 3 * kStatSlot, lastsum);                                                                 \
+        else if (nf % 4 == 0 && nf <= 128)                                                                        \
+            dy4_vec_kernel<HALF, SHARED, 1><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(                             \
+                L.S, L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA,             \
+                L.bsums + 3 * kStatSlot, lastsum);                                                                 \
+        else                                                                                                      \
+            dy4_kernel<HALF, SHARED><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(                                    \
+                L.S, L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, g, L.dyA,             \
+                L.bsums + 3 * kStatSlot, lastsum);                                                                 \
+    } while (0)
         if (precision == MFT_PREC_TF32) {
             if (g.Rs > 0) MFT_DY4(true, true); else MFT_DY4(true, false);
         } else {
@@ -659,10 +1070,6 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         MFT_CHECK_LAUNCH();
     }
 
-    if (precision == MFT_PREC_TF32) {
-        int rc = wcompute_bwd_prepare_tf32(p, L, F, nf, st);   // all four dgrad weight images, one launch
-        if (rc != MFT_OK) return rc;
-    }
     float* cur = L.dyA;
     float* nxt = L.dyB;
     for (int k = 3; k >= 0; --k) {   // layer k+1 of the reference (conv2d_{k+1}, bn_{k+1})
@@ -730,7 +1137,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     fa.nf = nf;
     {
         ProfScope ps(PC_FINALIZE, st);
-        finalize_grads_kernel<<<1, kMaxC, 0, st>>>(fa);
+        finalize_grads_kernel<<<5, kMaxC, 0, st>>>(fa);
         MFT_CHECK_LAUNCH();
         if (precision == MFT_PREC_TF32) {
             wgrad_reduce_kernel<<<L.C[1] + L.C[2] + L.C[3] + L.C[4], kRedThreads, 0, st>>>(fa);

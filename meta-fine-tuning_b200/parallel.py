@@ -29,8 +29,21 @@ def owned_episodes(n_episodes: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_episodes, world))
 
 
+def _mean_allreduce_(flat: torch.Tensor, world: int) -> None:
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)      # one kernel, no separate division
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+
+
 def allreduce_mean_grads(params: Iterable[torch.nn.Parameter], world: int | None = None) -> int:
-    """Average ``.grad`` over ranks with ONE collective on a flat buffer; returns the element count."""
+    """Average ``.grad`` over ranks; returns the element count.
+
+    The gradients GNN_nl's backward returns are views of ONE flat allocation (gnn._alloc_like_flat):
+    those are reduced in place with a single collective and no copy.  Gradients that live in
+    storages of their own (e.g. the ``fc`` layer of GnnHead) are packed into one more flat buffer,
+    reduced, and copied back with one fused launch."""
     if world is None:
         world = dist.get_world_size() if dist.is_initialized() else 1
     grads = [p.grad for p in params if p.grad is not None]
@@ -39,13 +52,27 @@ def allreduce_mean_grads(params: Iterable[torch.nn.Parameter], world: int | None
     n = sum(g.numel() for g in grads)
     if world == 1:
         return n
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.div_(world)
-    off = 0
+    by_storage = {}
     for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+        by_storage.setdefault(g.untyped_storage().data_ptr(), []).append(g)
+    loose: List[torch.Tensor] = []
+    for group in by_storage.values():
+        if len(group) < 2 or not all(g.is_contiguous() for g in group):
+            loose.extend(group)
+            continue
+        lo = min(g.storage_offset() for g in group)
+        hi = max(g.storage_offset() + g.numel() for g in group)
+        g0 = group[0]
+        span = torch.as_strided(g0, (hi - lo,), (1,), lo)  # covers every view (+ alignment padding)
+        _mean_allreduce_(span, world)
+    if loose:
+        flat = torch.cat([g.reshape(-1) for g in loose])
+        _mean_allreduce_(flat, world)
+        outs, off = [], 0
+        for g in loose:
+            outs.append(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        torch._foreach_copy_(loose, outs)
     return n
 
 

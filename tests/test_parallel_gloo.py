@@ -35,7 +35,20 @@ def _worker(rank, world, port, out_dir):
     loss = (O.gnn_nl(x.double(), p) * proj.double()).sum()
     loss.backward()
     params = [torch.nn.Parameter(v.detach()) for v in p.values()]
-    for prm, v in zip(params, p.values()):
+    # the layout the CUDA backward produces: all but the last two gradients are views of one flat
+    # allocation with 4-element alignment padding (gnn._alloc_like_flat); the rest own their storage
+    vals = list(p.values())
+    offs, total = [], 0
+    for v in vals[:-2]:
+        offs.append(total)
+        total += (v.numel() + 3) & ~3
+    flat = torch.full((total,), float("nan"), dtype=torch.float64)
+    for prm, v, o in zip(params[:-2], vals[:-2], offs):
+        view = flat[o:o + v.numel()].view(v.shape)
+        view.copy_(v.grad)
+        prm.grad = view
+    flat[torch.isnan(flat)] = 0.0          # padding
+    for prm, v in zip(params[-2:], vals[-2:]):
         prm.grad = v.grad.clone()
     n = parallel.allreduce_mean_grads(params, world)
     owned = parallel.owned_episodes(7, rank, world)

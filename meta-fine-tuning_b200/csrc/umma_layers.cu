@@ -656,14 +656,21 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
             const int sw = rsub & 7;
             int st = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int row0 = phys(tile) * UM_ROWS;
-                float wq[RQ];
+            // row multiplicities come from the pair table (a dependent global load): fetched one tile ahead
+            float wq[RQ], wq_next[RQ];
+            auto load_weights = [&](int tile, float (&dst)[RQ]) {
 #pragma unroll
                 for (int q = 0; q < RQ; ++q) {
-                    const int r = row0 + q * RSTEP + rsub;
-                    wq[q] = r < s.R ? aop.row_weight(r) : 0.f;
+                    const int r = phys(min(tile, ntiles - 1)) * UM_ROWS + q * RSTEP + rsub;
+                    dst[q] = (tile < ntiles && r < s.R) ? aop.row_weight(r) : 0.f;
                 }
+            };
+            load_weights(blockIdx.x, wq_next);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int row0 = phys(tile) * UM_ROWS;
+#pragma unroll
+                for (int q = 0; q < RQ; ++q) wq[q] = wq_next[q];
+                load_weights(tile + gridDim.x, wq_next);
                 for (int kc = 0; kc < s.KC; ++kc) {
                     mbar_wait(&rawfull[st], ph);
                     const uint8_t* rawb = rawring + (size_t)st * UM_RAW_BYTES;
@@ -900,16 +907,22 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
             for (int e = 0; e < 4; ++e) { s0[ch][e] = 0.f; s1[ch][e] = 0.f; }
         int it = 0;
+        float wq[8], wq_next[8];                              // row weights, fetched one tile ahead
+        auto load_weights = [&](int tile, float (&dst)[8]) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = phys(min(tile, ntiles - 1)) * UM_ROWS + ew * 32 + q * 4 + rsub;
+                dst[q] = (Epi::kRowWeight && tile < ntiles && r < s.R) ? epi.row_weight(r) : 0.f;
+            }
+        };
+        load_weights(blockIdx.x, wq_next);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int row0 = phys(tile) * UM_ROWS + ew * 32;  // first row of this warp's slab
-            float wq[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int r = row0 + q * 4 + rsub;
-                wq[q] = (Epi::kRowWeight && r < s.R) ? epi.row_weight(r) : 0.f;
-            }
+            for (int q = 0; q < 8; ++q) wq[q] = wq_next[q];
+            if (Epi::kRowWeight) load_weights(tile + gridDim.x, wq_next);
             mbar_wait(&tfull[acc], aph);
             tc_fence_after_sync();
             if (warp == UM_EPI_WARP0 && it == 0) MFT_MARK(12);             // first accumulator ready

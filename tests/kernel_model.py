@@ -36,15 +36,38 @@ def _dlrelu(y):
     return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, SLOPE))
 
 
-def wcompute_fwd(x, p, prefix):
+def pair_rows(bsz: int, n: int, shared=None):
+    """Row table of the edge MLP: (graph whose x the row reads, i, j, multiplicity, covers-all-graphs).
+
+    Without ``shared`` every graph contributes its N(N+1)/2 unordered pairs.  With ``shared`` (bool
+    [N], True where x[b, n] is the same row in every graph b -- GnnNet's support nodes) a pair of two
+    shared nodes gets ONE row that stands for all graphs: it reads graph 0 and carries bsz times
+    the multiplicity.  The shared rows come first, as in the CUDA pair table (common.cuh)."""
+    ii, jj = tri_rows(n)
+    mult = torch.where(ii == jj, 1.0, 2.0)
+    if shared is None or bsz < 2:
+        rg = ii.numel()
+        return (torch.arange(bsz).repeat_interleave(rg), ii.repeat(bsz), jj.repeat(bsz), mult.repeat(bsz),
+                torch.zeros(bsz * rg, dtype=torch.bool))
+    shared = torch.as_tensor(shared, dtype=torch.bool)
+    m = shared[ii] & shared[jj]
+    rs, rq = int(m.sum()), int((~m).sum())
+    rb = torch.cat([torch.zeros(rs, dtype=torch.long), torch.arange(bsz).repeat_interleave(rq)])
+    ri = torch.cat([ii[m], ii[~m].repeat(bsz)])
+    rj = torch.cat([jj[m], jj[~m].repeat(bsz)])
+    w = torch.cat([mult[m] * bsz, mult[~m].repeat(bsz)])
+    allg = torch.cat([torch.ones(rs, dtype=torch.bool), torch.zeros(bsz * rq, dtype=torch.bool)])
+    return rb, ri, rj, w, allg
+
+
+def wcompute_fwd(x, p, prefix, shared=None):
     """x [B,N,F] -> adjacency A [B,N,N] plus everything the backward needs."""
     bsz, n, f = x.shape
-    ii, jj = tri_rows(n)
-    rg = ii.numel()
-    w = torch.where(ii == jj, 1.0, 2.0).to(x.dtype).repeat(bsz)            # [R]
+    rb, ri, rj, w, allg = pair_rows(bsz, n, shared)
+    w = w.to(x.dtype)
     pairs = float(bsz * n * n)
-    d = (x[:, ii] - x[:, jj]).abs().reshape(bsz * rg, f)                   # [R,F]
-    saved = {"d": d, "w": w, "ii": ii, "jj": jj, "h": [], "mean": [], "rstd": [], "a": [d]}
+    d = (x[rb, ri] - x[rb, rj]).abs()                                      # [R,F]
+    saved = {"d": d, "w": w, "rows": (rb, ri, rj, allg), "h": [], "mean": [], "rstd": [], "a": [d]}
     a = d
     for k in (1, 2, 3, 4):
         wk = p[f"{prefix}conv2d_{k}.weight"].flatten(1)
@@ -63,9 +86,11 @@ def wcompute_fwd(x, p, prefix):
     wl = p[f"{prefix}conv2d_last.weight"].flatten()
     s = a @ wl + p[f"{prefix}conv2d_last.bias"]                             # [R]
     smat = torch.zeros(bsz, n, n, dtype=x.dtype)
-    s = s.reshape(bsz, rg)
-    smat[:, ii, jj] = s
-    smat[:, jj, ii] = s
+    one = ~allg
+    smat[rb[one], ri[one], rj[one]] = s[one]
+    smat[rb[one], rj[one], ri[one]] = s[one]
+    smat[:, ri[allg], rj[allg]] = s[allg]                                  # a shared pair scores in every graph
+    smat[:, rj[allg], ri[allg]] = s[allg]
     smat = smat - torch.eye(n, dtype=x.dtype) * 1e8
     adj = torch.softmax(smat, dim=2)
     saved["adj"] = adj
@@ -73,15 +98,18 @@ def wcompute_fwd(x, p, prefix):
 
 
 def wcompute_bwd(x, p, prefix, saved, d_adj):
-    """Closed-form backward of wcompute_fwd.  Returns dx and parameter grads."""
+    """Closed-form backward of wcompute_fwd.  Returns dx and parameter grads.  With shared rows the
+    gradient of a shared pair arrives summed over the graphs and is delivered to graph 0's nodes."""
     bsz, n, f = x.shape
-    ii, jj, w = saved["ii"], saved["jj"], saved["w"]
-    rg = ii.numel()
+    w = saved["w"]
+    rb, ri, rj, allg = saved["rows"]
     pairs = float(bsz * n * n)
     adj = saved["adj"]
     ds = adj * (d_adj - (adj * d_adj).sum(2, keepdim=True))                # softmax backward per row
-    g = ds[:, ii, jj] + ds[:, jj, ii]                                      # twin gradients summed
-    g = torch.where((ii == jj)[None, :], ds[:, ii, jj], g).reshape(-1)     # diagonal counted once (is 0)
+    twin = ds + ds.transpose(1, 2)                                         # twin gradients summed
+    twin = twin - torch.diag_embed(torch.diagonal(ds, dim1=1, dim2=2))     # diagonal counted once (is 0)
+    g = twin[rb, ri, rj]
+    g = torch.where(allg, twin.sum(0)[ri, rj], g)                          # shared rows: summed over the graphs
     grads = {}
     wl = p[f"{prefix}conv2d_last.weight"].flatten()
     grads[f"{prefix}conv2d_last.weight"] = (g[:, None] * saved["a"][4]).sum(0).reshape(1, -1, 1, 1)
@@ -103,13 +131,11 @@ def wcompute_bwd(x, p, prefix, saved, d_adj):
         grads[f"{prefix}conv2d_{k}.weight"] = (dh.t() @ saved["a"][k - 1]).reshape(*wk.shape, 1, 1)
         grads[f"{prefix}conv2d_{k}.bias"] = torch.zeros(wk.shape[0], dtype=x.dtype)   # BN removes the mean
         da = dh @ wk
-    dd = da.reshape(bsz, rg, f)
-    sgn = torch.sign(x[:, ii] - x[:, jj])
-    contrib = sgn * dd
-    dx = torch.zeros_like(x)
-    dx.index_add_(1, ii, contrib)
-    dx.index_add_(1, jj, -contrib)
-    return dx, grads
+    contrib = torch.sign(x[rb, ri] - x[rb, rj]) * da
+    dx = torch.zeros(bsz * n, f, dtype=x.dtype)
+    dx.index_add_(0, rb * n + ri, contrib)
+    dx.index_add_(0, rb * n + rj, -contrib)
+    return dx.reshape(bsz, n, f), grads
 
 
 def gconv_fwd(adj, x, p, prefix, bn_bool=True, lrelu=False):
@@ -160,7 +186,7 @@ def gconv_bwd(adj, x, p, prefix, saved, d_out, bn_bool=True, lrelu=False):
     return dx, d_adj, grads
 
 
-def gnn_nl_fwd_bwd(x, p, d_out, nf2, num_layers=2):
+def gnn_nl_fwd_bwd(x, p, d_out, nf2, num_layers=2, shared=None):
     """Whole GNN_nl forward + backward with the dense-concat bookkeeping the
     kernels use: one wide buffer xcat, later layers' dx accumulate into its
     leading columns."""
@@ -172,7 +198,7 @@ def gnn_nl_fwd_bwd(x, p, d_out, nf2, num_layers=2):
     f = f0
     for i in range(num_layers):
         xin = xcat[:, :, :f].clone()
-        adj, sw = wcompute_fwd(xin, p, f"layer_w{i}.")
+        adj, sw = wcompute_fwd(xin, p, f"layer_w{i}.", shared if i == 0 else None)   # later layers: per-graph x
         xn, sg = gconv_fwd(adj, xin, p, f"layer_l{i}.", True, True)
         xcat[:, :, f:f + nf2] = xn
         tape.append((f, sw, sg, adj))

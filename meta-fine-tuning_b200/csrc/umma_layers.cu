@@ -588,7 +588,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1)
 umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi epi, const float* __restrict__ wimg,
                  const __grid_constant__ UmmaShape s) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSETTING the shared array (an integer round trip would turn every
+    // shared-memory pointer below into a generic one: LD/ST instead of LDS/STS throughout the kernel)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t w_bytes = (uint32_t)s.KC * s.N_TILE * 128;
     float* Wsm = reinterpret_cast<float*>(smem);
     float* Asm = reinterpret_cast<float*>(smem + w_bytes);
@@ -1080,7 +1082,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp qop, float* __restrict__ dW, int ldw,
                   const __grid_constant__ WgradShape s) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSETTING the shared array (an integer round trip would turn every
+    // shared-memory pointer below into a generic one: LD/ST instead of LDS/STS throughout the kernel)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int stage_floats = (s.PB + s.QB) * WG_BLOCK_FLOATS;
     float* ring = reinterpret_cast<float*>(smem);
     float* stage = ring + (size_t)s.stages * stage_floats;

@@ -299,14 +299,22 @@ struct BnActT {
     __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
         return make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __device__ __forceinline__ float4 transform(uint2 raw, int k, const float* aux) const {
-        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+    // per-K-block constants of the thread's four channels: loaded once, used for all its rows
+    struct Consts { float4 sc, sh; bool on; };
+    __device__ __forceinline__ Consts consts(int k, const float* aux) const {
+        Consts c;
+        c.on = k < C;
+        const int kk = c.on ? k : 0;
+        c.sc = *reinterpret_cast<const float4*>(aux + kk);
+        c.sh = *reinterpret_cast<const float4*>(aux + kMaxC + kk);
+        return c;
+    }
+    __device__ __forceinline__ float4 transform(uint2 raw, const Consts& c) const {
+        if (!c.on) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 h = unpack_half4(raw);
-        float4 sc = *reinterpret_cast<const float4*>(aux + k);
-        float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
         float4 y;
-        y.x = fmaf(h.x, sc.x, sh.x); y.y = fmaf(h.y, sc.y, sh.y);
-        y.z = fmaf(h.z, sc.z, sh.z); y.w = fmaf(h.w, sc.w, sh.w);
+        y.x = fmaf(h.x, c.sc.x, c.sh.x); y.y = fmaf(h.y, c.sc.y, c.sh.y);
+        y.z = fmaf(h.z, c.sc.z, c.sh.z); y.w = fmaf(h.w, c.sc.w, c.sh.w);
         return make_float4(fmaxf(y.x, kSlope * y.x), fmaxf(y.y, kSlope * y.y), fmaxf(y.z, kSlope * y.z),
                            fmaxf(y.w, kSlope * y.w));
     }
@@ -347,17 +355,23 @@ struct DhInPlaceT {
     __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
         return make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __device__ __forceinline__ float4 transform(uint2, int, const float*) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ float row_weight(int r) const { return decode_row(r, g).w; }
-    __device__ __forceinline__ float4 transform2(float4 d, uint2 hraw, float w, int k, const float* aux) const {
-        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+    struct Consts { float4 P, Q, S; bool on; };
+    __device__ __forceinline__ Consts consts(int k, const float* aux) const {
+        Consts c;
+        c.on = k < C;
+        const int kk = c.on ? k : 0;
+        c.P = *reinterpret_cast<const float4*>(aux + kk);
+        c.Q = *reinterpret_cast<const float4*>(aux + kMaxC + kk);
+        c.S = *reinterpret_cast<const float4*>(aux + 2 * kMaxC + kk);
+        return c;
+    }
+    __device__ __forceinline__ float4 transform2(float4 d, uint2 hraw, float w, const Consts& c) const {
+        if (!c.on) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 h = unpack_half4(hraw);
-        float4 P = *reinterpret_cast<const float4*>(aux + k);
-        float4 Q = *reinterpret_cast<const float4*>(aux + kMaxC + k);
-        float4 S = *reinterpret_cast<const float4*>(aux + 2 * kMaxC + k);
         const float nw = -w;
-        return make_float4(fmaf(nw, fmaf(S.x, h.x, Q.x), P.x * d.x), fmaf(nw, fmaf(S.y, h.y, Q.y), P.y * d.y),
-                           fmaf(nw, fmaf(S.z, h.z, Q.z), P.z * d.z), fmaf(nw, fmaf(S.w, h.w, Q.w), P.w * d.w));
+        return make_float4(fmaf(nw, fmaf(c.S.x, h.x, c.Q.x), c.P.x * d.x), fmaf(nw, fmaf(c.S.y, h.y, c.Q.y), c.P.y * d.y),
+                           fmaf(nw, fmaf(c.S.z, h.z, c.Q.z), c.P.z * d.z), fmaf(nw, fmaf(c.S.w, h.w, c.Q.w), c.P.w * d.w));
     }
 };
 
@@ -457,10 +471,13 @@ struct EpiStoreU {
     int vec_ok;
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ float row_weight(int) const { return 1.f; }
+    struct Consts {};
+    __device__ __forceinline__ int row_stride() const { return ld; }
+    __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
     __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(int r, bool ok, float, int col, float4 v, uint2, int nvalid, float*,
-                                          float*, const float*) const {
-        float* o = out + (size_t)r * ld + col;
+    __device__ __forceinline__ void apply(int roff, bool ok, float, int col, float4 v, uint2, int nvalid, float*,
+                                          float*, const Consts&) const {
+        float* o = out + roff + col;
         if (!ok) return;
         if (vec_ok && nvalid == 4) {
             *reinterpret_cast<float4*>(o) = v;
@@ -485,10 +502,13 @@ struct EpiStoreBf16U {
     int ld;
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ float row_weight(int) const { return 1.f; }
+    struct Consts {};
+    __device__ __forceinline__ int row_stride() const { return ld; }
+    __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
     __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(int r, bool ok, float, int col, float4 v, uint2, int, float*, float*,
-                                          const float*) const {
-        if (ok && col < ld) *reinterpret_cast<uint2*>(out + (size_t)r * ld + col) = pack_bf4(v);
+    __device__ __forceinline__ void apply(int roff, bool ok, float, int col, float4 v, uint2, int, float*, float*,
+                                          const Consts&) const {
+        if (ok && col < ld) *reinterpret_cast<uint2*>(out + roff + col) = pack_bf4(v);
     }
     __device__ __forceinline__ void commit(int, float, float, const float*) const {}
 };
@@ -504,19 +524,15 @@ struct EpiFwdStatsU {
     PairGeom g;
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ float row_weight(int r) const { return decode_row(r, g).w; }
+    struct Consts {};
+    __device__ __forceinline__ int row_stride() const { return C; }
+    __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
     __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(int r, bool ok, float w, int col, float4 v, uint2, int, float* s0,
-                                          float* s1, const float*) const {
+    __device__ __forceinline__ void apply(int roff, bool ok, float w, int col, float4 v, uint2, int, float* s0,
+                                          float* s1, const Consts&) const {
         const uint2 packed = pack_half4(v);
-#ifndef MFT_EXP_NOSTORE
-        if (ok) *reinterpret_cast<uint2*>(H + (size_t)r * C + col) = packed;
-#else
-        if (ok && w > 1e30f) *reinterpret_cast<uint2*>(H + (size_t)r * C + col) = packed;
-#endif
+        if (ok) *reinterpret_cast<uint2*>(H + roff + col) = packed;
         v = unpack_half4(packed);            // statistics of what the next layer will actually read
-#ifdef MFT_EXP_NOSTATS
-        if (w < 1e30f) return;
-#endif
         s0[0] = fmaf(w, v.x, s0[0]); s1[0] = fmaf(w * v.x, v.x, s1[0]);
         s0[1] = fmaf(w, v.y, s0[1]); s1[1] = fmaf(w * v.y, v.y, s1[1]);
         s0[2] = fmaf(w, v.z, s0[2]); s1[2] = fmaf(w * v.z, v.z, s1[2]);
@@ -554,18 +570,25 @@ struct EpiDyU {
         }
     }
     __device__ __forceinline__ float row_weight(int) const { return 1.f; }
-    __device__ __forceinline__ uint2 prefetch(int r, int col) const { return ldg8(H + (size_t)r * C + col); }
-    __device__ __forceinline__ void apply(int r, bool ok, float, int col, float4 v, uint2 hraw, int, float* s0,
-                                          float* s1, const float* aux) const {
+    struct Consts { float4 sc, sh; };
+    __device__ __forceinline__ int row_stride() const { return C; }
+    __device__ __forceinline__ Consts consts(int col, const float* aux) const {   // once per chunk, not per row
+        Consts c;
+        c.sc = *reinterpret_cast<const float4*>(aux + col);
+        c.sh = *reinterpret_cast<const float4*>(aux + kMaxC + col);
+        return c;
+    }
+    __device__ __forceinline__ uint2 prefetch(int roff, int col) const { return ldg8(H + roff + col); }
+    __device__ __forceinline__ void apply(int roff, bool ok, float, int col, float4 v, uint2 hraw, int, float* s0,
+                                          float* s1, const Consts& k) const {
         const float4 h = unpack_half4(hraw);
-        float4 sc = *reinterpret_cast<const float4*>(aux + col);
-        float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + col);
+        const float4 sc = k.sc, sh = k.sh;
         float4 d;
         d.x = v.x * (fmaf(h.x, sc.x, sh.x) > 0.f ? 1.f : kSlope);
         d.y = v.y * (fmaf(h.y, sc.y, sh.y) > 0.f ? 1.f : kSlope);
         d.z = v.z * (fmaf(h.z, sc.z, sh.z) > 0.f ? 1.f : kSlope);
         d.w = v.w * (fmaf(h.w, sc.w, sh.w) > 0.f ? 1.f : kSlope);
-        if (ok) *reinterpret_cast<float4*>(dy + (size_t)r * C + col) = d;
+        if (ok) *reinterpret_cast<float4*>(dy + roff + col) = d;
         s0[0] += d.x; s1[0] = fmaf(d.x, h.x, s1[0]);
         s0[1] += d.y; s1[1] = fmaf(d.y, h.y, s1[1]);
         s0[2] += d.z; s1[2] = fmaf(d.z, h.z, s1[2]);
@@ -680,6 +703,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                     const int k = kc * UM_KB + c16 * 4;
                     uint2 hraw[RQ];
                     float4 d[RQ];
+                    const typename AOp::Consts kc4 = aop.consts(k, aux_a);
 #pragma unroll
                     for (int q = 0; q < RQ; ++q) {
                         const int rl = q * RSTEP + rsub;
@@ -689,7 +713,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
                     for (int q = 0; q < RQ; ++q) {
                         const int rl = q * RSTEP + rsub;
-                        float4 v = aop.transform2(d[q], hraw[q], wq[q], k, aux_a);
+                        float4 v = aop.transform2(d[q], hraw[q], wq[q], kc4);
                         if (row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
                         v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                         *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
@@ -724,10 +748,11 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                     mbar_wait(&empty[st], ph ^ 1);
                     float* blk = Asm + (size_t)st * UM_BLOCK_FLOATS;
                     const int k = kc * UM_KB + c16 * 4;
+                    const typename AOp::Consts kc4 = aop.consts(k, aux_a);
 #pragma unroll
                     for (int q = 0; q < RQ; ++q) {
                         const int rl = q * RSTEP + rsub;
-                        float4 v = aop.transform(raw[q], k, aux_a);
+                        float4 v = aop.transform(raw[q], kc4);
                         if (row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
                         v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                         *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
@@ -925,6 +950,9 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
             for (int q = 0; q < 8; ++q) wq[q] = wq_next[q];
             if (Epi::kRowWeight) load_weights(tile + gridDim.x, wq_next);
+            int roff[8];                                      // element offset of each of the thread's rows (clamped)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) roff[q] = min(row0 + q * 4 + rsub, s.R - 1) * epi.row_stride();
             mbar_wait(&tfull[acc], aph);
             tc_fence_after_sync();
             if (warp == UM_EPI_WARP0 && it == 0) MFT_MARK(12);             // first accumulator ready
@@ -939,7 +967,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                 if (Epi::kPrefetch && chunk_live(ch)) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)       // pure loads, row clamped in bounds
-                        dst[q] = epi.prefetch(min(row0 + q * 4 + rsub, s.R - 1), s.n0 + ch * 32 + c4);
+                        dst[q] = epi.prefetch(roff[q], s.n0 + ch * 32 + c4);
                 }
             };
             tmem_ld_32x32(tbase, v);
@@ -967,6 +995,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                     const int col = s.n0 + cl;            // global output column
                     if (cl < s.N_TILE && col < s.N) {
                         const int nvalid = min(4, s.N - col);
+                        const typename Epi::Consts ec = epi.consts(col, aux_e);
 #pragma unroll
                         // straight-line over the 8 rows (no branch per row: rows past the end hold
                         // exact zeros in TMEM and only their store is predicated off), so the eight
@@ -978,9 +1007,9 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int r = row0 + q * 4 + rsub;
-                            epi.apply(min(r, s.R - 1), r < s.R, wq[q], col, a[q], pre[Epi::kPrefetch ? (ch & 1) : 0][q],
+                            epi.apply(roff[q], r < s.R, wq[q], col, a[q], pre[Epi::kPrefetch ? (ch & 1) : 0][q],
                                       nvalid, s0[ch < UM_STAT_CHUNKS ? ch : 0], s1[ch < UM_STAT_CHUNKS ? ch : 0],
-                                      aux_e);
+                                      ec);
                         }
                     }
                     __syncwarp();
@@ -1486,6 +1515,10 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
     int passes = plan_passes(N, K, n0s, nts);
     if (passes == 0) {
         set_error(MFT_ERR_UNSUPPORTED, "umma_rows_gemm: no shared-memory plan for N=%d K=%d", N, K);
+        return MFT_ERR_UNSUPPORTED;
+    }
+    if ((size_t)R * (size_t)max(max(N, K), 256) >= ((size_t)1 << 31)) {   // the kernels index rows with 32-bit element offsets
+        set_error(MFT_ERR_UNSUPPORTED, "umma_rows_gemm: R=%d too large for 32-bit row offsets", R);
         return MFT_ERR_UNSUPPORTED;
     }
     const int ntiles = cdiv(R, UM_ROWS);

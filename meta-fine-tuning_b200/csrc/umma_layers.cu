@@ -474,10 +474,10 @@ struct EpiStoreU {
     struct Consts {};
     __device__ __forceinline__ int row_stride() const { return ld; }
     __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
-    __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(int roff, bool ok, float, int col, float4 v, uint2, int nvalid, float*,
+    __device__ __forceinline__ uint2 prefetch(unsigned, int) const { return make_uint2(0u, 0u); }
+    __device__ __forceinline__ void apply(unsigned roff, bool ok, float, int col, float4 v, uint2, int nvalid, float*,
                                           float*, const Consts&) const {
-        float* o = out + roff + col;
+        float* o = out + (roff + (unsigned)col);
         if (!ok) return;
         if (vec_ok && nvalid == 4) {
             *reinterpret_cast<float4*>(o) = v;
@@ -505,10 +505,12 @@ struct EpiStoreBf16U {
     struct Consts {};
     __device__ __forceinline__ int row_stride() const { return ld; }
     __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
-    __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(int roff, bool ok, float, int col, float4 v, uint2, int, float*, float*,
+    __device__ __forceinline__ uint2 prefetch(unsigned, int) const { return make_uint2(0u, 0u); }
+    __device__ __forceinline__ void apply(unsigned roff, bool ok, float, int col, float4 v, uint2, int, float*, float*,
                                           const Consts&) const {
-        if (ok && col < ld) *reinterpret_cast<uint2*>(out + roff + col) = pack_bf4(v);
+        uint2* o = reinterpret_cast<uint2*>(out + (roff + (unsigned)col));
+        const uint2 pk = pack_bf4(v);
+        if (ok && col < ld) *o = pk;
     }
     __device__ __forceinline__ void commit(int, float, float, const float*) const {}
 };
@@ -527,11 +529,12 @@ struct EpiFwdStatsU {
     struct Consts {};
     __device__ __forceinline__ int row_stride() const { return C; }
     __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
-    __device__ __forceinline__ uint2 prefetch(int, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(int roff, bool ok, float w, int col, float4 v, uint2, int, float* s0,
+    __device__ __forceinline__ uint2 prefetch(unsigned, int) const { return make_uint2(0u, 0u); }
+    __device__ __forceinline__ void apply(unsigned roff, bool ok, float w, int col, float4 v, uint2, int, float* s0,
                                           float* s1, const Consts&) const {
         const uint2 packed = pack_half4(v);
-        if (ok) *reinterpret_cast<uint2*>(H + roff + col) = packed;
+        uint2* o = reinterpret_cast<uint2*>(H + (roff + (unsigned)col));
+        if (ok) *o = packed;
         v = unpack_half4(packed);            // statistics of what the next layer will actually read
         s0[0] = fmaf(w, v.x, s0[0]); s1[0] = fmaf(w * v.x, v.x, s1[0]);
         s0[1] = fmaf(w, v.y, s0[1]); s1[1] = fmaf(w * v.y, v.y, s1[1]);
@@ -578,8 +581,8 @@ struct EpiDyU {
         c.sh = *reinterpret_cast<const float4*>(aux + kMaxC + col);
         return c;
     }
-    __device__ __forceinline__ uint2 prefetch(int roff, int col) const { return ldg8(H + roff + col); }
-    __device__ __forceinline__ void apply(int roff, bool ok, float, int col, float4 v, uint2 hraw, int, float* s0,
+    __device__ __forceinline__ uint2 prefetch(unsigned roff, int col) const { return ldg8(H + (roff + (unsigned)col)); }
+    __device__ __forceinline__ void apply(unsigned roff, bool ok, float, int col, float4 v, uint2 hraw, int, float* s0,
                                           float* s1, const Consts& k) const {
         const float4 h = unpack_half4(hraw);
         const float4 sc = k.sc, sh = k.sh;
@@ -588,7 +591,8 @@ struct EpiDyU {
         d.y = v.y * (fmaf(h.y, sc.y, sh.y) > 0.f ? 1.f : kSlope);
         d.z = v.z * (fmaf(h.z, sc.z, sh.z) > 0.f ? 1.f : kSlope);
         d.w = v.w * (fmaf(h.w, sc.w, sh.w) > 0.f ? 1.f : kSlope);
-        if (ok) *reinterpret_cast<float4*>(dy + roff + col) = d;
+        float4* o = reinterpret_cast<float4*>(dy + (roff + (unsigned)col));
+        if (ok) *o = d;
         s0[0] += d.x; s1[0] = fmaf(d.x, h.x, s1[0]);
         s0[1] += d.y; s1[1] = fmaf(d.y, h.y, s1[1]);
         s0[2] += d.z; s1[2] = fmaf(d.z, h.z, s1[2]);
@@ -950,9 +954,9 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
             for (int q = 0; q < 8; ++q) wq[q] = wq_next[q];
             if (Epi::kRowWeight) load_weights(tile + gridDim.x, wq_next);
-            int roff[8];                                      // element offset of each of the thread's rows (clamped)
+            unsigned roff[8];                                 // element offset of each of the thread's rows (clamped)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) roff[q] = min(row0 + q * 4 + rsub, s.R - 1) * epi.row_stride();
+            for (int q = 0; q < 8; ++q) roff[q] = (unsigned)(min(row0 + q * 4 + rsub, s.R - 1) * epi.row_stride());
             mbar_wait(&tfull[acc], aph);
             tc_fence_after_sync();
             if (warp == UM_EPI_WARP0 && it == 0) MFT_MARK(12);             // first accumulator ready

@@ -201,6 +201,12 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// Operand rounding in the producers: tcgen05 kind::tf32 reads only the upper 19 bits of an fp32
+// operand, so round-to-nearest (ties away, what cvt.rna does) is ONE integer add of half an ulp --
+// the three-instruction cvt.rna expansion (inf test, add, mask) made up a fifth of the producer loop.
+// Differs from cvt.rna only for |x| >= 2^128 * (1 - 2^-12) and non-finite values, which the
+// normalised activations / gradients of this path never are (a NaN stays a NaN).
+__device__ __forceinline__ float to_tf32_fast(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -697,6 +697,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
             load_weights(blockIdx.x, wq_next);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row0 = phys(tile) * UM_ROWS;
+                const bool partial = row0 + UM_ROWS > s.R;       // only the last tile has rows past the end
 #pragma unroll
                 for (int q = 0; q < RQ; ++q) wq[q] = wq_next[q];
                 load_weights(tile + gridDim.x, wq_next);
@@ -718,8 +719,8 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                     for (int q = 0; q < RQ; ++q) {
                         const int rl = q * RSTEP + rsub;
                         float4 v = aop.transform2(d[q], hraw[q], wq[q], kc4);
-                        if (row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                        if (partial && row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                         *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
                     }
                     fence_proxy_async_smem();
@@ -739,6 +740,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
             uint32_t ph = 0, rph = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row0 = phys(tile) * UM_ROWS;
+                const bool partial = row0 + UM_ROWS > s.R;       // only the last tile has rows past the end
                 for (int kc = 0; kc < s.KC; ++kc) {
                     mbar_wait(&rawfull[rs], rph);
                     const uint8_t* rawb = rawring + (size_t)rs * UM_RAW_BYTES;
@@ -757,8 +759,8 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                     for (int q = 0; q < RQ; ++q) {
                         const int rl = q * RSTEP + rsub;
                         float4 v = aop.transform(raw[q], kc4);
-                        if (row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                        if (partial && row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                         *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
                     }
                     fence_proxy_async_smem();
@@ -819,7 +821,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                 const int rl = q * RSTEP + rsub;
                 float4 v = aop.finish(buf[q], brow[q], k, aux_a);
                 if (!((vm >> q) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                 *reinterpret_cast<float4*>(dst + (rl >> 3) * 256 + sw * 32 + ((c16 ^ sw) << 2)) = v;
             }
             fence_proxy_async_smem();
@@ -977,7 +979,11 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
             tmem_ld_32x32(tbase, v);
             load_pre(0, pre[0]);
             long long t_ld = 0, t_sts = 0, t_apply = 0, tA = 0, tB = 0;
+#ifdef MFT_UMMA_TIMING
             const bool timing = dbg != nullptr && warp == UM_EPI_WARP0 && lane == 0;
+#else
+            constexpr bool timing = false;   // phase counters (slots 13-15) only in -DMFT_UMMA_TIMING builds
+#endif
 #pragma unroll
             for (int ch = 0; ch < UM_MAX_CHUNKS; ++ch) {
                 if (ch < nchunks) {
@@ -1218,7 +1224,7 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                 for (int b = 0; b < WG_MAX_PB; ++b) {
                     if (b < s.PB) {
                         float4 v = ok ? pop.transform(dv[b], hv[b], w, b * UM_KB + c16 * 4, aux_p) : zero;
-                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                        v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                         *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
                     }
                 }
@@ -1228,7 +1234,7 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                         float4 v;
                         if constexpr (QOp::kTma) v = ok ? qop.transform(qv[b], b * UM_KB + c16 * 4, aux_q) : zero;
                         else v = ok ? qop.finish(qraw[QOp::kTma ? 0 : b], qr, b * UM_KB + c16 * 4, aux_q) : zero;
-                        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                        v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                         *reinterpret_cast<float4*>(dst + (s.PB + b) * WG_BLOCK_FLOATS) = v;
                     }
                 }
@@ -1277,7 +1283,7 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             for (int b = 0; b < WG_MAX_PB; ++b) {
                 if (b < s.PB) {
                     float4 v = ok ? pop.finish(praw[b], pr, b * UM_KB + c16 * 4, aux_p) : zero;
-                    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                    v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                     *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
                 }
             }
@@ -1286,7 +1292,7 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             for (int b = 0; b < WG_MAX_QB; ++b) {
                 if (b < s.QB) {
                     float4 v = ok ? qop.finish(qraw[b], qr, b * UM_KB + c16 * 4, aux_q) : zero;
-                    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                    v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                     *reinterpret_cast<float4*>(dst + (s.PB + b) * WG_BLOCK_FLOATS) = v;
                 }
             }

@@ -254,6 +254,33 @@ template <> struct TapeD<true> {
     }
 };
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot for two lanes of arithmetic.
+// The hot loops of the tensor-core kernels are bound by instruction issue of one warp per scheduler.
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f2 a, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

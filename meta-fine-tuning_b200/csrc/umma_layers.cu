@@ -312,11 +312,13 @@ struct BnActT {
     __device__ __forceinline__ float4 transform(uint2 raw, const Consts& c) const {
         if (!c.on) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 h = unpack_half4(raw);
-        float4 y;
-        y.x = fmaf(h.x, c.sc.x, c.sh.x); y.y = fmaf(h.y, c.sc.y, c.sh.y);
-        y.z = fmaf(h.z, c.sc.z, c.sh.z); y.w = fmaf(h.w, c.sc.w, c.sh.w);
-        return make_float4(fmaxf(y.x, kSlope * y.x), fmaxf(y.y, kSlope * y.y), fmaxf(y.z, kSlope * y.z),
-                           fmaxf(y.w, kSlope * y.w));
+        const f2 ylo = fma2(pack2(h.x, h.y), pack2(c.sc.x, c.sc.y), pack2(c.sh.x, c.sh.y));
+        const f2 yhi = fma2(pack2(h.z, h.w), pack2(c.sc.z, c.sc.w), pack2(c.sh.z, c.sh.w));
+        const f2 sl = pack2(kSlope, kSlope);
+        float4 y, z;
+        unpack2(ylo, y.x, y.y); unpack2(yhi, y.z, y.w);
+        unpack2(mul2(ylo, sl), z.x, z.y); unpack2(mul2(yhi, sl), z.z, z.w);
+        return make_float4(fmaxf(y.x, z.x), fmaxf(y.y, z.y), fmaxf(y.z, z.z), fmaxf(y.w, z.w));
     }
 };
 
@@ -369,9 +371,14 @@ struct DhInPlaceT {
     __device__ __forceinline__ float4 transform2(float4 d, uint2 hraw, float w, const Consts& c) const {
         if (!c.on) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 h = unpack_half4(hraw);
-        const float nw = -w;
-        return make_float4(fmaf(nw, fmaf(c.S.x, h.x, c.Q.x), c.P.x * d.x), fmaf(nw, fmaf(c.S.y, h.y, c.Q.y), c.P.y * d.y),
-                           fmaf(nw, fmaf(c.S.z, h.z, c.Q.z), c.P.z * d.z), fmaf(nw, fmaf(c.S.w, h.w, c.Q.w), c.P.w * d.w));
+        const f2 nw = pack2(-w, -w);
+        const f2 lo = fma2(nw, fma2(pack2(c.S.x, c.S.y), pack2(h.x, h.y), pack2(c.Q.x, c.Q.y)),
+                           mul2(pack2(c.P.x, c.P.y), pack2(d.x, d.y)));
+        const f2 hi = fma2(nw, fma2(pack2(c.S.z, c.S.w), pack2(h.z, h.w), pack2(c.Q.z, c.Q.w)),
+                           mul2(pack2(c.P.z, c.P.w), pack2(d.z, d.w)));
+        float4 r;
+        unpack2(lo, r.x, r.y); unpack2(hi, r.z, r.w);
+        return r;
     }
 };
 
@@ -413,9 +420,12 @@ struct DhT {                                     // P = dH_k from (dy_k, H_k)
         float4 P = *reinterpret_cast<const float4*>(aux + k);
         float4 Q = *reinterpret_cast<const float4*>(aux + kMaxC + k);
         float4 S = *reinterpret_cast<const float4*>(aux + 2 * kMaxC + k);
-        const float nw = -w;
-        return make_float4(fmaf(nw, fmaf(S.x, h.x, Q.x), P.x * d.x), fmaf(nw, fmaf(S.y, h.y, Q.y), P.y * d.y),
-                           fmaf(nw, fmaf(S.z, h.z, Q.z), P.z * d.z), fmaf(nw, fmaf(S.w, h.w, Q.w), P.w * d.w));
+        const f2 nw = pack2(-w, -w);
+        const f2 lo = fma2(nw, fma2(pack2(S.x, S.y), pack2(h.x, h.y), pack2(Q.x, Q.y)), mul2(pack2(P.x, P.y), pack2(d.x, d.y)));
+        const f2 hi = fma2(nw, fma2(pack2(S.z, S.w), pack2(h.z, h.w), pack2(Q.z, Q.w)), mul2(pack2(P.z, P.w), pack2(d.z, d.w)));
+        float4 r;
+        unpack2(lo, r.x, r.y); unpack2(hi, r.z, r.w);
+        return r;
     }
 };
 
@@ -450,11 +460,13 @@ struct BnActQT {                                 // Q = LeakyReLU(BN(H_{k-1}))
         const float4 h = unpack_half4(hraw);
         float4 sc = *reinterpret_cast<const float4*>(aux + k);
         float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
-        float4 y;
-        y.x = fmaf(h.x, sc.x, sh.x); y.y = fmaf(h.y, sc.y, sh.y);
-        y.z = fmaf(h.z, sc.z, sh.z); y.w = fmaf(h.w, sc.w, sh.w);
-        return make_float4(fmaxf(y.x, kSlope * y.x), fmaxf(y.y, kSlope * y.y), fmaxf(y.z, kSlope * y.z),
-                           fmaxf(y.w, kSlope * y.w));
+        const f2 ylo = fma2(pack2(h.x, h.y), pack2(sc.x, sc.y), pack2(sh.x, sh.y));
+        const f2 yhi = fma2(pack2(h.z, h.w), pack2(sc.z, sc.w), pack2(sh.z, sh.w));
+        const f2 sl = pack2(kSlope, kSlope);
+        float4 y, z;
+        unpack2(ylo, y.x, y.y); unpack2(yhi, y.z, y.w);
+        unpack2(mul2(ylo, sl), z.x, z.y); unpack2(mul2(yhi, sl), z.z, z.w);
+        return make_float4(fmaxf(y.x, z.x), fmaxf(y.y, z.y), fmaxf(y.z, z.z), fmaxf(y.w, z.w));
     }
 };
 
@@ -536,10 +548,11 @@ struct EpiFwdStatsU {
         uint2* o = reinterpret_cast<uint2*>(H + (roff + (unsigned)col));
         if (ok) *o = packed;
         v = unpack_half4(packed);            // statistics of what the next layer will actually read
-        s0[0] = fmaf(w, v.x, s0[0]); s1[0] = fmaf(w * v.x, v.x, s1[0]);
-        s0[1] = fmaf(w, v.y, s0[1]); s1[1] = fmaf(w * v.y, v.y, s1[1]);
-        s0[2] = fmaf(w, v.z, s0[2]); s1[2] = fmaf(w * v.z, v.z, s1[2]);
-        s0[3] = fmaf(w, v.w, s0[3]); s1[3] = fmaf(w * v.w, v.w, s1[3]);
+        const f2 ww = pack2(w, w), vlo = pack2(v.x, v.y), vhi = pack2(v.z, v.w);
+        unpack2(fma2(ww, vlo, pack2(s0[0], s0[1])), s0[0], s0[1]);
+        unpack2(fma2(ww, vhi, pack2(s0[2], s0[3])), s0[2], s0[3]);
+        unpack2(fma2(mul2(ww, vlo), vlo, pack2(s1[0], s1[1])), s1[0], s1[1]);
+        unpack2(fma2(mul2(ww, vhi), vhi, pack2(s1[2], s1[3])), s1[2], s1[3]);
     }
     __device__ __forceinline__ void commit(int c, float v0, float v1, const float*) const {
         stat_add(sums, C, c, 0, v0);
@@ -585,18 +598,20 @@ struct EpiDyU {
     __device__ __forceinline__ void apply(unsigned roff, bool ok, float, int col, float4 v, uint2 hraw, int, float* s0,
                                           float* s1, const Consts& k) const {
         const float4 h = unpack_half4(hraw);
-        const float4 sc = k.sc, sh = k.sh;
+        const f2 hlo = pack2(h.x, h.y), hhi = pack2(h.z, h.w);
+        float4 y;
+        unpack2(fma2(hlo, pack2(k.sc.x, k.sc.y), pack2(k.sh.x, k.sh.y)), y.x, y.y);
+        unpack2(fma2(hhi, pack2(k.sc.z, k.sc.w), pack2(k.sh.z, k.sh.w)), y.z, y.w);
+        const f2 dlo = mul2(pack2(v.x, v.y), pack2(y.x > 0.f ? 1.f : kSlope, y.y > 0.f ? 1.f : kSlope));
+        const f2 dhi = mul2(pack2(v.z, v.w), pack2(y.z > 0.f ? 1.f : kSlope, y.w > 0.f ? 1.f : kSlope));
         float4 d;
-        d.x = v.x * (fmaf(h.x, sc.x, sh.x) > 0.f ? 1.f : kSlope);
-        d.y = v.y * (fmaf(h.y, sc.y, sh.y) > 0.f ? 1.f : kSlope);
-        d.z = v.z * (fmaf(h.z, sc.z, sh.z) > 0.f ? 1.f : kSlope);
-        d.w = v.w * (fmaf(h.w, sc.w, sh.w) > 0.f ? 1.f : kSlope);
+        unpack2(dlo, d.x, d.y); unpack2(dhi, d.z, d.w);
         float4* o = reinterpret_cast<float4*>(dy + (roff + (unsigned)col));
         if (ok) *o = d;
-        s0[0] += d.x; s1[0] = fmaf(d.x, h.x, s1[0]);
-        s0[1] += d.y; s1[1] = fmaf(d.y, h.y, s1[1]);
-        s0[2] += d.z; s1[2] = fmaf(d.z, h.z, s1[2]);
-        s0[3] += d.w; s1[3] = fmaf(d.w, h.w, s1[3]);
+        unpack2(add2(pack2(s0[0], s0[1]), dlo), s0[0], s0[1]);
+        unpack2(add2(pack2(s0[2], s0[3]), dhi), s0[2], s0[3]);
+        unpack2(fma2(dlo, hlo, pack2(s1[0], s1[1])), s1[0], s1[1]);
+        unpack2(fma2(dhi, hhi, pack2(s1[2], s1[3])), s1[2], s1[3]);
     }
     __device__ __forceinline__ void commit(int c, float v0, float v1, const float* aux) const {
         float m = aux[2 * kMaxC + c], r = aux[3 * kMaxC + c];

@@ -1131,7 +1131,9 @@ static inline size_t wgrad_smem_bytes(const WgradShape& s) {
            (3 + 3) * kMaxC * 4 + (size_t)s.raw_stages * s.raw_bytes + 32 * 8 + 16;
 }
 
-template <class POp, class QOp>
+// PBc / QBc: compile-time operand block counts (0 = take them from the shape at run time; the run-time
+// guards cost more instructions per chunk than the arithmetic of the small layers)
+template <class POp, class QOp, int PBc, int QBc>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp qop, float* __restrict__ dW, int ldw,
                   const __grid_constant__ WgradShape s) {
@@ -1139,7 +1141,9 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
     // 1024-byte alignment by OFFSETTING the shared array (an integer round trip would turn every
     // shared-memory pointer below into a generic one: LD/ST instead of LDS/STS throughout the kernel)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int stage_floats = (s.PB + s.QB) * WG_BLOCK_FLOATS;
+    const int nPB = PBc ? PBc : s.PB, nQB = QBc ? QBc : s.QB;
+    constexpr int kPBmax = PBc ? PBc : WG_MAX_PB, kQBmax = QBc ? QBc : WG_MAX_QB;
+    const int stage_floats = (nPB + nQB) * WG_BLOCK_FLOATS;
     float* ring = reinterpret_cast<float*>(smem);
     float* stage = ring + (size_t)s.stages * stage_floats;
     float* aux_p = stage + UM_ROWS * UM_STAGE_LD;
@@ -1197,19 +1201,25 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             uint32_t rph = 0;
             const uint32_t off_h = WG_ROWS * s.Cout * 4, off_q = off_h + WG_ROWS * s.Cout * 2;
             typename QOp::Row qr;
-            typename QOp::Raw qraw[QOp::kTma ? 1 : WG_MAX_QB];
+            typename QOp::Raw qraw[QOp::kTma ? 1 : kQBmax];
+            // the row multiplicity is a dependent global load (pair table): fetched one chunk ahead
+            float w_next = (c_begin < c_end && c_begin * WG_ROWS + rl < s.R) ? pop.row(c_begin * WG_ROWS + rl).w : 0.f;
             for (int c = c_begin; c < c_end; ++c) {
                 const int r = c * WG_ROWS + rl;
                 const bool ok = r < s.R;
-                const float w = ok ? pop.row(r).w : 0.f;
+                const float w = w_next;
+                {
+                    const int rn = r + WG_ROWS;
+                    w_next = (c + 1 < c_end && rn < s.R) ? pop.row(rn).w : 0.f;
+                }
                 mbar_wait(&rawfull[rs], rph);
                 const uint8_t* rb = rawring + (size_t)rs * s.raw_bytes;
-                float4 dv[WG_MAX_PB];
-                uint2 hv[WG_MAX_PB];
-                uint2 qv[WG_MAX_QB];
+                float4 dv[kPBmax];
+                uint2 hv[kPBmax];
+                uint2 qv[kQBmax];
 #pragma unroll
-                for (int b = 0; b < WG_MAX_PB; ++b) {
-                    if (b < s.PB) {
+                for (int b = 0; b < kPBmax; ++b) {
+                    if (PBc != 0 || b < s.PB) {
                         const int k = min(b * UM_KB + c16 * 4, s.Cout - 4);
                         dv[b] = *reinterpret_cast<const float4*>(rb + ((size_t)rl * s.Cout + k) * 4);
                         hv[b] = *reinterpret_cast<const uint2*>(rb + off_h + ((size_t)rl * s.Cout + k) * 2);
@@ -1217,8 +1227,8 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                 }
                 if constexpr (QOp::kTma) {
 #pragma unroll
-                    for (int b = 0; b < WG_MAX_QB; ++b)
-                        if (b < s.QB) {
+                    for (int b = 0; b < kQBmax; ++b)
+                        if (QBc != 0 || b < s.QB) {
                             const int k = min(b * UM_KB + c16 * 4, s.Cin - 4);
                             qv[b] = *reinterpret_cast<const uint2*>(rb + off_q + ((size_t)rl * s.Cin + k) * 2);
                         }
@@ -1229,28 +1239,28 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                 if constexpr (!QOp::kTma) {                       // |x_i - x_j| from the L2-resident node matrix
                     qr = qop.row(ok ? r : 0);
 #pragma unroll
-                    for (int b = 0; b < WG_MAX_QB; ++b)
-                        if (b < s.QB) qop.fetch(qr, b * UM_KB + c16 * 4, qraw[b]);
+                    for (int b = 0; b < kQBmax; ++b)
+                        if (QBc != 0 || b < s.QB) qop.fetch(qr, b * UM_KB + c16 * 4, qraw[b]);
                 }
                 mbar_wait(&empty[st], ph ^ 1);
                 float* dst = ring + (size_t)st * stage_floats + off;
                 const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int b = 0; b < WG_MAX_PB; ++b) {
-                    if (b < s.PB) {
+                for (int b = 0; b < kPBmax; ++b) {
+                    if (PBc != 0 || b < s.PB) {
                         float4 v = ok ? pop.transform(dv[b], hv[b], w, b * UM_KB + c16 * 4, aux_p) : zero;
                         v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                         *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
                     }
                 }
 #pragma unroll
-                for (int b = 0; b < WG_MAX_QB; ++b) {
-                    if (b < s.QB) {
+                for (int b = 0; b < kQBmax; ++b) {
+                    if (QBc != 0 || b < s.QB) {
                         float4 v;
                         if constexpr (QOp::kTma) v = ok ? qop.transform(qv[b], b * UM_KB + c16 * 4, aux_q) : zero;
                         else v = ok ? qop.finish(qraw[QOp::kTma ? 0 : b], qr, b * UM_KB + c16 * 4, aux_q) : zero;
                         v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
-                        *reinterpret_cast<float4*>(dst + (s.PB + b) * WG_BLOCK_FLOATS) = v;
+                        *reinterpret_cast<float4*>(dst + (nPB + b) * WG_BLOCK_FLOATS) = v;
                     }
                 }
                 fence_proxy_async_smem();
@@ -1259,8 +1269,8 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                 if (++st == s.stages) { st = 0; ph ^= 1; }
             }
         } else {
-        typename POp::Raw praw[WG_MAX_PB];
-        typename QOp::Raw qraw[WG_MAX_QB];
+        typename POp::Raw praw[kPBmax];
+        typename QOp::Raw qraw[kQBmax];
         bool ok = false;
         typename POp::Row pr;
         typename QOp::Row qr;
@@ -1276,15 +1286,15 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             ok = r < s.R;
             pr = pop.row(ok ? r : 0);
 #pragma unroll
-            for (int b = 0; b < WG_MAX_PB; ++b)
-                if (b < s.PB) pop.fetch(pr, b * UM_KB + c16 * 4, praw[b]);
+            for (int b = 0; b < kPBmax; ++b)
+                if (PBc != 0 || b < s.PB) pop.fetch(pr, b * UM_KB + c16 * 4, praw[b]);
         };
         auto fetch_q = [&](int chunk) {
             const int r = chunk * WG_ROWS + rl;
             qr = qop.row(r < s.R ? r : 0);
 #pragma unroll
-            for (int b = 0; b < WG_MAX_QB; ++b)
-                if (b < s.QB) qop.fetch(qr, b * UM_KB + c16 * 4, qraw[b]);
+            for (int b = 0; b < kQBmax; ++b)
+                if (QBc != 0 || b < s.QB) qop.fetch(qr, b * UM_KB + c16 * 4, qraw[b]);
         };
         if (my_chunks > 0) {
             fetch_p(c_begin);
@@ -1295,8 +1305,8 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             float* dst = ring + (size_t)st * stage_floats + off;
             const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int b = 0; b < WG_MAX_PB; ++b) {
-                if (b < s.PB) {
+            for (int b = 0; b < kPBmax; ++b) {
+                if (PBc != 0 || b < s.PB) {
                     float4 v = ok ? pop.finish(praw[b], pr, b * UM_KB + c16 * 4, aux_p) : zero;
                     v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                     *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
@@ -1304,11 +1314,11 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             }
             if (kLateQ) fetch_q(c);
 #pragma unroll
-            for (int b = 0; b < WG_MAX_QB; ++b) {
-                if (b < s.QB) {
+            for (int b = 0; b < kQBmax; ++b) {
+                if (QBc != 0 || b < s.QB) {
                     float4 v = ok ? qop.finish(qraw[b], qr, b * UM_KB + c16 * 4, aux_q) : zero;
                     v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
-                    *reinterpret_cast<float4*>(dst + (s.PB + b) * WG_BLOCK_FLOATS) = v;
+                    *reinterpret_cast<float4*>(dst + (nPB + b) * WG_BLOCK_FLOATS) = v;
                 }
             }
             fence_proxy_async_smem();
@@ -1359,7 +1369,7 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                 mbar_wait(&full[st], ph);
                 tc_fence_after_sync();
                 const uint32_t pb = ring0 + (uint32_t)st * stage_floats * 4;
-                const uint32_t qb = pb + (uint32_t)s.PB * lbo;
+                const uint32_t qb = pb + (uint32_t)nPB * lbo;
                 for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
                     const uint32_t acc_on = (c > c_begin || ks > 0) ? 1u : 0u;
                     const uint64_t bdesc = make_desc_sw128(qb + ks * kstep, sbo, lbo, 1);
@@ -1601,7 +1611,7 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
     return MFT_OK;
 }
 
-template <class POp, class QOp>
+template <class POp, class QOp, bool kSpecialize = true>
 static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R, int Cout, int Cin,
                       cudaStream_t st, int cat, int* copies_out = nullptr) {
     WgradShape s{};
@@ -1650,12 +1660,26 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
     if (copies_out) *copies_out = cdiv(nchunks, s.chunks_per_cta);
     s.reverse = next_direction();
     size_t smem = wgrad_smem_bytes(s);
-    MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<POp, QOp>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    ProfScope ps(cat, st);
-    umma_wgrad_kernel<POp, QOp><<<cdiv(nchunks, s.chunks_per_cta), WG_THREADS, smem, st>>>(pop, qop, dW, ldw, s);
-    MFT_CHECK_LAUNCH();
-    return MFT_OK;
+    const int grid_x = cdiv(nchunks, s.chunks_per_cta);
+#define MFT_WG_LAUNCH(PBC, QBC)                                                                                      \
+    do {                                                                                                             \
+        MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<POp, QOp, PBC, QBC>,                                    \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        ProfScope ps(cat, st);                                                                                       \
+        umma_wgrad_kernel<POp, QOp, PBC, QBC><<<grid_x, WG_THREADS, smem, st>>>(pop, qop, dW, ldw, s);                \
+        MFT_CHECK_LAUNCH();                                                                                          \
+        return MFT_OK;                                                                                               \
+    } while (0)
+    // the block counts of the reference's layer widths (nf = 96: 192/192/96/96, F = 133/181/229) are compiled in
+    if (kSpecialize) {
+        if (s.PB == 6 && s.QB == 6) MFT_WG_LAUNCH(6, 6);
+        if (s.PB == 3 && s.QB == 6) MFT_WG_LAUNCH(3, 6);
+        if (s.PB == 3 && s.QB == 3) MFT_WG_LAUNCH(3, 3);
+        if (s.PB == 6 && s.QB == 5) MFT_WG_LAUNCH(6, 5);
+        if (s.PB == 6 && s.QB == 8) MFT_WG_LAUNCH(6, 8);
+    }
+    MFT_WG_LAUNCH(0, 0);
+#undef MFT_WG_LAUNCH
 }
 
 // Test entry: dW[Cout, Cin] += P[R, Cout]^T Q[R, Cin] with plain operands.
@@ -1663,7 +1687,7 @@ int umma_debug_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW
                      int Cin, cudaStream_t st) {
     PlainU p{P, ldp, Cout, plain_vec_ok(P, ldp, Cout)};
     PlainU q{Q, ldq, Cin, plain_vec_ok(Q, ldq, Cin)};
-    return umma_wgrad(p, q, dW, ldw, R, Cout, Cin, st, PC_MISC);
+    return umma_wgrad<PlainU, PlainU, false>(p, q, dW, ldw, R, Cout, Cin, st, PC_MISC);
 }
 
 bool umma_shape_supported(int F, int nf) {

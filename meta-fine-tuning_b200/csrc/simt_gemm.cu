@@ -178,11 +178,12 @@ bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc
     const float* Ab = A.p + (size_t)b * A.sb;
     const float* Bb = Bm.p + (size_t)b * Bm.sb;
     const int total = OS_T * K;
-    if (A.s1 == 1) {                             // k contiguous in memory
-        for (int idx = t; idx < total; idx += 256) {
-            const int m = idx / K, k = idx - m * K;
+    const int lane = t & 31, wrp = t >> 5;
+    if (A.s1 == 1) {                             // k contiguous in memory: a warp walks along a row (no division)
+        for (int m = wrp; m < OS_T; m += 8) {
             const bool ok = m0 + m < M;
-            cp_async4(As + m * lda + k, Ab + (size_t)(ok ? m0 + m : 0) * A.s0 + k, ok);
+            const float* src = Ab + (size_t)(ok ? m0 + m : 0) * A.s0;
+            for (int k = lane; k < K; k += 32) cp_async4(As + m * lda + k, src + k, ok);
         }
     } else {                                     // m contiguous (or general strides)
         for (int idx = t; idx < total; idx += 256) {
@@ -197,11 +198,11 @@ bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc
             const bool ok = n0 + n < N;
             cp_async4(Bs + k * OS_T + n, Bb + (size_t)k * Bm.s0 + (ok ? n0 + n : 0), ok);
         }
-    } else {                                     // k contiguous (or general strides)
-        for (int idx = t; idx < total; idx += 256) {
-            const int n = idx / K, k = idx - n * K;
-            const bool ok = n0 + n < N;
-            cp_async4(Bs + k * OS_T + n, Bb + (size_t)k * Bm.s0 + (size_t)(ok ? n0 + n : 0) * Bm.s1, ok);
+    } else {                                     // k contiguous (or general strides): a warp walks along a column;
+        for (int n = wrp; n < OS_T; n += 8) {    // the panel is kept [n][k] (odd stride) so that neither these
+            const bool ok = n0 + n < N;          // writes nor the reads below conflict on banks
+            const float* src = Bb + (size_t)(ok ? n0 + n : 0) * Bm.s1;
+            for (int k = lane; k < K; k += 32) cp_async4(Bs + n * lda + k, src + (size_t)k * Bm.s0, ok);
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -210,14 +211,26 @@ bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc
     const int tx = t & 15, ty = t >> 4;          // thread -> outputs (2*ty + {0,1}, 2*tx + {0,1})
     const float* a0 = As + (2 * ty) * lda;
     const float* a1 = a0 + lda;
-    const float* bp = Bs + 2 * tx;
     float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+    if (Bm.s1 == 1) {                            // B panel [k][n]
+        const float* bp = Bs + 2 * tx;
 #pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-        const float x0 = a0[k], x1 = a1[k];
-        const float2 y = *reinterpret_cast<const float2*>(bp + k * OS_T);
-        c00 = fmaf(x0, y.x, c00); c01 = fmaf(x0, y.y, c01);
-        c10 = fmaf(x1, y.x, c10); c11 = fmaf(x1, y.y, c11);
+        for (int k = 0; k < K; ++k) {
+            const float x0 = a0[k], x1 = a1[k];
+            const float2 y = *reinterpret_cast<const float2*>(bp + k * OS_T);
+            c00 = fmaf(x0, y.x, c00); c01 = fmaf(x0, y.y, c01);
+            c10 = fmaf(x1, y.x, c10); c11 = fmaf(x1, y.y, c11);
+        }
+    } else {                                     // B panel [n][k]
+        const float* b0 = Bs + (2 * tx) * lda;
+        const float* b1 = b0 + lda;
+#pragma unroll 8
+        for (int k = 0; k < K; ++k) {
+            const float x0 = a0[k], x1 = a1[k];
+            const float y0 = b0[k], y1 = b1[k];
+            c00 = fmaf(x0, y0, c00); c01 = fmaf(x0, y1, c01);
+            c10 = fmaf(x1, y0, c10); c11 = fmaf(x1, y1, c11);
+        }
     }
     const float acc[2][2] = {{c00, c01}, {c10, c11}};
 #pragma unroll
@@ -240,14 +253,14 @@ cudaError_t launch_bgemm(BView A, BView Bm, float* C, long scb, int ldc, int bat
     if (batch <= 0 || M <= 0 || N <= 0) return cudaSuccess;
     if (K >= 1 && K <= OS_MAXK) {
         static bool attr_set = false;
-        const size_t max_smem = (size_t)(OS_T * (OS_MAXK | 1) + OS_MAXK * OS_T) * sizeof(float);
+        const size_t max_smem = (size_t)(2 * OS_T * (OS_MAXK | 1)) * sizeof(float);
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(bgemm_oneshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)max_smem);
             if (e != cudaSuccess) return e;
             attr_set = true;
         }
-        const size_t smem = (size_t)(OS_T * (K | 1) + K * OS_T) * sizeof(float);
+        const size_t smem = (size_t)(2 * OS_T * (K | 1)) * sizeof(float);
         dim3 grid(cdiv(N, OS_T), cdiv(M, OS_T), batch);
         bgemm_oneshot_kernel<<<grid, 256, smem, st>>>(A, Bm, C, scb, ldc, M, N, K, beta);
         return cudaGetLastError();

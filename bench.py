@@ -47,6 +47,17 @@ def head_flops(bsz, n, backward=True):
     return per_pair * (3 if backward else 1) * bsz * n * n
 
 
+def gemm_traffic(shape):
+    """DRAM bytes per edge-MLP GEMM launch from the committed `ncu` capture of this workload
+    (profiles/r01_gemm_traffic.json, written by tools/ncu_traffic.py), or None."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_traffic.json")
+    try:
+        rec = json.load(open(path))
+    except (OSError, ValueError):
+        return None
+    return rec.get("bytes_per_launch") if rec.get("shape", "5w20s") == shape else None
+
+
 def shape_dims(shape):
     n_way, n_shot, n_query, compress = SHAPES[shape]
     k = round(n_shot / 2) if compress else n_shot
@@ -388,7 +399,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": (achieved / tf32_peak) if achieved else None, "traffic": None,
+                "frac": (achieved / tf32_peak) if achieved else None, "traffic": gemm_traffic(args.shape),
                 "kernel": "edge-MLP GEMM launches (4 fwd + 4 dgrad + 4 wgrad per Wcompute, x3)",
                 "launches_per_step": gemm_n, "avg_launch_ms": (gemm_ms / gemm_n) if gemm_n else None,
                 "algorithmic_flops_per_step": alg,

@@ -161,6 +161,21 @@ int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way,
                 void* saved, void* workspace, int precision,
                 const unsigned char* shared_nodes, void* stream);
 
+/* ---- GnnNet pre-head: fc + graph assembly (gnnnet.py:30, 71-83, 35-38, 212) ----------------
+ * feat [n_way, n_support+n_query, feat_dim] contiguous (backbone features of one episode)
+ *   z = BatchNorm1d(Linear(feat))            (fc->fc_w [D, feat_dim], fc_b, bn_g, bn_b [D]; batch statistics)
+ *   nodes [n_query, n_way*(n_support+1), D+n_way]: graph q = per class its n_support support rows
+ *   then its q-th query row; columns D.. hold the one-hot class of a support node, zeros for a query.
+ * The backward sums the node gradients of a support row over the n_query graphs, runs BatchNorm1d
+ * backward and returns the fc / bn gradients (overwritten) and, if d_feat != NULL, d_feat. */
+size_t mft_head_saved_bytes(int n_way, int n_support, int n_query, int D);
+size_t mft_head_workspace_bytes(int n_way, int n_support, int n_query, int D);
+int mft_head_fwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
+                 const mft_gconv_params* fc, float* nodes, void* saved, void* workspace, void* stream);
+int mft_head_bwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
+                 const mft_gconv_params* fc, const float* d_nodes, float* d_feat,
+                 const mft_gconv_grads* g, void* saved, void* workspace, void* stream);
+
 /* ---- measurement hooks (new; the reference has no profiler) ---- */
 
 /* Kernels launched by this library in this process so far (bench.py: gpu_launches). */

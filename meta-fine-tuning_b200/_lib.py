@@ -72,6 +72,11 @@ SIGNATURES = {
     "mft_gnn_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, _vp, _vp, _i, C.c_char_p, _vp]),
     "mft_gnn_bwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, C.POINTER(GnnGrads), _vp, _vp,
                          _i, C.c_char_p, _vp]),
+    "mft_head_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "mft_head_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mft_head_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GconvParams), _vp, _vp, _vp, _vp]),
+    "mft_head_bwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GconvParams), _vp, _vp, C.POINTER(GconvGrads), _vp, _vp,
+                          _vp]),
     "mft_debug_umma_gemm_workspace_bytes": (_sz, [_i, _i]),
     "mft_debug_umma_gemm": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mft_debug_umma_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),

@@ -150,6 +150,29 @@ int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, con
                    (cudaStream_t)stream);
 }
 
+size_t mft_head_saved_bytes(int n_way, int n_support, int n_query, int D) {
+    return head_saved_bytes(n_way * (n_support + n_query), D);
+}
+size_t mft_head_workspace_bytes(int n_way, int n_support, int n_query, int D) {
+    return head_workspace_bytes(n_way * (n_support + n_query), D);
+}
+
+int mft_head_fwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
+                 const mft_gconv_params* fc, float* nodes, void* saved, void* workspace, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(feat && fc && nodes && saved && workspace, "mft_head_fwd: null pointer");
+    return head_fwd(feat, feat_dim, n_way, n_support, n_query, D, fc, nodes, saved, workspace, (cudaStream_t)stream);
+}
+
+int mft_head_bwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
+                 const mft_gconv_params* fc, const float* d_nodes, float* d_feat, const mft_gconv_grads* g,
+                 void* saved, void* workspace, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(feat && fc && d_nodes && g && saved && workspace, "mft_head_bwd: null pointer");
+    return head_bwd(feat, feat_dim, n_way, n_support, n_query, D, fc, d_nodes, d_feat, g, saved, workspace,
+                    (cudaStream_t)stream);
+}
+
 size_t mft_debug_umma_gemm_workspace_bytes(int N, int K) { return (umma_wimg_floats(N, K) + 64) * sizeof(float); }
 
 int mft_debug_umma_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w, float* C, int ldc,

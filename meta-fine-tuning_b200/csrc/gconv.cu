@@ -183,6 +183,184 @@ __global__ void add_cols_kernel(float* __restrict__ dx, int ldx, const float* __
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Pre-head of GnnNet: fc = Linear(feat_dim -> D) + BatchNorm1d over the n_way*(n_support+n_query)
+// episode rows (gnnnet.py:30, 71-78), then the assembly of the n_query graphs (gnnnet.py:79-83: every
+// graph = all supports + the q-th query of each class) with the support one-hot labels appended
+// (gnnnet.py:35-38, 212).  The assembly is pure data movement; here BN-apply writes straight into the
+// [n_query, n_way*(n_support+1), D+n_way] node tensor, and the backward gathers the node gradients
+// back onto the episode rows (sum over the graphs for a support row) in the kernel that also forms
+// the BatchNorm-backward reductions.
+// ---------------------------------------------------------------------------------------------
+__global__ void head_assemble_kernel(const float* __restrict__ Y, int D, const double* sums, const float* gamma,
+                                     const float* beta, int n_way, int n_support, int n_query,
+                                     float* __restrict__ nodes) {
+    __shared__ float aux[4 * kMaxC];
+    const int rows = n_way * (n_support + n_query);
+    bn_smem_fill(bn_smem_at(aux), sums, gamma, beta, D, 1.0 / (double)rows);
+    __syncthreads();
+    BnSmem s = bn_smem_at(aux);
+    const int npg = n_way * (n_support + 1), ldn = D + n_way;
+    const int total = n_query * npg;
+    for (int node = blockIdx.x; node < total; node += gridDim.x) {
+        const int q = node / npg, n = node - q * npg;
+        const int c = n / (n_support + 1), sidx = n - c * (n_support + 1);
+        const bool is_query = sidx == n_support;
+        const int src = c * (n_support + n_query) + (is_query ? n_support + q : sidx);
+        float* dst = nodes + (size_t)node * ldn;
+        for (int f = threadIdx.x; f < ldn; f += blockDim.x) {
+            float v;
+            if (f < D) v = fmaf((Y[(size_t)src * D + f] - s.mean[f]) * s.rstd[f], s.gamma[f], s.beta[f]);
+            else v = (!is_query && f - D == c) ? 1.f : 0.f;
+            dst[f] = v;
+        }
+    }
+}
+
+// dz[row, f] = sum over the graphs that hold the row; column sums of dz and dz*zhat for BatchNorm backward
+__global__ void __launch_bounds__(kGcRows * kGcCols)
+head_dz_kernel(const float* __restrict__ d_nodes, const float* __restrict__ Y, int D, const double* fsums,
+               int n_way, int n_support, int n_query, float* __restrict__ dY, double* bsums) {
+    __shared__ float aux[2 * kMaxC];
+    __shared__ float red[2][kGcRows][kMaxC];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int rows = n_way * (n_support + n_query);
+    for (int c = ty * kGcCols + tx; c < D; c += kGcRows * kGcCols) {
+        float m, r;
+        bn_mean_rstd(fsums, D, c, 1.0 / (double)rows, m, r);
+        aux[c] = m; aux[kMaxC + c] = r;
+    }
+    __syncthreads();
+    const int npg = n_way * (n_support + 1), ldn = D + n_way;
+    const int row = blockIdx.x * kGcRows + ty;
+    const bool live = row < rows;
+    const int c = live ? row / (n_support + n_query) : 0, sidx = live ? row - c * (n_support + n_query) : 0;
+    for (int f = tx; f < D; f += kGcCols) {
+        float d = 0.f, dh = 0.f;
+        if (live) {
+            if (sidx < n_support) {
+                const int n = c * (n_support + 1) + sidx;
+                for (int q = 0; q < n_query; ++q) d += d_nodes[((size_t)q * npg + n) * ldn + f];
+            } else {
+                const int q = sidx - n_support, n = c * (n_support + 1) + n_support;
+                d = d_nodes[((size_t)q * npg + n) * ldn + f];
+            }
+            dh = d * ((Y[(size_t)row * D + f] - aux[f]) * aux[kMaxC + f]);
+            dY[(size_t)row * D + f] = d;
+        }
+        red[0][ty][f] = d;
+        red[1][ty][f] = dh;
+    }
+    __syncthreads();
+    if (ty == 0) {
+        for (int f = tx; f < D; f += kGcCols) {
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < kGcRows; ++q) { v0 += red[0][q][f]; v1 += red[1][q][f]; }
+            stat_add(bsums, D, f, 0, v0);
+            stat_add(bsums, D, f, 1, v1);
+        }
+    }
+}
+
+}  // namespace
+
+struct HeadLayout {
+    float* Y;        // saved: pre-BN fc output [rows, D]
+    double* fsums;   // saved: BatchNorm1d statistics
+    float* dY;       // workspace bwd: [rows, D]
+    double* bsums;   // workspace bwd
+    size_t saved_bytes, workspace_bytes;
+};
+
+static HeadLayout head_layout(int rows, int D, void* saved, void* workspace) {
+    HeadLayout L;
+    Carver sv(saved);
+    L.Y = sv.take<float>((size_t)rows * D);
+    L.fsums = sv.take<double>(kStatSlot);
+    L.saved_bytes = sv.used();
+    Carver ws(workspace);
+    L.dY = ws.take<float>((size_t)rows * D);
+    L.bsums = ws.take<double>(kStatSlot);
+    L.workspace_bytes = ws.used();
+    return L;
+}
+
+size_t head_saved_bytes(int rows, int D) { return head_layout(rows, D, nullptr, nullptr).saved_bytes; }
+size_t head_workspace_bytes(int rows, int D) { return head_layout(rows, D, nullptr, nullptr).workspace_bytes; }
+
+int head_fwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
+             const mft_gconv_params* fc, float* nodes, void* saved, void* workspace, cudaStream_t st) {
+    MFT_REQUIRE(n_way > 0 && n_support > 0 && n_query > 0 && feat_dim > 0 && D > 0, "head_fwd: bad shape");
+    MFT_REQUIRE(D <= kMaxC, "head_fwd: D=%d exceeds %d", D, kMaxC);
+    MFT_REQUIRE(fc->bn_g && fc->bn_b, "head_fwd: the fc pre-head has a BatchNorm1d (gnnnet.py:30)");
+    const int rows = n_way * (n_support + n_query);
+    HeadLayout L = head_layout(rows, D, saved, workspace);
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * kStatSlot, st));
+    {
+        BView X{feat, 0, feat_dim, 1};               // (m = row, k)
+        BView W{fc->fc_w, 0, 1, feat_dim};           // (k, n = c) -> fc_w[c*feat_dim + k]
+        ProfScope ps(PC_GCONV_FWD, st);
+        MFT_CHECK_CUDA(launch_bgemm(X, W, L.Y, 0, D, 1, rows, D, feat_dim, 0.f, st));
+    }
+    {
+        ProfScope ps(PC_GCONV_FWD, st);
+        gconv_bias_stats_kernel<<<cdiv(rows, kGcRows), dim3(kGcCols, kGcRows), 0, st>>>(L.Y, D, fc->fc_b, rows, D, L.fsums);
+        MFT_CHECK_LAUNCH();
+    }
+    {
+        ProfScope ps(PC_GCONV_FWD, st);
+        const int total = n_query * n_way * (n_support + 1);
+        head_assemble_kernel<<<min(total, 148 * 8), 160, 0, st>>>(L.Y, D, L.fsums, fc->bn_g, fc->bn_b, n_way, n_support,
+                                                                   n_query, nodes);
+        MFT_CHECK_LAUNCH();
+    }
+    return MFT_OK;
+}
+
+int head_bwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
+             const mft_gconv_params* fc, const float* d_nodes, float* d_feat, const mft_gconv_grads* g, void* saved,
+             void* workspace, cudaStream_t st) {
+    MFT_REQUIRE(n_way > 0 && n_support > 0 && n_query > 0 && feat_dim > 0 && D > 0, "head_bwd: bad shape");
+    MFT_REQUIRE(D <= kMaxC, "head_bwd: D=%d exceeds %d", D, kMaxC);
+    const int rows = n_way * (n_support + n_query);
+    HeadLayout L = head_layout(rows, D, saved, workspace);
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * kStatSlot, st));
+    MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)D * feat_dim, st));
+    {
+        ProfScope ps(PC_GCONV_BWD, st);
+        head_dz_kernel<<<cdiv(rows, kGcRows), dim3(kGcCols, kGcRows), 0, st>>>(d_nodes, L.Y, D, L.fsums, n_way, n_support,
+                                                                               n_query, L.dY, L.bsums);
+        MFT_CHECK_LAUNCH();
+    }
+    {
+        const int total = rows * D;
+        ProfScope ps(PC_GCONV_BWD, st);
+        gconv_dy_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(L.dY, L.Y, rows, D, L.fsums, fc->bn_g, L.bsums);
+        MFT_CHECK_LAUNCH();
+    }
+    {
+        ProfScope ps(PC_GCONV_BWD, st);
+        gconv_small_grads_kernel<<<cdiv(D, 128), 128, 0, st>>>(L.bsums, D, 1, g->fc_b, g->bn_g, g->bn_b);
+        MFT_CHECK_LAUNCH();
+    }
+    {
+        PlainOp dy{L.dY, D};
+        PlainOp qx{feat, feat_dim};
+        ProfScope ps(PC_GCONV_BWD, st);
+        MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, feat_dim, D, feat_dim, rows, st)));
+    }
+    if (d_feat) {   // only when the features carry a gradient (meta-training through the backbone)
+        BView Dy{L.dY, 0, D, 1};                     // (m = row, k = c)
+        BView Wf{fc->fc_w, 0, feat_dim, 1};          // (k = c, n = f)
+        ProfScope ps(PC_GCONV_BWD, st);
+        MFT_CHECK_CUDA(launch_bgemm(Dy, Wf, d_feat, 0, feat_dim, 1, rows, feat_dim, D, 0.f, st));
+    }
+    return MFT_OK;
+}
+
+namespace {
 }  // namespace
 
 GcLayout gc_layout(int B, int N, int F, int n_out, void* saved, void* workspace) {

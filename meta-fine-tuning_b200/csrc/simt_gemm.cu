@@ -153,12 +153,12 @@ bgemm64_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int 
     }
 }
 
-// One-shot variant for K <= 256 (every Gconv product except the weight gradients): a 32x32 output
+// One-shot variant for K <= 512 (every Gconv product except the weight gradients, and GnnNet's fc): a 32x32 output
 // tile whose complete A and B panels are brought into shared memory by cp.async in ONE round of
 // loads (the looped kernels above pay one L2 round trip per 16-32 columns of K with nothing to
 // overlap it: 27-CTA launches that took 12-17 us), then multiplied from shared memory.
 constexpr int OS_T = 32;
-constexpr int OS_MAXK = 256;
+constexpr int OS_MAXK = 512;                        // 2 x 32 x 513 floats = 131 KB of panels at most
 
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid) {
     const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));

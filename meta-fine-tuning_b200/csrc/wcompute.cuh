@@ -76,4 +76,12 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
               int lrelu, const float* d_out, int ldo, float* dx, float* d_adj, const mft_gconv_grads* g,
               void* saved, void* workspace, cudaStream_t st);
 
+size_t head_saved_bytes(int rows, int D);
+size_t head_workspace_bytes(int rows, int D);
+int head_fwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
+             const mft_gconv_params* fc, float* nodes, void* saved, void* workspace, cudaStream_t st);
+int head_bwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
+             const mft_gconv_params* fc, const float* d_nodes, float* d_feat, const mft_gconv_grads* g, void* saved,
+             void* workspace, cudaStream_t st);
+
 }  // namespace mft

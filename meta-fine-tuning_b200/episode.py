@@ -14,7 +14,10 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .gnn import GNN_nl
+import ctypes as C
+
+from . import _lib
+from .gnn import GNN_nl, _alloc_like_flat, _blob, _contig, _fill_gc, _require_cuda, _stream
 
 __all__ = ["support_label", "build_graphs", "select_scores", "query_labels", "GnnHead"]
 
@@ -61,6 +64,51 @@ def select_scores(out: torch.Tensor, n_way: int, n_support: int, n_query: int) -
     return out.view(n_query, n_way, n_support + 1, n_way)[:, :, -1].permute(1, 0, 2).contiguous().view(-1, n_way)
 
 
+class _HeadFn(torch.autograd.Function):
+    """feat [n_way, n_support+n_query, feat_dim] -> nodes [n_query, n_way*(n_support+1), D+n_way]:
+    fc (Linear + BatchNorm1d, batch statistics) + graph assembly + label one-hots in one library call
+    per direction (mft_head_fwd / _bwd; gnnnet.py:30, 71-83, 212)."""
+
+    @staticmethod
+    def forward(ctx, feat, n_way, n_support, n_query, *params):
+        lib = _lib.load_library()
+        _require_cuda(feat, "GnnHead")
+        feat = feat.contiguous()
+        feat_dim = feat.size(-1)
+        params = _contig(params)                   # fc.weight [D, feat_dim], fc.bias, bn.weight, bn.bias
+        D = params[0].shape[0]
+        p = _lib.GconvParams()
+        _fill_gc(p, params)
+        nodes = torch.empty(n_query, n_way * (n_support + 1), D + n_way, dtype=torch.float32, device=feat.device)
+        saved = _blob(lib.mft_head_saved_bytes(n_way, n_support, n_query, D), feat.device)
+        ws = _blob(lib.mft_head_workspace_bytes(n_way, n_support, n_query, D), feat.device)
+        with torch.cuda.device(feat.device):
+            _lib.check(lib.mft_head_fwd(feat.data_ptr(), feat_dim, n_way, n_support, n_query, D, C.byref(p),
+                                        nodes.data_ptr(), saved.data_ptr(), ws.data_ptr(), _stream()), "mft_head_fwd")
+        ctx.save_for_backward(feat, saved, *params)
+        ctx.meta = (n_way, n_support, n_query, D, feat_dim)
+        return nodes
+
+    @staticmethod
+    def backward(ctx, d_nodes):
+        lib = _lib.load_library()
+        feat, saved, *params = ctx.saved_tensors
+        n_way, n_support, n_query, D, feat_dim = ctx.meta
+        d_nodes = d_nodes.contiguous()
+        p = _lib.GconvParams()
+        _fill_gc(p, params)
+        grads = _alloc_like_flat(params)
+        g = _lib.GconvGrads()
+        _fill_gc(g, grads)
+        d_feat = torch.empty_like(feat) if ctx.needs_input_grad[0] else None
+        ws = _blob(lib.mft_head_workspace_bytes(n_way, n_support, n_query, D), feat.device)
+        with torch.cuda.device(feat.device):
+            _lib.check(lib.mft_head_bwd(feat.data_ptr(), feat_dim, n_way, n_support, n_query, D, C.byref(p),
+                                        d_nodes.data_ptr(), d_feat.data_ptr() if d_feat is not None else None,
+                                        C.byref(g), saved.data_ptr(), ws.data_ptr(), _stream()), "mft_head_bwd")
+        return (d_feat, None, None, None, *grads)
+
+
 class GnnHead(nn.Module):
     """``fc`` + ``gnn`` of the reference GnnNet (gnnnet.py:30-31), driven on features.
 
@@ -73,6 +121,10 @@ class GnnHead(nn.Module):
         # The graphs build_graphs makes differ only in their query nodes: tell GNN_nl so that
         # layer_w0 evaluates the support-support pairs once (GNN_nl.shared_nodes).
         self.share_support = share_support
+        # fc + BatchNorm1d + graph assembly as one library call per direction (mft_head_fwd/_bwd) instead
+        # of the reference's Linear / BatchNorm1d / cat / expand kernels; the compressed variant
+        # (gnnnet_copy.py) averages the supports in between and keeps the torch ops
+        self.fused_pre_head = True
         self.n_way = n_way
         self.n_support_in = n_support
         self.compress = compress
@@ -85,6 +137,14 @@ class GnnHead(nn.Module):
         self.register_buffer("support_label", support_label(n_way, self.n_support), persistent=False)
 
     def nodes(self, feat: torch.Tensor) -> torch.Tensor:
+        if self.fused_pre_head and not self.compress and feat.is_cuda and feat.dtype == torch.float32:
+            lin, bn = self.fc[0], self.fc[1]
+            per_class = feat.numel() // (self.n_way * feat.size(-1))
+            if per_class != self.n_support + self.n_query:
+                raise ValueError("GnnHead: %d rows per class, expected n_support + n_query = %d"
+                                 % (per_class, self.n_support + self.n_query))
+            return _HeadFn.apply(feat.reshape(self.n_way, per_class, feat.size(-1)), self.n_way, self.n_support,
+                                 self.n_query, lin.weight, lin.bias, bn.weight, bn.bias)
         z = self.fc(feat.reshape(-1, feat.size(-1)))
         z = z.view(self.n_way, -1, z.size(1))
         return build_graphs(z, self.support_label, self.n_way, self.n_support_in, self.n_query, self.compress)

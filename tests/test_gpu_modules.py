@@ -132,3 +132,46 @@ def test_cuda_graph_replay_equals_eager():
         for p in params:
             p.grad = None
     mft_b200.set_precision("auto")
+
+
+@pytest.mark.parametrize("n_support,n_query", [(5, 16), (20, 16), (1, 15), (5, 3)])
+def test_fused_pre_head_equals_torch_ops(n_support, n_query):
+    """mft_head_fwd/_bwd (fc Linear + BatchNorm1d + graph assembly + labels) against the reference's
+    op sequence (nn.Linear, nn.BatchNorm1d, cat/expand; gnnnet.py:71-83, 212) run by torch."""
+    import mft_b200
+    torch.manual_seed(7)
+    head = mft_b200.GnnHead(5, n_support).cuda()
+    head.n_query = n_query
+    feat = torch.randn(5, n_support + n_query, 512, device="cuda")
+    up = torch.randn(n_query, 5 * (n_support + 1), 133, device="cuda")
+    res = []
+    for fused in (True, False):
+        head.fused_pre_head = fused
+        head.zero_grad(set_to_none=True)
+        f = feat.clone().requires_grad_(True)
+        nodes = head.nodes(f)
+        (nodes * up).sum().backward()
+        res.append((nodes.detach(), f.grad.clone(), {k: v.grad.clone() for k, v in head.fc.named_parameters()}))
+    (n1, df1, g1), (n0, df0, g0) = res
+    assert n1.shape == n0.shape
+    assert torch.equal(n1[..., 128:], n0[..., 128:])                     # label one-hots: exact
+    assert U.rel(n1.cpu().numpy(), n0.cpu().numpy()) < 2e-6
+    assert U.rel(df1.cpu().numpy(), df0.cpu().numpy()) < 2e-5
+    for k in g0:
+        a, b = g1[k].cpu().numpy(), g0[k].cpu().numpy()
+        if k == "0.bias":                       # Linear bias under BatchNorm: analytically zero
+            assert np.abs(a).max() <= 1e-6 and np.abs(b).max() < 1e-3
+        else:
+            assert U.rel(a, b) < 5e-5, (k, U.rel(a, b))
+
+
+def test_fused_pre_head_without_feature_gradient_and_bad_shape():
+    import mft_b200
+    head = mft_b200.GnnHead(5, 5).cuda()
+    head.n_query = 16
+    feat = torch.randn(5, 21, 512, device="cuda")
+    loss = head.set_forward_loss(feat)          # feat carries no gradient: d_feat is not computed
+    loss.backward()
+    assert all(p.grad is not None for p in head.parameters())
+    with pytest.raises(ValueError, match="rows per class"):
+        head.nodes(torch.randn(5, 20, 512, device="cuda"))

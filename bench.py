@@ -296,14 +296,37 @@ def run_ours(args):
     loss_ev = [torch.cuda.Event() for _ in range(2)]
     losses = []
 
-    def e2e_step(fh, k):
+    # Input prefetch: the H2D copy of step k+1 runs on a copy stream into one of two staging buffers
+    # while step k computes; the step itself starts with a device-side copy staging -> static input.
+    copy_stream = torch.cuda.Stream()
+    staging = [torch.empty_like(feats_host[0], device=dev) for _ in range(2)]
+    staged_ev = [torch.cuda.Event() for _ in range(2)]
+    consumed_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(fh, k):
+        slot = k & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed_ev[slot])        # the step that last read this buffer is done with it
+            staging[slot].copy_(fh, non_blocking=True)
+            staged_ev[slot].record(copy_stream)
+
+    def e2e_step(fh, k, nxt=None):
+        if k == 0 or not getattr(e2e_step, "primed", False):
+            prefetch(fh, k)
+            e2e_step.primed = True
+        if nxt is not None:
+            prefetch(nxt, k + 1)
+        torch.cuda.current_stream().wait_event(staged_ev[k & 1])
+        fdev = staging[k & 1]
         if use_graph:
-            loss = g_e2e(fh)                      # pinned host -> static device tensor inside the call
+            loss = g_e2e(fdev)                    # device copy into the graph's static input + replay
+            consumed_ev[k & 1].record()
         else:
             for prm in all_params:
                 prm.grad = None
-            loss = head.set_forward_loss(fh.to(dev, non_blocking=True))
+            loss = head.set_forward_loss(fdev)
             loss.backward()
+            consumed_ev[k & 1].record()
         if world > 1:
             parallel.allreduce_mean_grads(all_params, world)
         slot = k & 1
@@ -319,14 +342,17 @@ def run_ours(args):
             losses.append(float(loss_host[k & 1][0]))
 
     for it in range(args.warmup):
+        e2e_step.primed = False
         e2e_step(feats_host[it], it)
     e2e_drain(args.warmup)
     losses.clear()
     barrier()
+    e2e_step.primed = False
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        e2e_step(feats_host[args.warmup + k], k)
+        nxt = feats_host[args.warmup + k + 1] if k + 1 < args.steps else None
+        e2e_step(feats_host[args.warmup + k], k, nxt)
     e2e_drain(args.steps)
     e1.record()
     barrier()
@@ -393,7 +419,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_eps, "unit": "episodes/s",
                     "h2d_bytes_per_step": int(feats_host[0].numel() * 4), "d2h_bytes_per_step": 4,
-                    "what": "pinned host features -> H2D -> fc(Linear+BN1d) -> graphs -> GNN_nl -> CE -> backward "
+                    "what": "pinned host features -> H2D (prefetched one step ahead on a copy stream) -> fc(Linear+BN1d) -> "
+                            "graphs -> GNN_nl -> CE -> backward "
                             "(all head parameters) -> loss copied to pinned host memory every step (read by the host one "
                             "step later, so the queue never drains)"},
             "gpu_launches": int(launches),

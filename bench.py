@@ -47,7 +47,7 @@ def head_flops(bsz, n, backward=True):
     return per_pair * (3 if backward else 1) * bsz * n * n
 
 
-def gemm_traffic(shape):
+def gemm_traffic(shape, share, prec):
     """DRAM bytes per edge-MLP GEMM launch from the committed `ncu` capture of this workload
     (profiles/r01_gemm_traffic.json, written by tools/ncu_traffic.py), or None."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_traffic.json")
@@ -55,7 +55,8 @@ def gemm_traffic(shape):
         rec = json.load(open(path))
     except (OSError, ValueError):
         return None
-    return rec.get("bytes_per_launch") if rec.get("shape", "5w20s") == shape else None
+    same = rec.get("config") == {"shape": shape, "share_support": bool(share), "precision": prec}
+    return rec.get("bytes_per_launch") if same else None   # the capture describes ONE configuration
 
 
 def shape_dims(shape):
@@ -426,7 +427,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": (achieved / tf32_peak) if achieved else None, "traffic": gemm_traffic(args.shape),
+                "frac": (achieved / tf32_peak) if achieved else None, "traffic": gemm_traffic(args.shape, not args.no_share, prec),
                 "kernel": "edge-MLP GEMM launches (4 fwd + 4 dgrad + 4 wgrad per Wcompute, x3)",
                 "launches_per_step": gemm_n, "avg_launch_ms": (gemm_ms / gemm_n) if gemm_n else None,
                 "algorithmic_flops_per_step": alg,

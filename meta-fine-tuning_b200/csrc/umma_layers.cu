@@ -157,43 +157,7 @@ struct AbsDiffU {
     }
 };
 
-// a = LeakyReLU(scale*h + shift), scale = gamma*rstd, shift = beta - mean*scale (C % 4 == 0)
 __device__ __forceinline__ uint2 ldg8(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
-
-struct BnActU {
-    static constexpr bool kTma = false;
-    static constexpr int kAhead = 2;
-    const __half* H;                         // fp16 tape
-    int C;
-    const double* sums;
-    const float* gamma;
-    const float* beta;
-    double inv_count;
-    struct Row { const __half* h; };
-    struct Raw { uint2 h; };
-    __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
-        for (int c = tid; c < C; c += nthreads) {
-            float m, r;
-            bn_mean_rstd(sums, C, c, inv_count, m, r);
-            float sc = gamma[c] * r;
-            aux[c] = sc;
-            aux[kMaxC + c] = beta[c] - m * sc;
-        }
-    }
-    __device__ __forceinline__ Row row(int r) const { return Row{H + (size_t)r * C}; }
-    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const { o.h = ldg8(rw.h + min(k, C - 4)); }
-    __device__ __forceinline__ float4 finish(const Raw& raw, const Row&, int k, const float* aux) const {
-        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
-        struct { float4 h; } r = {unpack_half4(raw.h)};
-        float4 sc = *reinterpret_cast<const float4*>(aux + k);
-        float4 sh = *reinterpret_cast<const float4*>(aux + kMaxC + k);
-        float4 y;
-        y.x = fmaf(r.h.x, sc.x, sh.x); y.y = fmaf(r.h.y, sc.y, sh.y);
-        y.z = fmaf(r.h.z, sc.z, sh.z); y.w = fmaf(r.h.w, sc.w, sh.w);
-        return make_float4(fmaxf(y.x, kSlope * y.x), fmaxf(y.y, kSlope * y.y), fmaxf(y.z, kSlope * y.z),
-                           fmaxf(y.w, kSlope * y.w));
-    }
-};
 
 struct PlainU {
     static constexpr bool kTma = false;
@@ -225,50 +189,9 @@ struct PlainU {
 
 // dH = gamma*rstd*(dy - w*m1 - w*hhat*m2): BatchNorm backward of the twin-summed gradient, fused
 // into the operand build so that dH never exists in HBM.  With P = gamma*rstd, S = P*rstd*m2,
-// Q = P*m1 - S*mean this is  dH = P*dy - w*(Q + S*h)  (C % 4 == 0).
-struct DhU {
-    static constexpr bool kTma = false;
-    static constexpr int kAhead = 1;
-    const float* dy;                         // fp32 (bf16 gradients cost 10% accuracy on small problems)
-    const __half* H;                         // fp16 tape
-    int C;
-    const double* fsums;
-    const float* gamma;
-    const double* bsums;
-    double inv_count;
-    PairGeom g;
-    struct Row { int off; float w; };
-    struct Raw { float4 d; uint2 h; };
-    __device__ __forceinline__ void init(float* aux, int tid, int nthreads) const {
-        for (int c = tid; c < C; c += nthreads) {
-            float m, r;
-            bn_mean_rstd(fsums, C, c, inv_count, m, r);
-            float P = gamma[c] * r;
-            float S = P * r * (float)(stat_get(bsums, C, c, 1) * inv_count);
-            aux[c] = P;
-            aux[kMaxC + c] = P * (float)(stat_get(bsums, C, c, 0) * inv_count) - S * m;
-            aux[2 * kMaxC + c] = S;
-        }
-    }
-    __device__ __forceinline__ Row row(int r) const { return Row{r * C, decode_row(r, g).w}; }
-    __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
-        const int kk = min(k, C - 4);
-        o.d = ldg4(dy + (size_t)rw.off + kk);
-        o.h = ldg8(H + (size_t)rw.off + kk);
-    }
-    __device__ __forceinline__ float4 finish(const Raw& raw, const Row& rw, int k, const float* aux) const {
-        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
-        struct { float4 d, h; } r = {raw.d, unpack_half4(raw.h)};
-        float4 P = *reinterpret_cast<const float4*>(aux + k);
-        float4 Q = *reinterpret_cast<const float4*>(aux + kMaxC + k);
-        float4 S = *reinterpret_cast<const float4*>(aux + 2 * kMaxC + k);
-        const float nw = -rw.w;
-        return make_float4(fmaf(nw, fmaf(S.x, r.h.x, Q.x), P.x * r.d.x), fmaf(nw, fmaf(S.y, r.h.y, Q.y), P.y * r.d.y),
-                           fmaf(nw, fmaf(S.z, r.h.z, Q.z), P.z * r.d.z), fmaf(nw, fmaf(S.w, r.h.w, Q.w), P.w * r.d.w));
-    }
-};
+// Q = P*m1 - S*mean this is  dH = P*dy - w*(Q + S*h)  (C % 4 == 0): DhInPlaceT (rows kernel) and DhT (wgrad).
 
-// Tensor-map variant of BnActU for the rows kernel: the raw [128 rows x 32 ch] block of H lands in
+// a = LeakyReLU(scale*h + shift), scale = gamma*rstd, shift = beta - mean*scale (C % 4 == 0), tensor-map fed: the raw [128 rows x 32 ch] block of H lands in
 // the ring stage by TMA, already in the K-major SWIZZLE_128B arrangement the MMA wants (the TMA and
 // UMMA 128-byte swizzles are the same function), and the producer warps apply BN + LeakyReLU + TF32
 // rounding IN PLACE.  No register staging, no scoreboard-limited prefetch: every free stage has a
@@ -322,7 +245,7 @@ struct BnActT {
     }
 };
 
-// Tensor-map variant of DhU for the rows kernel (dgrad A operand).  The fp32 [128 rows x 32 ch] block
+// dH for the rows kernel (dgrad A operand), tensor-map fed.  The fp32 [128 rows x 32 ch] block
 // of dy lands by TMA (SWIZZLE_128B) DIRECTLY in the ring stage -- the K-major swizzled arrangement
 // the MMA reads -- and the matching fp16 block of H in a raw slot of the same index; the producer
 // threads then turn dy into dH = P*dy - w*(Q + S*h) in place.  No register staging: every stage the

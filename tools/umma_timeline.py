@@ -1,5 +1,8 @@
 """Per-CTA phase timeline (clock64) of one tcgen05 rows-GEMM launch inside a real 5w20s forward /
-backward (debug tool, GPU only).  usage: python tools/umma_timeline.py [launch index ...]"""
+backward (debug tool, GPU only).  usage: python tools/umma_timeline.py [launch index ...]
+The three "epi cycles" phase counters are only filled by a library built with -DMFT_UMMA_TIMING
+(make EXTRA=-DMFT_UMMA_TIMING); the default build leaves them at 0 to keep clock reads out of the
+epilogue loop."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -182,6 +182,11 @@ int mft_head_bwd(const float* feat, int feat_dim, int n_way, int n_support, int 
 unsigned long long mft_launch_count(void);
 /* Bracket every kernel launch with CUDA events on its stream (on != 0) or stop (0). */
 int mft_prof_enable(int on);
+/* Launch overlap (new): 0 = plain stream order; 1 = the consecutive tcgen05 GEMM launches of an
+ * edge MLP use programmatic dependent launch (prologue of launch n+1 -- barrier/TMEM set-up and the
+ * resident weight image -- runs under the tail of launch n); 2 = also the row kernels around them
+ * (default; environment MFT_PDL).  Results are identical at every level.  Returns the old level. */
+int mft_set_pdl(int level);
 int mft_prof_categories(void);
 const char* mft_prof_name(int cat);
 /* Synchronise, then ms[c] / counts[c] = summed device time and launches of category c

@@ -83,6 +83,7 @@ SIGNATURES = {
     "mft_debug_set_timeline": (_i, [_vp, _i]),
     "mft_launch_count": (C.c_ulonglong, []),
     "mft_prof_enable": (_i, [_i]),
+    "mft_set_pdl": (_i, [_i]),
     "mft_prof_categories": (_i, []),
     "mft_prof_name": (C.c_char_p, [_i]),
     "mft_prof_collect": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_int), _i]),

@@ -41,6 +41,45 @@ int last_code();
     } while (0)
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor on the stream is still draining; pdl_wait() blocks until that
+// predecessor has completed and its writes are visible, pdl_launch_dependents()
+// lets the NEXT launch of the stream start early in turn.  Both are no-ops in a
+// kernel launched the ordinary way.  Convention of this library: wait first,
+// release dependents second, touch upstream data third -- so completion of a
+// kernel always implies completion of everything before it on the stream.
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
+#endif
+
+// 0 = plain stream order, 1 = programmatic dependent launch inside the edge-MLP GEMM chains,
+// 2 = also for the row kernels around them (default; MFT_PDL in the environment, mft_set_pdl()).
+int pdl_level();
+bool prof_enabled();
+
+// Kernel launch with the programmatic-serialization attribute when `pdl` (and never while
+// per-launch event timing is on: the events would sit between the two kernels anyway).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && !prof_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+// ---------------------------------------------------------------------------
 // Pair-row geometry.  One graph has N nodes; the edge MLP runs on the Rg =
 // N(N+1)/2 unordered pairs (i<=j) of each of the B graphs, row-major in i:
 //   r_local = i*N - i*(i-1)/2 + (j-i),   r = b*Rg + r_local.

@@ -440,6 +440,18 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
 
     MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * kStatSlot, st));
     MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)n_out * 2 * F, st));
+    // Three chains besides the main one:
+    //   side 0:  AX = adj x (needs no gradient: starts at once) -> [after dY] small grads, d fc.weight[:, F:] = dY^T AX
+    //   side 1:  [after dY] d fc.weight[:, :F] = dY^T x ; then (after DU) d_adj = DU2 x^T
+    //   main  :  dZ -> dY -> DU = dY W  ->  dx += DU1 + adj^T DU2
+    Branches br(st);
+    cudaStream_t s0 = br.fork(0);
+    {
+        // AX = adj x   [B*N, F]
+        BView A{adj, (long)N * N, N, 1};
+        BView X{x, (long)N * ldx, ldx, 1};
+        { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA(launch_bgemm(A, X, L.AX, (long)N * F, F, B, N, F, N, 0.f, s0)); }
+    }
     dim3 blk(kGcCols, kGcRows);
     { ProfScope ps(PC_GCONV_BWD, st); gconv_dz_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(d_out, ldo, L.Y, rows, n_out, L.fsums, p->bn_g, p->bn_b,
                                                           has_bn, lrelu_on, L.dY, L.bsums);
@@ -450,21 +462,12 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
                                                                         L.bsums);
         MFT_CHECK_LAUNCH(); }
     }
-    { ProfScope ps(PC_GCONV_BWD, st); gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, st>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
+    br.sync_to_main(0);                              // dY and the reductions exist
+    cudaStream_t s1 = br.fork(1);
+    { ProfScope ps(PC_GCONV_BWD, s0); gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, s0>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
     MFT_CHECK_LAUNCH(); }
-
-    // Three independent chains from here (all read dY):
-    //   side 0:  AX = adj x  ->  d fc.weight[:, F:] = dY^T AX
-    //   side 1:  d fc.weight[:, :F] = dY^T x ; then (after DU) d_adj = DU2 x^T
-    //   main  :  DU = dY W  ->  dx += DU1  ->  dx += adj^T DU2
-    Branches br(st);
-    cudaStream_t s0 = br.fork(0), s1 = br.fork(1);
     PlainOp dy{L.dY, n_out};
     {
-        // AX = adj x   [B*N, F]
-        BView A{adj, (long)N * N, N, 1};
-        BView X{x, (long)N * ldx, ldx, 1};
-        { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA(launch_bgemm(A, X, L.AX, (long)N * F, F, B, N, F, N, 0.f, s0)); }
         PlainOp qax{L.AX, F};
         { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA((launch_gemm_tn(dy, qax, g->fc_w + F, 2 * F, n_out, F, rows, s0))); }
     }
@@ -489,12 +492,17 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     }
     // dx += DU1 + adj^T DU2
     {
-        int total = rows * F;
-        { ProfScope ps(PC_GCONV_BWD, st); add_cols_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(dx, ldx, L.DU, 2 * F, rows, F);
-        MFT_CHECK_LAUNCH(); }
         BView At{adj, (long)N * N, 1, N};                       // (m=j, k=i) -> adj[b, i, j]
         BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (k=i, n=f)
-        { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st)); }
+        if (bgemm_takes_addend(N)) {                            // DU1 rides along as the product's addend
+            ProfScope ps(PC_GCONV_BWD, st);
+            MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st, L.DU, (long)N * 2 * F, 2 * F));
+        } else {
+            int total = rows * F;
+            { ProfScope ps(PC_GCONV_BWD, st); add_cols_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(dx, ldx, L.DU, 2 * F, rows, F);
+            MFT_CHECK_LAUNCH(); }
+            { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st)); }
+        }
     }
     br.join(0);
     br.join(1);

@@ -6,6 +6,7 @@
 // is ever made.  The backward mirrors it with `dxcat`.
 #include "common.cuh"
 #include "wcompute.cuh"
+#include "prof.cuh"
 
 namespace mft {
 
@@ -20,7 +21,9 @@ struct GnnLayout {
     void* gc_saved[MFT_MAX_LAYERS];
     float* dxcat;          // workspace
     float* d_adj;
-    void* sub_ws;          // shared by every Wcompute / Gconv call (stream-ordered)
+    void* wc_ws;           // shared by every Wcompute call (stream-ordered)
+    void* gc_ws;           // shared by every Gconv call; separate from wc_ws because a Gconv runs beside the
+                           // preparation (forward) / gradient finalisation (backward) of a neighbouring Wcompute
     size_t saved_bytes, workspace_bytes;
 };
 
@@ -37,21 +40,22 @@ static GnnLayout gnn_layout(int B, int N, int F0, int nf, int n_way, void* saved
     size_t rows = (size_t)B * N;
     Carver sv(saved);
     G.xcat = sv.take<float>(rows * G.ldx);
-    size_t sub_ws = 0;
+    size_t wc_ws = 0, gc_ws = 0;
     for (int l = 0; l < G.L; ++l) {
         G.adj[l] = sv.take<float>((size_t)B * N * N);
         WcLayout w = wc_layout(B, N, G.F[l], nf, nullptr, nullptr);
         GcLayout c = gc_layout(B, N, G.F[l], G.nout[l], nullptr, nullptr);
         G.wc_saved[l] = sv.take<char>(w.saved_bytes);
         G.gc_saved[l] = sv.take<char>(c.saved_bytes);
-        sub_ws = sub_ws > w.workspace_bytes ? sub_ws : w.workspace_bytes;
-        sub_ws = sub_ws > c.workspace_bytes ? sub_ws : c.workspace_bytes;
+        wc_ws = wc_ws > w.workspace_bytes ? wc_ws : w.workspace_bytes;
+        gc_ws = gc_ws > c.workspace_bytes ? gc_ws : c.workspace_bytes;
     }
     G.saved_bytes = sv.used();
     Carver ws(workspace);
     G.dxcat = ws.take<float>(rows * G.ldx);
     G.d_adj = ws.take<float>((size_t)B * N * N);
-    G.sub_ws = ws.take<char>(sub_ws);
+    G.wc_ws = ws.take<char>(wc_ws);
+    G.gc_ws = ws.take<char>(gc_ws);
     G.workspace_bytes = ws.used();
     return G;
 }
@@ -70,17 +74,32 @@ int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_g
     const int rows = B * N;
     MFT_CHECK_CUDA(cudaMemcpy2DAsync(G.xcat, sizeof(float) * G.ldx, x, sizeof(float) * F0, sizeof(float) * F0,
                                      rows, cudaMemcpyDeviceToDevice, st));
+    // later layers see per-graph features: only layer 0 may share support pairs
+    auto prepare = [&](int l, cudaStream_t s) {
+        return wcompute_fwd_prepare(B, N, G.F[l], nf, &p->w[l], G.wc_saved[l], G.wc_ws, precision,
+                                    l == 0 ? shared_nodes : nullptr, s);
+    };
+    int rc = prepare(0, st);
+    if (rc != MFT_OK) return rc;
+    Branches br(st);
     for (int l = 0; l < G.L; ++l) {
-        int rc = wcompute_fwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.wc_saved[l], G.sub_ws,
-                              precision, l == 0 ? shared_nodes : nullptr, st);   // later layers see per-graph features
+        rc = wcompute_fwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.wc_saved[l], G.wc_ws,
+                          precision, l == 0 ? shared_nodes : nullptr, st, true);
         if (rc != MFT_OK) return rc;
         const bool last = (l == G.L - 1);
+        if (!last) {
+            // tables and weight images of the next Wcompute (parameters only) beside this layer's Gconv
+            rc = prepare(l + 1, br.fork(2));
+            if (rc != MFT_OK) return rc;
+        }
         float* dst = last ? out : G.xcat + G.F[l];
         int ldo = last ? n_way : G.ldx;
         rc = gconv_fwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, dst, ldo,
-                       G.gc_saved[l], G.sub_ws, st);
+                       G.gc_saved[l], G.gc_ws, st);
         if (rc != MFT_OK) return rc;
+        br.join(2);
     }
+    MFT_REQUIRE(br.ok(), "gnn_fwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
     return MFT_OK;
 }
 
@@ -91,6 +110,7 @@ int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const m
     GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace);
     const int rows = B * N;
     MFT_CHECK_CUDA(cudaMemsetAsync(G.dxcat, 0, sizeof(float) * (size_t)rows * G.ldx, st));
+    Branches tail(st);   // slot 2: parameter-gradient finalisation of layer l beside the Gconv backward of layer l-1
     for (int l = G.L - 1; l >= 0; --l) {
         const bool last = (l == G.L - 1);
         // upstream of this Gconv: d_out for the last one, else the columns it produced in xcat
@@ -98,14 +118,17 @@ int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const m
         const float* up = last ? d_out : G.dxcat + G.F[l];
         int ldu = last ? n_way : G.ldx;
         int rc = gconv_bwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, up, ldu,
-                           G.dxcat, G.d_adj, &g->l[l], G.gc_saved[l], G.sub_ws, st);
+                           G.dxcat, G.d_adj, &g->l[l], G.gc_saved[l], G.gc_ws, st);
         if (rc != MFT_OK) return rc;
+        tail.join(2);      // the Wcompute workspace (partial dW copies, reductions) is about to be reused
         rc = wcompute_bwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.d_adj, G.dxcat, &g->w[l],
-                          G.wc_saved[l], G.sub_ws, precision, l == 0 ? shared_nodes : nullptr, st);
+                          G.wc_saved[l], G.wc_ws, precision, l == 0 ? shared_nodes : nullptr, st, &tail, 2);
         if (rc != MFT_OK) return rc;
     }
     MFT_CHECK_CUDA(cudaMemcpy2DAsync(dx, sizeof(float) * F0, G.dxcat, sizeof(float) * G.ldx, sizeof(float) * F0,
                                      rows, cudaMemcpyDeviceToDevice, st));
+    tail.join(2);
+    MFT_REQUIRE(tail.ok(), "gnn_bwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
     return MFT_OK;
 }
 

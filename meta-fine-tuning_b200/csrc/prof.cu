@@ -1,4 +1,5 @@
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -29,6 +30,21 @@ struct Slot { cudaEvent_t a, b; int cat; };
 static std::vector<Slot> g_slots;
 static size_t g_used = 0;
 constexpr size_t kMaxSlots = 16384;
+
+bool prof_enabled() { return g_enabled.load(std::memory_order_relaxed); }
+
+static std::atomic<int> g_pdl{-1};
+int pdl_level() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("MFT_PDL");
+        v = (e && *e) ? atoi(e) : 2;
+        if (v < 0) v = 0;
+        g_pdl.store(v);
+    }
+    return v;
+}
+void set_pdl_level(int v) { g_pdl.store(v < 0 ? 0 : v); }
 
 ProfScope::ProfScope(int cat, cudaStream_t stream) : slot(-1), st(stream) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -64,6 +80,12 @@ int mft_prof_enable(int on) {
     g_enabled.store(on != 0);
     g_used = 0;
     return MFT_OK;
+}
+
+int mft_set_pdl(int level) {
+    int before = pdl_level();
+    set_pdl_level(level);
+    return before;
 }
 
 int mft_prof_categories(void) { return PC_COUNT; }

@@ -24,6 +24,7 @@ enum ProfCat {
 };
 
 const char* prof_name(int cat);
+void set_pdl_level(int v);
 
 struct ProfScope {
     int slot;
@@ -44,7 +45,7 @@ struct ProfScope {
 // ---------------------------------------------------------------------------------------------
 namespace mft {
 
-constexpr int kSideStreams = 2;
+constexpr int kSideStreams = 3;   // 0, 1: inside one Wcompute / Gconv call; 2: gnn_fwd / gnn_bwd across calls
 
 class Branches {
 public:

@@ -167,7 +167,8 @@ __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, boo
 }
 
 __global__ void __launch_bounds__(256)
-bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int M, int N, int K, float beta) {
+bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int M, int N, int K, float beta,
+                     const float* __restrict__ addend, long sadd, int ldadd) {
     extern __shared__ float os_smem[];
     const int lda = K | 1;                       // odd row stride: conflict-free column walks
     float* As = os_smem;                         // [32][lda]  (m, k)
@@ -242,15 +243,21 @@ bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc
             const int n = n0 + 2 * tx + j;
             if (n < N) {
                 float* c = C + (size_t)b * scb + (size_t)m * ldc + n;
-                *c = (beta == 0.f) ? acc[i][j] : fmaf(beta, *c, acc[i][j]);
+                float v = acc[i][j];
+                if (addend) v += addend[(size_t)b * sadd + (size_t)m * ldadd + n];
+                *c = (beta == 0.f) ? v : fmaf(beta, *c, v);
             }
         }
     }
 }
 
+bool bgemm_takes_addend(int K) { return K >= 1 && K <= OS_MAXK; }
+
+// C[b] = beta * C[b] + A[b] B[b] (+ addend[b], one-shot path only: see bgemm_takes_addend)
 cudaError_t launch_bgemm(BView A, BView Bm, float* C, long scb, int ldc, int batch, int M, int N, int K,
-                         float beta, cudaStream_t st) {
+                         float beta, cudaStream_t st, const float* addend, long sadd, int ldadd) {
     if (batch <= 0 || M <= 0 || N <= 0) return cudaSuccess;
+    if (addend && !bgemm_takes_addend(K)) return cudaErrorInvalidValue;
     if (K >= 1 && K <= OS_MAXK) {
         static bool attr_set = false;
         const size_t max_smem = (size_t)(2 * OS_T * (OS_MAXK | 1)) * sizeof(float);
@@ -262,7 +269,7 @@ cudaError_t launch_bgemm(BView A, BView Bm, float* C, long scb, int ldc, int bat
         }
         const size_t smem = (size_t)(2 * OS_T * (K | 1)) * sizeof(float);
         dim3 grid(cdiv(N, OS_T), cdiv(M, OS_T), batch);
-        bgemm_oneshot_kernel<<<grid, 256, smem, st>>>(A, Bm, C, scb, ldc, M, N, K, beta);
+        bgemm_oneshot_kernel<<<grid, 256, smem, st>>>(A, Bm, C, scb, ldc, M, N, K, beta, addend, sadd, ldadd);
         return cudaGetLastError();
     }
     if (M >= 48 && N >= 40) {

@@ -296,7 +296,10 @@ struct BView {
 __global__ void bgemm_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int M, int N, int K,
                              float beta);
 
+// C[b] = beta * C[b] + A[b] B[b] + addend[b]; the addend (batch stride sadd, row stride ldadd) is only
+// available where bgemm_takes_addend(K) (the one-shot kernel).
+bool bgemm_takes_addend(int K);
 cudaError_t launch_bgemm(BView A, BView Bm, float* C, long scb, int ldc, int batch, int M, int N, int K,
-                         float beta, cudaStream_t st);
+                         float beta, cudaStream_t st, const float* addend = nullptr, long sadd = 0, int ldadd = 0);
 
 }  // namespace mft

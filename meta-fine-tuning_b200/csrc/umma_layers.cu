@@ -597,6 +597,23 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
         fence_mbar_init();
     }
     if (warp == UM_MMA_WARP) tmem_alloc(tmem_slot, UM_TMEM_COLS);
+    __syncthreads();                                   // barrier inits visible to the MMA thread
+    if (warp == UM_MMA_WARP && lane == 0) {
+        // The weight image was complete before the PREVIOUS launch of this stream started (host
+        // side: pdl only between consecutive GEMM launches of one call), so under programmatic
+        // dependent launch it may land while that launch is still draining.
+        mbar_arrive_expect_tx(wbar, w_bytes);
+        const uint32_t blk = (uint32_t)s.N_TILE * 128;
+        for (int kc = 0; kc < s.KC; ++kc)
+            bulk_g2s(reinterpret_cast<uint8_t*>(Wsm) + (size_t)kc * blk,
+                     reinterpret_cast<const uint8_t*>(wimg) + (size_t)kc * blk, blk, wbar);
+    }
+    // Everything above overlaps the tail of the preceding kernel when this one was launched with
+    // programmatic stream serialization; everything below reads what that kernel wrote.  (Both
+    // instructions are no-ops for an ordinary launch.)  Dependents are released only AFTER the
+    // wait, so a kernel's prologue never runs beside anything older than its direct predecessor.
+    pdl_wait();
+    pdl_launch_dependents();
     aop.init(aux_a, tid, UM_THREADS);
     epi.init(aux_e, tid, UM_THREADS);
     tc_fence_before_sync();
@@ -787,12 +804,8 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
     } else if (warp == UM_MMA_WARP) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(wbar, w_bytes);
             const uint32_t blk = (uint32_t)s.N_TILE * 128;
-            for (int kc = 0; kc < s.KC; ++kc)
-                bulk_g2s(reinterpret_cast<uint8_t*>(Wsm) + (size_t)kc * blk,
-                         reinterpret_cast<const uint8_t*>(wimg) + (size_t)kc * blk, blk, wbar);
-            mbar_wait(wbar, 0);
+            mbar_wait(wbar, 0);                                            // issued in the prologue
             MFT_MARK(1);                                                   // weights resident
             const uint32_t idesc = make_idesc_tf32(UM_ROWS, s.N_TILE);
             const int ksteps = (s.K + 7) / 8;
@@ -1103,6 +1116,8 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
         fence_mbar_init();
     }
     if (warp == 8) tmem_alloc(tmem_slot, UM_TMEM_COLS);
+    pdl_wait();                 // see umma_rows_kernel: no-ops unless launched with programmatic serialization
+    pdl_launch_dependents();
     pop.init(aux_p, tid, WG_THREADS);
     qop.init(aux_q, tid, WG_THREADS);
     tc_fence_before_sync();
@@ -1468,7 +1483,9 @@ size_t umma_wimg_floats(int N, int K) {
 
 template <class AOp, class Epi>
 static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ldw, int transpose, int R, int N,
-                          int K, float* wimg, cudaStream_t st, int cat, bool prebuilt = false) {
+                          int K, float* wimg, cudaStream_t st, int cat, bool prebuilt = false, bool pdl = false) {
+    // pdl: the launch directly before this one on `st` is a kernel of this library that follows the
+    // wait-then-release convention (common.cuh) AND started after the weight images were complete.
     int n0s[4], nts[4];
     int passes = plan_passes(N, K, n0s, nts);
     if (passes == 0) {
@@ -1528,15 +1545,17 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
         MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_rows_kernel<AOp, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
         ProfScope ps(cat, st);
-        umma_rows_kernel<AOp, Epi><<<grid, UM_THREADS, smem, st>>>(aop, epi, img, s);
-        MFT_CHECK_LAUNCH();
+        // a second pass follows the first pass of the same layer: same images, same convention
+        const bool use_pdl = prebuilt && pdl_level() >= 1 && (pdl || p > 0);
+        MFT_CHECK_CUDA(launch_kernel(umma_rows_kernel<AOp, Epi>, dim3(grid), dim3(UM_THREADS), smem, st, use_pdl,
+                                     aop, epi, (const float*)img, s));
     }
     return MFT_OK;
 }
 
 template <class POp, class QOp, bool kSpecialize = true>
 static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R, int Cout, int Cin,
-                      cudaStream_t st, int cat, int* copies_out = nullptr) {
+                      cudaStream_t st, int cat, int* copies_out = nullptr, bool pdl = false) {
     WgradShape s{};
     s.R = R; s.Cout = Cout; s.Cin = Cin;
     s.copy_stride = Cout * ldw;
@@ -1589,8 +1608,8 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
         MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<POp, QOp, PBC, QBC>,                                    \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
         ProfScope ps(cat, st);                                                                                       \
-        umma_wgrad_kernel<POp, QOp, PBC, QBC><<<grid_x, WG_THREADS, smem, st>>>(pop, qop, dW, ldw, s);                \
-        MFT_CHECK_LAUNCH();                                                                                          \
+        MFT_CHECK_CUDA(launch_kernel(umma_wgrad_kernel<POp, QOp, PBC, QBC>, dim3(grid_x), dim3(WG_THREADS), smem, st, \
+                                     pdl, pop, qop, dW, ldw, s));                                                    \
         return MFT_OK;                                                                                               \
     } while (0)
     // the block counts of the reference's layer widths (nf = 96: 192/192/96/96, F = 133/181/229) are compiled in
@@ -1671,15 +1690,20 @@ int wcompute_bwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, i
     return build_images(p, L.wimg, F, nf, true, st);
 }
 
+int wcompute_fwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, cudaStream_t st) {
+    if (!umma_shape_supported(F, nf)) {
+        set_error(MFT_ERR_UNSUPPORTED, "tf32 path: unsupported shape F=%d nf=%d", F, nf);
+        return MFT_ERR_UNSUPPORTED;
+    }
+    return build_images(p, L.wimg, F, nf, false, st);
+}
+
+// (the four forward weight images exist: wcompute_fwd_prepare_tf32)
 int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_wcompute_params* p,
                              const WcLayout& L, const PairGeom& g, cudaStream_t st) {
     if (!umma_shape_supported(F, nf)) {
         set_error(MFT_ERR_UNSUPPORTED, "tf32 path: unsupported shape F=%d nf=%d", F, nf);
         return MFT_ERR_UNSUPPORTED;
-    }
-    {
-        int rc0 = build_images(p, L.wimg, F, nf, false, st);
-        if (rc0 != MFT_OK) return rc0;
     }
     for (int k = 0; k < 4; ++k) {
         double* sums = L.fsums + (size_t)k * kStatSlot;
@@ -1688,7 +1712,7 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
         int rc;
         if (k == 0) {
             AbsDiffU a{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
-            rc = umma_rows_gemm(a, epi, p->conv_w[0], F, 0, g.R, L.C[1], F, img, st, PC_FWD_L1, true);
+            rc = umma_rows_gemm(a, epi, p->conv_w[0], F, 0, g.R, L.C[1], F, img, st, PC_FWD_L1, true, false);
         } else {
             const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
             BnActT a{};
@@ -1697,7 +1721,7 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
             if (rc != MFT_OK) return rc;
             a.C = L.C[k]; a.sums = ps; a.gamma = p->bn_g[k - 1]; a.beta = p->bn_b[k - 1]; a.inv_count = g.inv_pairs;
             rc = umma_rows_gemm(a, epi, p->conv_w[k], L.C[k], 0, g.R, L.C[k + 1], L.C[k], img, st,
-                                PC_FWD_L1 + k, true);
+                                PC_FWD_L1 + k, true, true);      // follows the previous layer's launch
         }
         if (rc != MFT_OK) return rc;
     }
@@ -1710,6 +1734,7 @@ int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_w
 __global__ void __launch_bounds__(256)
 dx_gather_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
                  int ldx, int F, PairGeom g) {
+    pdl_enter();
     const int N = g.N;
     const int node = blockIdx.x;            // b*N + n
     const int b = node / N, n = node - b * N;
@@ -1736,6 +1761,7 @@ __global__ void __launch_bounds__(256)
 dx_gather_vec_kernel(const __nv_bfloat16* __restrict__ dD, int ldd, const float* __restrict__ x, float* __restrict__ dx,
                      int ldx, int F, PairGeom g) {
     __shared__ float4 part[256];
+    pdl_enter();
     const int N = g.N;
     const int node = blockIdx.x;
     const int b = node / N, n = node - b * N;
@@ -1799,25 +1825,25 @@ int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, in
         const int ldd = (F + 3) & ~3;
         EpiStoreBf16U e{reinterpret_cast<__nv_bfloat16*>(L.dD), ldd};
         int rc = umma_rows_gemm(a, e, p->conv_w[0], Cin, 1, g.R, Cin, Cout, L.wimg + img_offset(F, nf, 0), st,
-                                PC_DGRAD_L1, true);
+                                PC_DGRAD_L1, true, true);        // follows this layer's wgrad launch
         if (rc != MFT_OK) return rc;
         ProfScope ps(PC_DGRAD_L1, st);
+        const bool gpdl = pdl_level() >= 2;
         // x rows 16-byte aligned and padded to a multiple of 4 floats (always true for the xcat of gnn_fwd):
         // beyond-F lanes of the last float4 read padding that is masked on the way out
         if (absdiff_vec_ok(x, ldx, F) && F <= 256)
-            dx_gather_vec_kernel<<<g.B * g.N, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(L.dD), ldd, x, dx,
-                                                            ldx, F, g);
+            MFT_CHECK_CUDA(launch_kernel(dx_gather_vec_kernel, dim3(g.B * g.N), dim3(256), 0, st, gpdl,
+                                         reinterpret_cast<const __nv_bfloat16*>(L.dD), ldd, x, dx, ldx, F, g));
         else
-            dx_gather_kernel<<<g.B * g.N, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(L.dD), ldd, x, dx,
-                                                        ldx, F, g);
-        MFT_CHECK_LAUNCH();
+            MFT_CHECK_CUDA(launch_kernel(dx_gather_kernel, dim3(g.B * g.N), dim3(256), 0, st, gpdl,
+                                         reinterpret_cast<const __nv_bfloat16*>(L.dD), ldd, x, dx, ldx, F, g));
         return MFT_OK;
     }
     const double* ps = L.fsums + (size_t)(k - 1) * kStatSlot;
     double* pbs = L.bsums + (size_t)(k - 1) * kStatSlot;
     EpiDyU e{reinterpret_cast<const __half*>(L.H[k - 1]), dy_next, Cin, ps, p->bn_g[k - 1], p->bn_b[k - 1], g.inv_pairs, pbs};
     return umma_rows_gemm(a, e, p->conv_w[k], Cin, 1, g.R, Cin, Cout, L.wimg + img_offset(F, nf, k), st,
-                          PC_DGRAD_L1 + k, true);
+                          PC_DGRAD_L1 + k, true, true);          // follows this layer's wgrad launch
 }
 
 // wgrad of conv layer k: d conv2d_{k+1}.weight [Cout, Cin] += dH_k^T a_k (a_0 = |x_i - x_j|).
@@ -1825,6 +1851,8 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
                               const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                               const PairGeom& g, int* copies, cudaStream_t st) {
     const int Cout = L.C[k + 1], Cin = L.C[k];
+    // layer 3 follows the dy8 row kernel, the others the dgrad launch of the layer above
+    const bool pdl = pdl_level() >= (k == 3 ? 2 : 1);
     DhT P{};
     int rc = make_tmap_2d(&P.tmap_dy, dh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.R, Cout, Cout, Cout, WG_ROWS,
                           CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -1836,7 +1864,7 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
     P.bsums = L.bsums + (size_t)k * kStatSlot; P.inv_count = g.inv_pairs; P.g = g;
     if (k == 0) {
         AbsDiffU Q{x, ldx, F, g, absdiff_vec_ok(x, ldx, F)};
-        return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[0], (Cin + 3) & ~3, g.R, Cout, Cin, st, PC_WGRAD_L1, copies);
+        return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[0], (Cin + 3) & ~3, g.R, Cout, Cin, st, PC_WGRAD_L1, copies, pdl);
     }
     BnActQT Q{};
     rc = make_tmap_2d(&Q.tmap_h, L.H[k - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g.R, Cin, Cin, Cin, WG_ROWS,
@@ -1844,7 +1872,7 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
     if (rc != MFT_OK) return rc;
     Q.C = Cin; Q.sums = L.fsums + (size_t)(k - 1) * kStatSlot; Q.gamma = p->bn_g[k - 1]; Q.beta = p->bn_b[k - 1];
     Q.inv_count = g.inv_pairs;
-    return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[k], (Cin + 3) & ~3, g.R, Cout, Cin, st, PC_WGRAD_L1 + k, copies);
+    return umma_wgrad(P, Q, L.wgpart + L.wgpart_off[k], (Cin + 3) & ~3, g.R, Cout, Cin, st, PC_WGRAD_L1 + k, copies, pdl);
 }
 
 // Debug / test entry: C[M, N] = A[M, K] * op(W)^T through the tcgen05 rows kernel with plain

@@ -515,8 +515,9 @@ score8_kernel(const void* __restrict__ H4, int C, const double* sums, const floa
               const float* last_w, const float* last_b, PairGeom g, float* __restrict__ S) {
     __shared__ float aux[4 * kMaxC];
     __shared__ float wls[kMaxC];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) wls[c] = last_w[c];   // a parameter: not upstream data
+    pdl_enter();
     bn_smem_fill(bn_smem_at(aux), sums, gamma, beta, C, g.inv_pairs);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) wls[c] = last_w[c];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sl = lane & 7, rg = lane >> 3;
@@ -570,8 +571,9 @@ dy8_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, con
     __shared__ float aux[4 * kMaxC];
     __shared__ float wls[kMaxC];
     __shared__ float red[3][kRowWarps][32 * NGL];
-    bn_smem_fill(bn_smem_at(aux), fsums, gamma, beta, C, g.inv_pairs);
     for (int c = threadIdx.x; c < C; c += blockDim.x) wls[c] = last_w[c];
+    pdl_enter();
+    bn_smem_fill(bn_smem_at(aux), fsums, gamma, beta, C, g.inv_pairs);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sl = lane & 7, rg = lane >> 3;
@@ -672,6 +674,7 @@ dy8_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, con
 // adj[b,i,:] = softmax_j(S[b,i,j] - 1e8 [i==j])   (gnn.py:105-115), one warp per row
 __global__ void __launch_bounds__(kRowWarps * 32)
 softmax_rows_kernel(const float* __restrict__ S, float* __restrict__ adj, int rows, int N) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int row = blockIdx.x * kRowWarps + warp;
     if (row >= rows) return;
@@ -701,6 +704,7 @@ softmax_rows_kernel(const float* __restrict__ S, float* __restrict__ adj, int ro
 __global__ void __launch_bounds__(kRowWarps * 32)
 softmax_bwd_kernel(const float* __restrict__ adj, const float* __restrict__ d_adj, float* __restrict__ dS,
                    int rows, int N) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int row = blockIdx.x * kRowWarps + warp;
     if (row >= rows) return;
@@ -841,6 +845,7 @@ struct FinalizeArgs {
 };
 
 __global__ void finalize_grads_kernel(FinalizeArgs a) {   // grid = 5: one CTA per BN layer + one for conv2d_last
+    pdl_enter();
     const int t = threadIdx.x, k = blockIdx.x;
     if (k < 4) {
         if (t < a.C[k]) {
@@ -861,6 +866,7 @@ constexpr int kRedThreads = 256;
 __global__ void __launch_bounds__(kRedThreads)
 wgrad_reduce_kernel(FinalizeArgs a) {
     __shared__ float4 part[kRedThreads];
+    pdl_enter();
     int k = 0, co = blockIdx.x;
     while (k < 4 && co >= a.wsize[k] / a.cin[k]) { co -= a.wsize[k] / a.cin[k]; ++k; }
     if (k == 4 || a.wgpart[k] == nullptr) return;
@@ -938,8 +944,28 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     return L;
 }
 
+int wcompute_fwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params* p, void* saved, void* workspace,
+                         int precision, const unsigned char* shared_nodes, cudaStream_t st) {
+    MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_fwd: bad shape B=%d N=%d F=%d nf=%d", B, N, F, nf);
+    MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_fwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
+    MFT_REQUIRE(N < 32768, "wcompute_fwd: N=%d too large", N);
+    WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
+    NodeMask mask;
+    const int n_shared = mask_from_host(shared_nodes, B, N, mask);
+    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared);
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 4 * kStatSlot, st));
+    {
+        ProfScope ps(PC_PREP, st);
+        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, N, g.Rg, g.Rs, n_shared, mask);
+        MFT_CHECK_LAUNCH();
+    }
+    if (precision == MFT_PREC_TF32) return wcompute_fwd_prepare_tf32(p, L, F, nf, st);
+    return MFT_OK;
+}
+
 int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p, float* adj,
-                 void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st) {
+                 void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st,
+                 bool prepared) {
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_fwd: bad shape B=%d N=%d F=%d nf=%d", B, N, F, nf);
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_fwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
     MFT_REQUIRE(N < 32768, "wcompute_fwd: N=%d too large", N);
@@ -949,11 +975,9 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     const int n_shared = mask_from_host(shared_nodes, B, N, mask);
     PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared);
 
-    MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 4 * kStatSlot, st));
-    {
-        ProfScope ps(PC_PREP, st);
-        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, N, g.Rg, g.Rs, n_shared, mask);
-        MFT_CHECK_LAUNCH();
+    if (!prepared) {
+        int rc = wcompute_fwd_prepare(B, N, F, nf, p, saved, workspace, precision, shared_nodes, st);
+        if (rc != MFT_OK) return rc;
     }
 
     if (precision == MFT_PREC_TF32) {
@@ -980,8 +1004,9 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
 #define MFT_SCORE(HALF, SHARED)                                                                                   \
     do {                                                                                                          \
         if (nf % 4 == 0 && nf <= 96)                                                                              \
-            score8_kernel<HALF, SHARED, 3><<<row_grid8(g.R), kRowWarps * 32, 0, st>>>(                             \
-                L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, g, L.S);        \
+            MFT_CHECK_CUDA(launch_kernel(score8_kernel<HALF, SHARED, 3>, dim3(row_grid8(g.R)),                    \
+                dim3(kRowWarps * 32), 0, st, row_pdl, (const void*)L.H[3], nf,                                    \
+                (const double*)(L.fsums + 3 * kStatSlot), p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, g, L.S));  \
         else if (nf % 4 == 0 && nf <= 128)                                                                        \
             score_vec_kernel<HALF, SHARED, 1><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(                           \
                 L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, g, L.S);        \
@@ -989,6 +1014,8 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             score_kernel<HALF, SHARED><<<row_grid(g.R), kRowWarps * 32, 0, st>>>(                                  \
                 L.H[3], nf, L.fsums + 3 * kStatSlot, p->bn_g[3], p->bn_b[3], p->last_w, p->last_b, g, L.S);        \
     } while (0)
+        // follows the layer-4 GEMM launch on the tensor-core path (wait-then-release convention)
+        const bool row_pdl = precision == MFT_PREC_TF32 && pdl_level() >= 2;
         if (precision == MFT_PREC_TF32) {
             if (g.Rs > 0) MFT_SCORE(true, true); else MFT_SCORE(true, false);
         } else {
@@ -999,15 +1026,18 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     }
     {
         ProfScope ps(PC_SOFTMAX, st);
-        softmax_rows_kernel<<<cdiv(B * N, kRowWarps), kRowWarps * 32, 0, st>>>(L.S, adj, B * N, N);
-        MFT_CHECK_LAUNCH();
+        // only score8_kernel is known to release its dependents after its own wait
+        const bool pdl = precision == MFT_PREC_TF32 && pdl_level() >= 2 && nf % 4 == 0 && nf <= 96;
+        MFT_CHECK_CUDA(launch_kernel(softmax_rows_kernel, dim3(cdiv(B * N, kRowWarps)), dim3(kRowWarps * 32), 0, st,
+                                     pdl, (const float*)L.S, adj, B * N, N));
     }
     return MFT_OK;
 }
 
 int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
                  const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* gr, void* saved,
-                 void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st) {
+                 void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st,
+                 Branches* tail, int tail_slot) {
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_bwd: bad shape");
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_bwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
@@ -1136,12 +1166,16 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     fa.last_b = gr->last_b;
     fa.nf = nf;
     {
-        ProfScope ps(PC_FINALIZE, st);
-        finalize_grads_kernel<<<5, kMaxC, 0, st>>>(fa);
-        MFT_CHECK_LAUNCH();
+        // These only finish parameter gradients: on the caller's tail branch (if any) they run beside
+        // whatever the main stream does next.  On the main stream of the tensor-core path they follow the
+        // dx gather launched by wcompute_bwd_layer_tf32(0, ...) (programmatic launch allowed).
+        cudaStream_t fs = tail ? tail->fork(tail_slot) : st;
+        const bool pdl = fs == st && precision == MFT_PREC_TF32 && pdl_level() >= 2;
+        ProfScope ps(PC_FINALIZE, fs);
+        MFT_CHECK_CUDA(launch_kernel(finalize_grads_kernel, dim3(5), dim3(kMaxC), 0, fs, pdl, fa));
         if (precision == MFT_PREC_TF32) {
-            wgrad_reduce_kernel<<<L.C[1] + L.C[2] + L.C[3] + L.C[4], kRedThreads, 0, st>>>(fa);
-            MFT_CHECK_LAUNCH();
+            MFT_CHECK_CUDA(launch_kernel(wgrad_reduce_kernel, dim3(L.C[1] + L.C[2] + L.C[3] + L.C[4]),
+                                         dim3(kRedThreads), 0, fs, pdl, fa));
         }
     }
     return MFT_OK;

@@ -38,16 +38,27 @@ int umma_debug_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW
 
 WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace);
 
+// wcompute_fwd_prepare: everything of the forward that depends on the parameters and the shape only
+// (statistics slots zeroed, pair tables, the four tcgen05 weight images) -- gnn_fwd issues it for layer
+// l+1 on a side branch while the Gconv of layer l runs; wcompute_fwd(prepared = true) then skips it.
+int wcompute_fwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params* p, void* saved, void* workspace,
+                         int precision, const unsigned char* shared_nodes, cudaStream_t st);
 int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p, float* adj,
-                 void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st);
+                 void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st,
+                 bool prepared = false);
+// tail_st: stream for the kernels that only finish parameter gradients (finalize_grads, wgrad_reduce);
+// when it differs from st the caller has ordered it after st's work so far and joins it before the
+// workspace is reused (gnn_bwd runs them under the next layer's Gconv backward).
 int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
                  const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* gr, void* saved,
-                 void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st);
+                 void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st,
+                 class Branches* tail = nullptr, int tail_slot = 0);
 
 // tcgen05 (MFT_PREC_TF32) replacements for the four forward layer GEMMs and for the
 // dgrad + wgrad pair of one backward layer; same buffers in and out as the fp32 path.
 int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_wcompute_params* p,
                              const WcLayout& L, const PairGeom& g, cudaStream_t st);
+int wcompute_fwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, cudaStream_t st);
 int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, int ldx, float* dx, int F, int nf,
                             const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                             const PairGeom& g, cudaStream_t st);

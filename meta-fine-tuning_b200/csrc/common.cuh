@@ -93,6 +93,10 @@ struct PairGeom {
     double inv_pairs;
     const int* tri;   // [Rg] packed (j << 16) | i: the Rs shared pairs first, then the Rq per-graph ones
     const int* inv;   // [N*N] (i <= j): index into the per-graph part, or -1 - index into the shared part
+    // Per-ROW tables (tri_table_kernel) for the tcgen05 kernels, whose roles must not stall on a
+    // division plus a dependent table load per row: a pure load each, consumed a tile later.
+    const float* roww;  // [R + 1] multiplicity w of row r (see PairRow); roww[R] = 0 stands for "past the end"
+    const int2* rowij;  // [R + 1] node-matrix rows (b*N + i, b*N + j) of row r (b = 0 for a shared row)
 };
 
 // Shared nodes (include/mft_gnn.h, `shared_nodes`): node n is "shared" when x[b, n, :] is the same
@@ -117,7 +121,8 @@ inline int mask_from_host(const unsigned char* shared_nodes, int B, int N, NodeM
     return S;
 }
 
-inline PairGeom make_geom(int B, int N, const int* tri, const int* inv = nullptr, int n_shared = 0) {
+inline PairGeom make_geom(int B, int N, const int* tri, const int* inv = nullptr, int n_shared = 0,
+                          const float* roww = nullptr, const int2* rowij = nullptr) {
     PairGeom g;
     g.B = B;
     g.N = N;
@@ -128,6 +133,8 @@ inline PairGeom make_geom(int B, int N, const int* tri, const int* inv = nullptr
     g.inv_pairs = 1.0 / ((double)B * (double)N * (double)N);
     g.tri = tri;
     g.inv = inv;
+    g.roww = roww;
+    g.rowij = rowij;
     return g;
 }
 

@@ -132,8 +132,8 @@ struct AbsDiffU {
     struct Raw { float4 a, b; };
     __device__ __forceinline__ void init(float*, int, int) const {}
     __device__ __forceinline__ Row row(int r) const {
-        PairRow p = decode_row(r, g);
-        return Row{x + (size_t)(p.b * g.N + p.i) * ldx, x + (size_t)(p.b * g.N + p.j) * ldx};
+        const int2 n = __ldg(g.rowij + r);             // one load, no division (tri_table_kernel)
+        return Row{x + (size_t)n.x * ldx, x + (size_t)n.y * ldx};
     }
     __device__ __forceinline__ void fetch(const Row& rw, int k, Raw& o) const {
         if (vec_ok) {
@@ -280,7 +280,7 @@ struct DhInPlaceT {
     __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
         return make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __device__ __forceinline__ float row_weight(int r) const { return decode_row(r, g).w; }
+    __device__ __forceinline__ float row_weight(int r) const { return __ldg(g.roww + r); }   // r <= R
     struct Consts { float4 P, Q, S; bool on; };
     __device__ __forceinline__ Consts consts(int k, const float* aux) const {
         Consts c;
@@ -331,7 +331,7 @@ struct DhT {                                     // P = dH_k from (dy_k, H_k)
             aux[2 * kMaxC + c] = S;
         }
     }
-    __device__ __forceinline__ Row row(int r) const { return Row{decode_row(r, g).w}; }
+    __device__ __forceinline__ Row row(int r) const { return Row{__ldg(g.roww + r)}; }       // r <= R
     __device__ __forceinline__ void fetch(const Row&, int, Raw&) const {}
     __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
         return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -460,7 +460,7 @@ struct EpiFwdStatsU {
     double* sums;
     PairGeom g;
     __device__ __forceinline__ void init(float*, int, int) const {}
-    __device__ __forceinline__ float row_weight(int r) const { return decode_row(r, g).w; }
+    __device__ __forceinline__ float row_weight(int r) const { return __ldg(g.roww + r); }   // r <= R
     struct Consts {};
     __device__ __forceinline__ int row_stride() const { return C; }
     __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
@@ -645,8 +645,9 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
             auto load_weights = [&](int tile, float (&dst)[RQ]) {
 #pragma unroll
                 for (int q = 0; q < RQ; ++q) {
+                    // pure loads (entry R of the row table is 0): nothing here may wait on a result
                     const int r = phys(min(tile, ntiles - 1)) * UM_ROWS + q * RSTEP + rsub;
-                    dst[q] = (tile < ntiles && r < s.R) ? aop.row_weight(r) : 0.f;
+                    dst[q] = aop.row_weight(tile < ntiles ? min(r, s.R) : s.R);
                 }
             };
             load_weights(blockIdx.x, wq_next);
@@ -896,7 +897,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int r = phys(min(tile, ntiles - 1)) * UM_ROWS + ew * 32 + q * 4 + rsub;
-                dst[q] = (Epi::kRowWeight && tile < ntiles && r < s.R) ? epi.row_weight(r) : 0.f;
+                dst[q] = Epi::kRowWeight ? epi.row_weight(tile < ntiles ? min(r, s.R) : s.R) : 0.f;   // pure loads
             }
         };
         load_weights(blockIdx.x, wq_next);
@@ -1141,14 +1142,14 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             typename QOp::Row qr;
             typename QOp::Raw qraw[QOp::kTma ? 1 : kQBmax];
             // the row multiplicity is a dependent global load (pair table): fetched one chunk ahead
-            float w_next = (c_begin < c_end && c_begin * WG_ROWS + rl < s.R) ? pop.row(c_begin * WG_ROWS + rl).w : 0.f;
+            float w_next = pop.row(c_begin < c_end ? min(c_begin * WG_ROWS + rl, s.R) : s.R).w;   // pure load
             for (int c = c_begin; c < c_end; ++c) {
                 const int r = c * WG_ROWS + rl;
                 const bool ok = r < s.R;
                 const float w = w_next;
                 {
                     const int rn = r + WG_ROWS;
-                    w_next = (c + 1 < c_end && rn < s.R) ? pop.row(rn).w : 0.f;
+                    w_next = pop.row(c + 1 < c_end ? min(rn, s.R) : s.R).w;
                 }
                 mbar_wait(&rawfull[rs], rph);
                 const uint8_t* rb = rawring + (size_t)rs * s.raw_bytes;

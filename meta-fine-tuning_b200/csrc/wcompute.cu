@@ -215,26 +215,45 @@ __device__ __forceinline__ int shared_below(const NodeMask& m, int n) {
     return c + __popc(m.w[n >> 5] & ((1u << (n & 31)) - 1u));
 }
 
-__global__ void tri_table_kernel(int* tri, int* inv, int N, int Rg, int Rs, int n_shared, NodeMask mask) {
+__global__ void tri_table_kernel(int* tri, int* inv, float* roww, int2* rowij, int B, int N, int Rg, int Rs,
+                                 int n_shared, NodeMask mask) {
     int rl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Rq = Rg - Rs, R = Rs + B * Rq;
+    if (rl == 0) {                       // the "past the end" entry
+        roww[R] = 0.f;
+        rowij[R] = make_int2(0, 0);
+    }
     if (rl >= Rg) return;
     int i, j;
     decode_local(rl, N, i, j);
     const int packed = (j << 16) | i;
+    int q;                               // index inside the per-graph part, or -1 for a shared pair
     if (Rs == 0) {
         tri[rl] = packed;
         inv[i * N + j] = rl;
-        return;
-    }
-    const bool mi = (mask.w[i >> 5] >> (i & 31)) & 1u, mj = (mask.w[j >> 5] >> (j & 31)) & 1u;
-    const int si = shared_below(mask, i), sj = shared_below(mask, j);
-    const int before = si * n_shared - (si * (si - 1)) / 2 + (mi ? (sj - si) : 0);   // shared pairs ahead of (i,j)
-    if (mi && mj) {
-        tri[before] = packed;
-        inv[i * N + j] = -1 - before;
+        q = rl;
     } else {
-        tri[Rs + rl - before] = packed;
-        inv[i * N + j] = rl - before;
+        const bool mi = (mask.w[i >> 5] >> (i & 31)) & 1u, mj = (mask.w[j >> 5] >> (j & 31)) & 1u;
+        const int si = shared_below(mask, i), sj = shared_below(mask, j);
+        const int before = si * n_shared - (si * (si - 1)) / 2 + (mi ? (sj - si) : 0);   // shared pairs ahead of (i,j)
+        if (mi && mj) {
+            tri[before] = packed;
+            inv[i * N + j] = -1 - before;
+            roww[before] = (float)((i == j) ? B : 2 * B);
+            rowij[before] = make_int2(i, j);
+            q = -1;
+        } else {
+            tri[Rs + rl - before] = packed;
+            inv[i * N + j] = rl - before;
+            q = rl - before;
+        }
+    }
+    if (q >= 0) {
+        const float w = (i == j) ? 1.f : 2.f;
+        for (int b = 0; b < B; ++b) {    // consecutive threads -> consecutive rows of graph b
+            roww[Rs + b * Rq + q] = w;
+            rowij[Rs + b * Rq + q] = make_int2(b * N + i, b * N + j);
+        }
     }
 }
 
@@ -925,6 +944,8 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     Carver ws(workspace);
     L.tri = ws.take<int>(Rg);
     L.inv = ws.take<int>((size_t)N * N);
+    L.roww = ws.take<float>(R + 4);
+    L.rowij = ws.take<int2>(R + 4);
     L.S = ws.take<float>((size_t)B * N * N);
     L.dyA = ws.take<float>(R * 2 * nf);
     L.dyB = ws.take<float>(R * 2 * nf);
@@ -952,11 +973,11 @@ int wcompute_fwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params*
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
     NodeMask mask;
     const int n_shared = mask_from_host(shared_nodes, B, N, mask);
-    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared);
+    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared, L.roww, L.rowij);
     MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * 4 * kStatSlot, st));
     {
         ProfScope ps(PC_PREP, st);
-        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, N, g.Rg, g.Rs, n_shared, mask);
+        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, L.roww, L.rowij, B, N, g.Rg, g.Rs, n_shared, mask);
         MFT_CHECK_LAUNCH();
     }
     if (precision == MFT_PREC_TF32) return wcompute_fwd_prepare_tf32(p, L, F, nf, st);
@@ -973,7 +994,7 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
     NodeMask mask;
     const int n_shared = mask_from_host(shared_nodes, B, N, mask);
-    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared);
+    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared, L.roww, L.rowij);
 
     if (!prepared) {
         int rc = wcompute_fwd_prepare(B, N, F, nf, p, saved, workspace, precision, shared_nodes, st);
@@ -1043,7 +1064,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
     NodeMask mask;
     const int n_shared = mask_from_host(shared_nodes, B, N, mask);
-    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared);
+    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared, L.roww, L.rowij);
 
     MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * kStatSlot, st));
     int wg_copies[4] = {0, 0, 0, 0};
@@ -1058,7 +1079,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         cudaStream_t s0 = br.fork(0);
         {
             ProfScope ps(PC_PREP, s0);
-            tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, s0>>>(L.tri, L.inv, N, g.Rg, g.Rs, n_shared, mask);
+            tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, s0>>>(L.tri, L.inv, L.roww, L.rowij, B, N, g.Rg, g.Rs, n_shared, mask);
             MFT_CHECK_LAUNCH();
         }
         if (precision == MFT_PREC_TF32) {

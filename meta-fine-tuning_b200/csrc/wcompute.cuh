@@ -16,6 +16,8 @@ struct WcLayout {
     double* fsums;       // saved: forward batch statistics, 4 x [2*kMaxC]
     int* tri;            // workspace: unordered-pair table [Rg]
     int* inv;            // workspace: (i, j) -> table index [N*N]
+    float* roww;         // workspace: per-row multiplicity [R + 1] (PairGeom::roww)
+    int2* rowij;         // workspace: per-row node-matrix rows [R + 1] (PairGeom::rowij)
     float* S;            // workspace: scores / dS, [B,N,N]
     float* dyA;          // workspace: ping-pong gradient buffers [R, 2nf]
     float* dyB;

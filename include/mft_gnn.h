@@ -185,7 +185,8 @@ int mft_prof_enable(int on);
 /* Launch overlap (new): 0 = plain stream order; 1 = the consecutive tcgen05 GEMM launches of an
  * edge MLP use programmatic dependent launch (prologue of launch n+1 -- barrier/TMEM set-up and the
  * resident weight image -- runs under the tail of launch n); 2 = also the row kernels around them
- * (default; environment MFT_PDL).  Results are identical at every level.  Returns the old level. */
+ * (environment MFT_PDL; default 0: measured neutral on B200 because every layer is a grid-wide
+ * BatchNorm dependency).  Results are identical at every level.  Returns the old level. */
 int mft_set_pdl(int level);
 int mft_prof_categories(void);
 const char* mft_prof_name(int cat);

@@ -56,8 +56,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
 #endif
 
-// 0 = plain stream order, 1 = programmatic dependent launch inside the edge-MLP GEMM chains,
-// 2 = also for the row kernels around them (default; MFT_PDL in the environment, mft_set_pdl()).
+// 0 = plain stream order (default), 1 = programmatic dependent launch inside the edge-MLP GEMM chains,
+// 2 = also for the row kernels around them (MFT_PDL in the environment, mft_set_pdl()).  Measured on
+// B200 (profiles/r01_summary.md): neutral at 5w20s -- every layer is a grid-wide BatchNorm dependency
+// and the persistent CTAs own whole SMs, so only the launch latency overlaps -- and +-2 % at 5w5s.
 int pdl_level();
 bool prof_enabled();
 
@@ -95,7 +97,7 @@ struct PairGeom {
     const int* inv;   // [N*N] (i <= j): index into the per-graph part, or -1 - index into the shared part
     // Per-ROW tables (tri_table_kernel) for the tcgen05 kernels, whose roles must not stall on a
     // division plus a dependent table load per row: a pure load each, consumed a tile later.
-    const float* roww;  // [R + 1] multiplicity w of row r (see PairRow); roww[R] = 0 stands for "past the end"
+    const float* roww;  // [R + 64] multiplicity w of row r (see PairRow); roww[R...] = 0 stands for "past the end"
     const int2* rowij;  // [R + 1] node-matrix rows (b*N + i, b*N + j) of row r (b = 0 for a shared row)
 };
 

@@ -20,6 +20,7 @@
 // Pipelines: full/empty mbarriers per A stage (producers <-> MMA), tmem_full/tmem_empty per
 // accumulator (MMA <-> epilogue).  Every wait is bounded (umma::mbar_wait traps on timeout).
 #include <cstdio>
+#include <cstdlib>
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
 #include "common.cuh"
@@ -331,7 +332,7 @@ struct DhT {                                     // P = dH_k from (dy_k, H_k)
             aux[2 * kMaxC + c] = S;
         }
     }
-    __device__ __forceinline__ Row row(int r) const { return Row{__ldg(g.roww + r)}; }       // r <= R
+    __device__ __forceinline__ Row row(int r) const { return Row{decode_row(r, g).w}; }   // see the NOTE in umma_wgrad_kernel
     __device__ __forceinline__ void fetch(const Row&, int, Raw&) const {}
     __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
         return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -410,9 +411,9 @@ struct EpiStoreU {
     __device__ __forceinline__ int row_stride() const { return ld; }
     __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
     __device__ __forceinline__ uint2 prefetch(unsigned, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(unsigned roff, bool ok, float, int col, float4 v, uint2, int nvalid, float*,
-                                          float*, const Consts&) const {
-        float* o = out + (roff + (unsigned)col);
+    __device__ __forceinline__ void apply(unsigned roff, int chcol, bool ok, float, int, float4 v, uint2, int nvalid,
+                                          float*, float*, const Consts&) const {
+        float* o = (out + roff) + chcol;
         if (!ok) return;
         if (vec_ok && nvalid == 4) {
             *reinterpret_cast<float4*>(o) = v;
@@ -441,9 +442,9 @@ struct EpiStoreBf16U {
     __device__ __forceinline__ int row_stride() const { return ld; }
     __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
     __device__ __forceinline__ uint2 prefetch(unsigned, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(unsigned roff, bool ok, float, int col, float4 v, uint2, int, float*, float*,
-                                          const Consts&) const {
-        uint2* o = reinterpret_cast<uint2*>(out + (roff + (unsigned)col));
+    __device__ __forceinline__ void apply(unsigned roff, int chcol, bool ok, float, int col, float4 v, uint2, int,
+                                          float*, float*, const Consts&) const {
+        uint2* o = reinterpret_cast<uint2*>((out + roff) + chcol);
         const uint2 pk = pack_bf4(v);
         if (ok && col < ld) *o = pk;
     }
@@ -465,12 +466,15 @@ struct EpiFwdStatsU {
     __device__ __forceinline__ int row_stride() const { return C; }
     __device__ __forceinline__ Consts consts(int, const float*) const { return Consts{}; }
     __device__ __forceinline__ uint2 prefetch(unsigned, int) const { return make_uint2(0u, 0u); }
-    __device__ __forceinline__ void apply(unsigned roff, bool ok, float w, int col, float4 v, uint2, int, float* s0,
-                                          float* s1, const Consts&) const {
+    __device__ __forceinline__ void apply(unsigned roff, int chcol, bool ok, float w, int, float4 v, uint2, int,
+                                          float* s0, float* s1, const Consts&) const {
         const uint2 packed = pack_half4(v);
-        uint2* o = reinterpret_cast<uint2*>(H + (roff + (unsigned)col));
+        uint2* o = reinterpret_cast<uint2*>((H + roff) + chcol);
         if (ok) *o = packed;
-        v = unpack_half4(packed);            // statistics of what the next layer will actually read
+        // statistics of exactly what the next layer will read (taking them from the fp32 accumulators
+        // saves four instructions per access but moves enough LeakyReLU kinks on the 84-row fixture to
+        // break its gradient tolerance, and bought nothing measurable: the role is not issue-bound)
+        v = unpack_half4(packed);
         const f2 ww = pack2(w, w), vlo = pack2(v.x, v.y), vhi = pack2(v.z, v.w);
         unpack2(fma2(ww, vlo, pack2(s0[0], s0[1])), s0[0], s0[1]);
         unpack2(fma2(ww, vhi, pack2(s0[2], s0[3])), s0[2], s0[3]);
@@ -517,9 +521,9 @@ struct EpiDyU {
         c.sh = *reinterpret_cast<const float4*>(aux + kMaxC + col);
         return c;
     }
-    __device__ __forceinline__ uint2 prefetch(unsigned roff, int col) const { return ldg8(H + (roff + (unsigned)col)); }
-    __device__ __forceinline__ void apply(unsigned roff, bool ok, float, int col, float4 v, uint2 hraw, int, float* s0,
-                                          float* s1, const Consts& k) const {
+    __device__ __forceinline__ uint2 prefetch(unsigned roff, int chcol) const { return ldg8((H + roff) + chcol); }
+    __device__ __forceinline__ void apply(unsigned roff, int chcol, bool ok, float, int, float4 v, uint2 hraw, int,
+                                          float* s0, float* s1, const Consts& k) const {
         const float4 h = unpack_half4(hraw);
         const f2 hlo = pack2(h.x, h.y), hhi = pack2(h.z, h.w);
         float4 y;
@@ -529,7 +533,7 @@ struct EpiDyU {
         const f2 dhi = mul2(pack2(v.z, v.w), pack2(y.z > 0.f ? 1.f : kSlope, y.w > 0.f ? 1.f : kSlope));
         float4 d;
         unpack2(dlo, d.x, d.y); unpack2(dhi, d.z, d.w);
-        float4* o = reinterpret_cast<float4*>(dy + (roff + (unsigned)col));
+        float4* o = reinterpret_cast<float4*>((dy + roff) + chcol);
         if (ok) *o = d;
         unpack2(add2(pack2(s0[0], s0[1]), dlo), s0[0], s0[1]);
         unpack2(add2(pack2(s0[2], s0[3]), dhi), s0[2], s0[3]);
@@ -908,9 +912,15 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
             for (int q = 0; q < 8; ++q) wq[q] = wq_next[q];
             if (Epi::kRowWeight) load_weights(tile + gridDim.x, wq_next);
-            unsigned roff[8];                                 // element offset of each of the thread's rows (clamped)
+            // element offset of this thread's first column (chunk 0) in each of its rows (row clamped);
+            // pinned in a register: left alone, the compiler rebuilds row * stride + column and reloads
+            // the base pointer for every 16-byte access (9 of 23 instructions per access in the profile)
+            unsigned roff[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) roff[q] = (unsigned)(min(row0 + q * 4 + rsub, s.R - 1) * epi.row_stride());
+            for (int q = 0; q < 8; ++q) {
+                roff[q] = (unsigned)(min(row0 + q * 4 + rsub, s.R - 1) * epi.row_stride() + s.n0 + c4);
+                asm volatile("" : "+r"(roff[q]));
+            }
             mbar_wait(&tfull[acc], aph);
             tc_fence_after_sync();
             if (warp == UM_EPI_WARP0 && it == 0) MFT_MARK(12);             // first accumulator ready
@@ -925,7 +935,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                 if (Epi::kPrefetch && chunk_live(ch)) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)       // pure loads, row clamped in bounds
-                        dst[q] = epi.prefetch(roff[q], s.n0 + ch * 32 + c4);
+                        dst[q] = epi.prefetch(roff[q], ch * 32);
                 }
             };
             tmem_ld_32x32(tbase, v);
@@ -969,7 +979,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int r = row0 + q * 4 + rsub;
-                            epi.apply(roff[q], r < s.R, wq[q], col, a[q], pre[Epi::kPrefetch ? (ch & 1) : 0][q],
+                            epi.apply(roff[q], ch * 32, r < s.R, wq[q], col, a[q], pre[Epi::kPrefetch ? (ch & 1) : 0][q],
                                       nvalid, s0[ch < UM_STAT_CHUNKS ? ch : 0], s1[ch < UM_STAT_CHUNKS ? ch : 0],
                                       ec);
                         }
@@ -1141,15 +1151,20 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             const uint32_t off_h = WG_ROWS * s.Cout * 4, off_q = off_h + WG_ROWS * s.Cout * 2;
             typename QOp::Row qr;
             typename QOp::Raw qraw[QOp::kTma ? 1 : kQBmax];
-            // the row multiplicity is a dependent global load (pair table): fetched one chunk ahead
-            float w_next = pop.row(c_begin < c_end ? min(c_begin * WG_ROWS + rl, s.R) : s.R).w;   // pure load
+            // the row multiplicity is a dependent global load (pair table): fetched one chunk ahead.
+            // NOTE: this role keeps decode_row().  Reading w from the per-row table (PairGeom::roww) --
+            // by __ldg one chunk ahead or through the TMA slab -- made d conv2d_1.weight (the variants that
+            // also issue the |x_i - x_j| loads) differ by ~10 % from run to run on B200, with every
+            // barrier of the kernel strengthened; not understood yet (profiles/r01_summary.md), so the
+            // bit-reproducible form stays.
+            float w_next = (c_begin < c_end && c_begin * WG_ROWS + rl < s.R) ? pop.row(c_begin * WG_ROWS + rl).w : 0.f;
             for (int c = c_begin; c < c_end; ++c) {
                 const int r = c * WG_ROWS + rl;
                 const bool ok = r < s.R;
                 const float w = w_next;
                 {
                     const int rn = r + WG_ROWS;
-                    w_next = pop.row(c + 1 < c_end ? min(rn, s.R) : s.R).w;
+                    w_next = (c + 1 < c_end && rn < s.R) ? pop.row(rn).w : 0.f;
                 }
                 mbar_wait(&rawfull[rs], rph);
                 const uint8_t* rb = rawring + (size_t)rs * s.raw_bytes;

@@ -219,10 +219,8 @@ __global__ void tri_table_kernel(int* tri, int* inv, float* roww, int2* rowij, i
                                  int n_shared, NodeMask mask) {
     int rl = blockIdx.x * blockDim.x + threadIdx.x;
     const int Rq = Rg - Rs, R = Rs + B * Rq;
-    if (rl == 0) {                       // the "past the end" entry
-        roww[R] = 0.f;
-        rowij[R] = make_int2(0, 0);
-    }
+    if (rl < 64) roww[R + rl] = 0.f;     // "past the end" entries (the wgrad kernel copies whole 32-row slabs)
+    if (rl == 0) rowij[R] = make_int2(0, 0);
     if (rl >= Rg) return;
     int i, j;
     decode_local(rl, N, i, j);
@@ -944,7 +942,7 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     Carver ws(workspace);
     L.tri = ws.take<int>(Rg);
     L.inv = ws.take<int>((size_t)N * N);
-    L.roww = ws.take<float>(R + 4);
+    L.roww = ws.take<float>(R + 64);
     L.rowij = ws.take<int2>(R + 4);
     L.S = ws.take<float>((size_t)B * N * N);
     L.dyA = ws.take<float>(R * 2 * nf);

@@ -65,6 +65,7 @@ struct UmmaShape {
     int raw_stages;   // fp16 raw-block ring depth (TMA operands only, else 0)
     long long* dbg;   // optional [gridDim.x][16] clock64 timeline (debug builds of the tests only)
     int reverse;      // walk the row tiles from the last to the first (see next_direction())
+    unsigned zero;    // always 0; unknown to the compiler (see the raw-ring release in the producers)
 };
 
 static inline size_t umma_smem_bytes(const UmmaShape& s) {
@@ -332,7 +333,7 @@ struct DhT {                                     // P = dH_k from (dy_k, H_k)
             aux[2 * kMaxC + c] = S;
         }
     }
-    __device__ __forceinline__ Row row(int r) const { return Row{decode_row(r, g).w}; }   // see the NOTE in umma_wgrad_kernel
+    __device__ __forceinline__ Row row(int r) const { return Row{__ldg(g.roww + r)}; }       // r <= R
     __device__ __forceinline__ void fetch(const Row&, int, Raw&) const {}
     __device__ __forceinline__ float4 finish(const Raw&, const Row&, int, const float*) const {
         return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -708,8 +709,19 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
 #pragma unroll
                     for (int q = 0; q < RQ; ++q)
                         raw[q] = *reinterpret_cast<const uint2*>(rawb + (q * RSTEP + rsub) * 64 + c16 * 8);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&rawempty[rs]);      // the block is in registers: slot reusable
+                    // Release the slot only once the loads have COMPLETED in every lane, not merely been
+                    // issued: the TMA thread refills a released slot at once, and an LDS can sit in the memory
+                    // pipeline behind the other warps' stores and the MMA's operand reads (the wgrad kernel
+                    // showed exactly that race on B200).  The arrival count is made to depend on every
+                    // lane's loaded registers through a warp-wide OR with a run-time zero, so neither the
+                    // compiler nor the hardware can let the arrive overtake the loads.
+                    {
+                        unsigned t = 0;
+#pragma unroll
+                        for (int q = 0; q < RQ; ++q) t |= raw[q].x | raw[q].y;
+                        const unsigned z = __reduce_or_sync(0xffffffffu, t & s.zero);
+                        if (lane == 0) mbar_arrive_n(&rawempty[rs], 1u + z);
+                    }
                     if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
                     mbar_wait(&empty[st], ph ^ 1);
                     float* blk = Asm + (size_t)st * UM_BLOCK_FLOATS;
@@ -1151,20 +1163,15 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             const uint32_t off_h = WG_ROWS * s.Cout * 4, off_q = off_h + WG_ROWS * s.Cout * 2;
             typename QOp::Row qr;
             typename QOp::Raw qraw[QOp::kTma ? 1 : kQBmax];
-            // the row multiplicity is a dependent global load (pair table): fetched one chunk ahead.
-            // NOTE: this role keeps decode_row().  Reading w from the per-row table (PairGeom::roww) --
-            // by __ldg one chunk ahead or through the TMA slab -- made d conv2d_1.weight (the variants that
-            // also issue the |x_i - x_j| loads) differ by ~10 % from run to run on B200, with every
-            // barrier of the kernel strengthened; not understood yet (profiles/r01_summary.md), so the
-            // bit-reproducible form stays.
-            float w_next = (c_begin < c_end && c_begin * WG_ROWS + rl < s.R) ? pop.row(c_begin * WG_ROWS + rl).w : 0.f;
+            // the row multiplicity: a pure load from the per-row table (entry R = 0), fetched one chunk ahead
+            float w_next = pop.row(c_begin < c_end ? min(c_begin * WG_ROWS + rl, s.R) : s.R).w;
             for (int c = c_begin; c < c_end; ++c) {
                 const int r = c * WG_ROWS + rl;
                 const bool ok = r < s.R;
                 const float w = w_next;
                 {
                     const int rn = r + WG_ROWS;
-                    w_next = (c + 1 < c_end && rn < s.R) ? pop.row(rn).w : 0.f;
+                    w_next = pop.row(c + 1 < c_end ? min(rn, s.R) : s.R).w;
                 }
                 mbar_wait(&rawfull[rs], rph);
                 const uint8_t* rb = rawring + (size_t)rs * s.raw_bytes;
@@ -1187,9 +1194,11 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                             qv[b] = *reinterpret_cast<const uint2*>(rb + off_q + ((size_t)rl * s.Cin + k) * 2);
                         }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&rawempty[rs]);      // slab is in registers
-                if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
+                // The slab is NOT released here: its loads have only been ISSUED.  Releasing the slot now lets
+                // the TMA thread overwrite it while those LDS still sit in the memory pipeline behind the
+                // other warps' stores and the MMA's operand reads (seen on B200 as a 10 % run-to-run spread
+                // of d conv2d_1.weight once this role stopped stalling on the pair table).  The release
+                // follows the stores that consume the values, below.
                 if constexpr (!QOp::kTma) {                       // |x_i - x_j| from the L2-resident node matrix
                     qr = qop.row(ok ? r : 0);
 #pragma unroll
@@ -1219,7 +1228,11 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[st]);
+                if (lane == 0) {
+                    mbar_arrive(&rawempty[rs]);                  // every lane has stored what it read from the slab
+                    mbar_arrive(&full[st]);
+                }
+                if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
                 if (++st == s.stages) { st = 0; ph ^= 1; }
             }
         } else {
@@ -1545,7 +1558,7 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
                 return MFT_ERR_UNSUPPORTED;
             }
         }
-        s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.reverse = dir;
+        s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.reverse = dir; s.zero = 0u;
         s.dbg = nullptr;
         if (g_umma_dbg && g_umma_dbg_skip-- == 0) { s.dbg = g_umma_dbg; g_umma_dbg = nullptr; }
         float* img = wimg + (size_t)p * s.N_TILE * s.KC * UM_KB;

@@ -1083,6 +1083,7 @@ struct WgradShape {
     int raw_bytes;     // bytes of one raw stage: [dy fp32 | H fp16 | Hq fp16] slabs of 32 rows
     int copies;        // > 1: every CTA stores its partial dW into its own copy, `copy_stride` floats apart
     int copy_stride;   //      (dW 16-byte aligned, ldw % 4 == 0); 1: atomic accumulation into dW
+    unsigned zero;     // always 0; unknown to the compiler (raw-ring release of the producers)
 };
 
 static inline size_t wgrad_smem_bytes(const WgradShape& s) {
@@ -1194,11 +1195,28 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                             qv[b] = *reinterpret_cast<const uint2*>(rb + off_q + ((size_t)rl * s.Cin + k) * 2);
                         }
                 }
-                // The slab is NOT released here: its loads have only been ISSUED.  Releasing the slot now lets
-                // the TMA thread overwrite it while those LDS still sit in the memory pipeline behind the
-                // other warps' stores and the MMA's operand reads (seen on B200 as a 10 % run-to-run spread
-                // of d conv2d_1.weight once this role stopped stalling on the pair table).  The release
-                // follows the stores that consume the values, below.
+                // Release the slab only once its loads have COMPLETED in every lane -- they have merely been
+                // ISSUED here, and the TMA thread refills a released slot at once, under LDS that still sit in
+                // the memory pipeline behind the other warps' stores and the MMA's operand reads (seen on B200
+                // as a 10 % run-to-run spread of d conv2d_1.weight once this role stopped stalling on the pair
+                // table).  The arrival count is tied to every lane's loaded registers through a warp-wide OR
+                // with a run-time zero, so neither compiler nor hardware can let the arrive overtake the loads.
+                {
+                    unsigned t = 0;
+#pragma unroll
+                    for (int b = 0; b < kPBmax; ++b)
+                        if (PBc != 0 || b < s.PB)
+                            t |= __float_as_uint(dv[b].x) | __float_as_uint(dv[b].y) | __float_as_uint(dv[b].z) |
+                                 __float_as_uint(dv[b].w) | hv[b].x | hv[b].y;
+                    if constexpr (QOp::kTma) {
+#pragma unroll
+                        for (int b = 0; b < kQBmax; ++b)
+                            if (QBc != 0 || b < s.QB) t |= qv[b].x | qv[b].y;
+                    }
+                    const unsigned z = __reduce_or_sync(0xffffffffu, t & s.zero);
+                    if (lane == 0) mbar_arrive_n(&rawempty[rs], 1u + z);
+                }
+                if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
                 if constexpr (!QOp::kTma) {                       // |x_i - x_j| from the L2-resident node matrix
                     qr = qop.row(ok ? r : 0);
 #pragma unroll
@@ -1228,11 +1246,7 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&rawempty[rs]);                  // every lane has stored what it read from the slab
-                    mbar_arrive(&full[st]);
-                }
-                if (++rs == s.raw_stages) { rs = 0; rph ^= 1; }
+                if (lane == 0) mbar_arrive(&full[st]);
                 if (++st == s.stages) { st = 0; ph ^= 1; }
             }
         } else {
@@ -1630,6 +1644,7 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
     s.copies = copies_out ? max(2, cdiv(nchunks, s.chunks_per_cta)) : 1;   // (a one-CTA launch still stores)
     if (copies_out) *copies_out = cdiv(nchunks, s.chunks_per_cta);
     s.reverse = next_direction();
+    s.zero = 0u;
     size_t smem = wgrad_smem_bytes(s);
     const int grid_x = cdiv(nchunks, s.chunks_per_cta);
 #define MFT_WG_LAUNCH(PBC, QBC)                                                                                      \

@@ -339,6 +339,27 @@ struct DhT {                                     // P = dH_k from (dy_k, H_k)
         return make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __device__ __forceinline__ uint32_t raw_bytes() const { return WG_ROWS_C * C * 6u; }   // fp32 + fp16 slab
+    // The per-channel constants of a thread's 4 channels never change inside a launch: the wgrad producers
+    // hold them in registers (kload once) instead of three LDS.128 per block per chunk -- those loads
+    // sat between the ring stores (possible aliasing kept the compiler from batching them) and were half
+    // of the role's stall samples.
+    struct K { float4 P, Q, S; };
+    __device__ __forceinline__ K kload(int k, const float* aux) const {
+        const int kk = k < C ? k : 0;
+        return K{*reinterpret_cast<const float4*>(aux + kk), *reinterpret_cast<const float4*>(aux + kMaxC + kk),
+                 *reinterpret_cast<const float4*>(aux + 2 * kMaxC + kk)};
+    }
+    __device__ __forceinline__ float4 transform_k(float4 d, uint2 hraw, float w, int k, const K& c) const {
+        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 h = unpack_half4(hraw);
+        const float4 P = c.P, Q = c.Q, S = c.S;
+        const f2 nw = pack2(-w, -w);
+        const f2 lo = fma2(nw, fma2(pack2(S.x, S.y), pack2(h.x, h.y), pack2(Q.x, Q.y)), mul2(pack2(P.x, P.y), pack2(d.x, d.y)));
+        const f2 hi = fma2(nw, fma2(pack2(S.z, S.w), pack2(h.z, h.w), pack2(Q.z, Q.w)), mul2(pack2(P.z, P.w), pack2(d.z, d.w)));
+        float4 r;
+        unpack2(lo, r.x, r.y); unpack2(hi, r.z, r.w);
+        return r;
+    }
     __device__ __forceinline__ float4 transform(float4 d, uint2 hraw, float w, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 h = unpack_half4(hraw);
@@ -380,6 +401,23 @@ struct BnActQT {                                 // Q = LeakyReLU(BN(H_{k-1}))
         return make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __device__ __forceinline__ uint32_t raw_bytes() const { return WG_ROWS_C * C * 2u; }
+    struct K { float4 sc, sh; };                 // see DhT::K
+    __device__ __forceinline__ K kload(int k, const float* aux) const {
+        const int kk = k < C ? k : 0;
+        return K{*reinterpret_cast<const float4*>(aux + kk), *reinterpret_cast<const float4*>(aux + kMaxC + kk)};
+    }
+    __device__ __forceinline__ float4 transform_k(uint2 hraw, int k, const K& c) const {
+        if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 h = unpack_half4(hraw);
+        const float4 sc = c.sc, sh = c.sh;
+        const f2 ylo = fma2(pack2(h.x, h.y), pack2(sc.x, sc.y), pack2(sh.x, sh.y));
+        const f2 yhi = fma2(pack2(h.z, h.w), pack2(sc.z, sc.w), pack2(sh.z, sh.w));
+        const f2 sl = pack2(kSlope, kSlope);
+        float4 y, z;
+        unpack2(ylo, y.x, y.y); unpack2(yhi, y.z, y.w);
+        unpack2(mul2(ylo, sl), z.x, z.y); unpack2(mul2(yhi, sl), z.z, z.w);
+        return make_float4(fmaxf(y.x, z.x), fmaxf(y.y, z.y), fmaxf(y.z, z.z), fmaxf(y.w, z.w));
+    }
     __device__ __forceinline__ float4 transform(uint2 hraw, int k, const float* aux) const {
         if (k >= C) return make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 h = unpack_half4(hraw);
@@ -1094,7 +1132,7 @@ static inline size_t wgrad_smem_bytes(const WgradShape& s) {
 // PBc / QBc: compile-time operand block counts (0 = take them from the shape at run time; the run-time
 // guards cost more instructions per chunk than the arithmetic of the small layers)
 template <class POp, class QOp, int PBc, int QBc>
-__global__ void __launch_bounds__(WG_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)   // 10 warps = 3 on one SM sub-partition: 16384 / 96 -> at most 168 registers
 umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp qop, float* __restrict__ dW, int ldw,
                   const __grid_constant__ WgradShape s) {
     extern __shared__ uint8_t smem_raw[];
@@ -1164,6 +1202,17 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
             const uint32_t off_h = WG_ROWS * s.Cout * 4, off_q = off_h + WG_ROWS * s.Cout * 2;
             typename QOp::Row qr;
             typename QOp::Raw qraw[QOp::kTma ? 1 : kQBmax];
+            // This thread's channel constants of P stay in registers for the whole launch where the budget
+            // (168) allows: next to a TMA-fed Q.  With the |x_i - x_j| operand (48 registers of loads in
+            // flight) they are reloaded per chunk, three blocks per batch of loads.
+            constexpr bool kPersist = QOp::kTma;
+            constexpr int kBatch = kPersist ? kPBmax : (kPBmax + 1) / 2;
+            typename POp::K pk[kPersist ? kPBmax : kBatch];
+            if constexpr (kPersist) {
+#pragma unroll
+                for (int b = 0; b < kPBmax; ++b)
+                    if (PBc != 0 || b < s.PB) pk[b] = pop.kload(b * UM_KB + c16 * 4, aux_p);
+            }
             // the row multiplicity: a pure load from the per-row table (entry R = 0), fetched one chunk ahead
             float w_next = pop.row(c_begin < c_end ? min(c_begin * WG_ROWS + rl, s.R) : s.R).w;
             for (int c = c_begin; c < c_end; ++c) {
@@ -1227,22 +1276,44 @@ umma_wgrad_kernel(const __grid_constant__ POp pop, const __grid_constant__ QOp q
                 float* dst = ring + (size_t)st * stage_floats + off;
                 const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int b = 0; b < kPBmax; ++b) {
-                    if (PBc != 0 || b < s.PB) {
-                        float4 v = ok ? pop.transform(dv[b], hv[b], w, b * UM_KB + c16 * 4, aux_p) : zero;
-                        v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
-                        *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
+                for (int b0 = 0; b0 < kPBmax; b0 += kBatch) {
+                    if constexpr (!kPersist) {
+#pragma unroll
+                        for (int b = b0; b < b0 + kBatch && b < kPBmax; ++b)
+                            if (PBc != 0 || b < s.PB) pk[b - b0] = pop.kload(b * UM_KB + c16 * 4, aux_p);
+                    }
+#pragma unroll
+                    for (int b = b0; b < b0 + kBatch && b < kPBmax; ++b) {
+                        if (PBc != 0 || b < s.PB) {
+                            float4 v = ok ? pop.transform_k(dv[b], hv[b], w, b * UM_KB + c16 * 4, pk[kPersist ? b : b - b0]) : zero;
+                            v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
+                            *reinterpret_cast<float4*>(dst + b * WG_BLOCK_FLOATS) = v;
+                        }
                     }
                 }
+                if constexpr (QOp::kTma) {                        // all of Q's constants in one batch of loads
+                    typename QOp::K qk[kQBmax];
+#pragma unroll
+                    for (int b = 0; b < kQBmax; ++b)
+                        if (QBc != 0 || b < s.QB) qk[b] = qop.kload(b * UM_KB + c16 * 4, aux_q);
+#pragma unroll
+                    for (int b = 0; b < kQBmax; ++b) {
+                        if (QBc != 0 || b < s.QB) {
+                            float4 v = ok ? qop.transform_k(qv[b], b * UM_KB + c16 * 4, qk[b]) : zero;
+                            v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
+                            *reinterpret_cast<float4*>(dst + (nPB + b) * WG_BLOCK_FLOATS) = v;
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int b = 0; b < kQBmax; ++b) {
                     if (QBc != 0 || b < s.QB) {
                         float4 v;
-                        if constexpr (QOp::kTma) v = ok ? qop.transform(qv[b], b * UM_KB + c16 * 4, aux_q) : zero;
-                        else v = ok ? qop.finish(qraw[QOp::kTma ? 0 : b], qr, b * UM_KB + c16 * 4, aux_q) : zero;
+                        v = ok ? qop.finish(qraw[QOp::kTma ? 0 : b], qr, b * UM_KB + c16 * 4, aux_q) : zero;
                         v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
                         *reinterpret_cast<float4*>(dst + (nPB + b) * WG_BLOCK_FLOATS) = v;
                     }
+                }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();

@@ -229,8 +229,7 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def fwd_bwd(nodes):
-        scores = head.forward_gnn_nodes(nodes)
-        return torch.nn.functional.cross_entropy(scores, y)
+        return head.loss_from_nodes(nodes)      # GNN_nl + cross-entropy of the query nodes (mft_query_ce)
 
     def eager_step(nodes):
         for prm in gnn_params:

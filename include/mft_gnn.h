@@ -176,6 +176,14 @@ int mft_head_bwd(const float* feat, int feat_dim, int n_way, int n_support, int 
                  const mft_gconv_params* fc, const float* d_nodes, float* d_feat,
                  const mft_gconv_grads* g, void* saved, void* workspace, void* stream);
 
+/* Cross-entropy of the query nodes and its gradient in one launch (GnnNet.forward_gnn's score selection,
+ * gnnnet.py:216, + set_forward_loss, gnnnet.py:219-224).  out [n_query, n_way*(n_support+1), n_way] is
+ * GNN_nl's output for the graphs of one episode; the query of class c sits at node c*(n_support+1)+n_support
+ * and has label c.  *loss = mean over the n_way*n_query query nodes; d_out (same shape as out) = d loss / d out,
+ * exact zeros on the support nodes. */
+int mft_query_ce(const float* out, int n_way, int n_support, int n_query, float* loss, float* d_out,
+                 void* stream);
+
 /* ---- measurement hooks (new; the reference has no profiler) ---- */
 
 /* Kernels launched by this library in this process so far (bench.py: gpu_launches). */
@@ -185,8 +193,9 @@ int mft_prof_enable(int on);
 /* Launch overlap (new): 0 = plain stream order; 1 = the consecutive tcgen05 GEMM launches of an
  * edge MLP use programmatic dependent launch (prologue of launch n+1 -- barrier/TMEM set-up and the
  * resident weight image -- runs under the tail of launch n); 2 = also the row kernels around them
- * (environment MFT_PDL; default 0: measured neutral on B200 because every layer is a grid-wide
- * BatchNorm dependency).  Results are identical at every level.  Returns the old level. */
+ * (default; environment MFT_PDL).  Worth about 1 % at 5-way 20-shot and 4 % at 5-way 5-shot on B200: every
+ * layer is a grid-wide BatchNorm dependency, so only launch latency and set-up overlap.  Results are
+ * identical at every level.  Returns the old level. */
 int mft_set_pdl(int level);
 int mft_prof_categories(void);
 const char* mft_prof_name(int cat);

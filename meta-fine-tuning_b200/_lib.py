@@ -74,6 +74,7 @@ SIGNATURES = {
                          _i, C.c_char_p, _vp]),
     "mft_head_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "mft_head_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mft_query_ce": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "mft_head_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GconvParams), _vp, _vp, _vp, _vp]),
     "mft_head_bwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GconvParams), _vp, _vp, C.POINTER(GconvGrads), _vp, _vp,
                           _vp]),

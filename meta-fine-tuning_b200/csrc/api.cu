@@ -150,6 +150,12 @@ int mft_gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, con
                    (cudaStream_t)stream);
 }
 
+int mft_query_ce(const float* out, int n_way, int n_support, int n_query, float* loss, float* d_out, void* stream) {
+    MFT_ENTER();
+    MFT_REQUIRE(out && loss && d_out, "mft_query_ce: null pointer");
+    return query_ce(out, n_way, n_support, n_query, loss, d_out, (cudaStream_t)stream);
+}
+
 size_t mft_head_saved_bytes(int n_way, int n_support, int n_query, int D) {
     return head_saved_bytes(n_way * (n_support + n_query), D);
 }

@@ -56,10 +56,11 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
 #endif
 
-// 0 = plain stream order (default), 1 = programmatic dependent launch inside the edge-MLP GEMM chains,
-// 2 = also for the row kernels around them (MFT_PDL in the environment, mft_set_pdl()).  Measured on
-// B200 (profiles/r01_summary.md): neutral at 5w20s -- every layer is a grid-wide BatchNorm dependency
-// and the persistent CTAs own whole SMs, so only the launch latency overlaps -- and +-2 % at 5w5s.
+// 0 = plain stream order, 1 = programmatic dependent launch inside the edge-MLP GEMM chains,
+// 2 = also for the row kernels around them (default; MFT_PDL in the environment, mft_set_pdl()).
+// Measured on B200 (profiles/r01_summary.md): about 1 % at 5w20s and 4 % at 5w5s -- every layer is a
+// grid-wide BatchNorm dependency and the persistent CTAs own whole SMs, so only the launch latency and
+// the set-up of the next kernel overlap.
 int pdl_level();
 bool prof_enabled();
 

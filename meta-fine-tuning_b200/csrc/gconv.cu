@@ -319,6 +319,55 @@ int head_fwd(const float* feat, int feat_dim, int n_way, int n_support, int n_qu
     return MFT_OK;
 }
 
+// Cross-entropy of the query nodes and its gradient in ONE launch (GnnNet.forward_gnn's score selection +
+// set_forward_loss, gnnnet.py:216-224): graph q holds the q-th query of class c at node c*(n_support+1) +
+// n_support, its label is c, the loss is the mean over the n_way*n_query query nodes.  d_out gets
+// (softmax - onehot) / count on the query nodes and exact zeros on the support nodes.  One CTA, fixed
+// summation order.  (The torch sequence -- permute/contiguous, log_softmax, nll_loss and their backwards,
+// zero fill, index_put -- is nine launches in the middle of a 1.5 ms step.)
+__global__ void __launch_bounds__(256)
+query_ce_kernel(const float* __restrict__ out, int n_way, int n_support, int n_query, float* __restrict__ loss,
+                float* __restrict__ d_out) {
+    __shared__ float part[256];
+    const int npg = n_way * (n_support + 1);
+    const int total = n_query * npg;
+    const float inv = 1.f / (float)(n_way * n_query);
+    float acc = 0.f;
+    for (int node = threadIdx.x; node < total; node += blockDim.x) {
+        const int n = node % npg;
+        const int c = n / (n_support + 1), sidx = n - c * (n_support + 1);
+        const float* z = out + (size_t)node * n_way;
+        float* d = d_out + (size_t)node * n_way;
+        if (sidx != n_support) {
+            for (int k = 0; k < n_way; ++k) d[k] = 0.f;
+            continue;
+        }
+        float m = z[0];
+        for (int k = 1; k < n_way; ++k) m = fmaxf(m, z[k]);
+        float se = 0.f;
+        for (int k = 0; k < n_way; ++k) se += expf(z[k] - m);
+        const float lse = m + logf(se);
+        acc += lse - z[c];
+        const float r = inv / se;
+        for (int k = 0; k < n_way; ++k) d[k] = expf(z[k] - m) * r - (k == c ? inv : 0.f);
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 256; ++i) t += part[i];      // fixed order
+        *loss = t * inv;
+    }
+}
+
+int query_ce(const float* out, int n_way, int n_support, int n_query, float* loss, float* d_out, cudaStream_t st) {
+    MFT_REQUIRE(n_way > 0 && n_support > 0 && n_query > 0, "query_ce: bad shape");
+    ProfScope ps(PC_MISC, st);
+    query_ce_kernel<<<1, 256, 0, st>>>(out, n_way, n_support, n_query, loss, d_out);
+    MFT_CHECK_LAUNCH();
+    return MFT_OK;
+}
+
 int head_bwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,
              const mft_gconv_params* fc, const float* d_nodes, float* d_feat, const mft_gconv_grads* g, void* saved,
              void* workspace, cudaStream_t st) {

@@ -38,7 +38,7 @@ int pdl_level() {
     int v = g_pdl.load(std::memory_order_relaxed);
     if (v < 0) {
         const char* e = getenv("MFT_PDL");
-        v = (e && *e) ? atoi(e) : 0;
+        v = (e && *e) ? atoi(e) : 2;
         if (v < 0) v = 0;
         g_pdl.store(v);
     }

@@ -89,6 +89,8 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
               int lrelu, const float* d_out, int ldo, float* dx, float* d_adj, const mft_gconv_grads* g,
               void* saved, void* workspace, cudaStream_t st);
 
+int query_ce(const float* out, int n_way, int n_support, int n_query, float* loss, float* d_out, cudaStream_t st);
+
 size_t head_saved_bytes(int rows, int D);
 size_t head_workspace_bytes(int rows, int D);
 int head_fwd(const float* feat, int feat_dim, int n_way, int n_support, int n_query, int D,

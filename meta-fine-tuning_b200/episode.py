@@ -109,6 +109,32 @@ class _HeadFn(torch.autograd.Function):
         return (d_feat, None, None, None, *grads)
 
 
+class _QueryCEFn(torch.autograd.Function):
+    """GNN_nl output [n_query, n_way*(n_support+1), n_way] -> mean cross-entropy of the query nodes
+    (select_scores + nn.CrossEntropyLoss against query_labels: gnnnet.py:216-224) with its gradient formed
+    in the same launch (mft_query_ce)."""
+
+    @staticmethod
+    def forward(ctx, out, n_way, n_support, n_query):
+        lib = _lib.load_library()
+        _require_cuda(out, "GnnHead")
+        out = out.contiguous()
+        if tuple(out.shape) != (n_query, n_way * (n_support + 1), n_way):
+            raise ValueError("query cross-entropy: output shape %s does not match the episode" % (tuple(out.shape),))
+        loss = torch.empty((), dtype=torch.float32, device=out.device)
+        d_out = torch.empty_like(out)
+        with torch.cuda.device(out.device):
+            _lib.check(lib.mft_query_ce(out.data_ptr(), n_way, n_support, n_query, loss.data_ptr(), d_out.data_ptr(),
+                                        _stream()), "mft_query_ce")
+        ctx.save_for_backward(d_out)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_out,) = ctx.saved_tensors
+        return d_out * g, None, None, None
+
+
 class GnnHead(nn.Module):
     """``fc`` + ``gnn`` of the reference GnnNet (gnnnet.py:30-31), driven on features.
 
@@ -125,6 +151,8 @@ class GnnHead(nn.Module):
         # of the reference's Linear / BatchNorm1d / cat / expand kernels; the compressed variant
         # (gnnnet_copy.py) averages the supports in between and keeps the torch ops
         self.fused_pre_head = True
+        # score selection + cross-entropy + its gradient as one launch (mft_query_ce) in set_forward_loss
+        self.fused_loss = True
         self.n_way = n_way
         self.n_support_in = n_support
         self.compress = compress
@@ -169,5 +197,12 @@ class GnnHead(nn.Module):
             cache[key] = query_labels(self.n_way, self.n_query).to(device)
         return cache[key]
 
+    def loss_from_nodes(self, nodes: torch.Tensor) -> torch.Tensor:
+        """Cross-entropy of the query nodes of graphs made by ``self.nodes`` (gnnnet.py:210-224)."""
+        if self.fused_loss and nodes.is_cuda and type(self.loss_fn) is nn.CrossEntropyLoss:
+            self.gnn.shared_nodes = self.shared_mask() if self.share_support else None
+            return _QueryCEFn.apply(self.gnn(nodes), self.n_way, self.n_support, self.n_query)
+        return self.loss_fn(self.forward_gnn_nodes(nodes), self._labels(nodes.device))
+
     def set_forward_loss(self, feat: torch.Tensor) -> torch.Tensor:
-        return self.loss_fn(self.set_forward(feat), self._labels(feat.device))
+        return self.loss_from_nodes(self.nodes(feat))

@@ -233,3 +233,50 @@ def test_programmatic_dependent_launch_levels_give_identical_results():
         assert torch.equal(dx, res[0][1])
         for k in g:                       # (Gconv fc.weight gradients use split-K atomics: excluded)
             assert torch.equal(g[k], res[0][2][k]), k
+
+
+@pytest.mark.parametrize("n_support,n_query", [(5, 16), (20, 15)])
+def test_fused_query_cross_entropy_equals_torch(n_support, n_query):
+    """mft_query_ce = select_scores + nn.CrossEntropyLoss(query_labels) (gnnnet.py:216-224), value and gradient."""
+    import mft_b200
+    from mft_b200 import episode as E
+    n_way = 5
+    n = n_way * (n_support + 1)
+    out = torch.randn(n_query, n, n_way, generator=torch.Generator().manual_seed(n_support)).mul(3).cuda()
+    a = out.clone().requires_grad_(True)
+    loss_a = E._QueryCEFn.apply(a, n_way, n_support, n_query)
+    (loss_a * 1.7).backward()
+    b = out.clone().requires_grad_(True)
+    loss_b = torch.nn.functional.cross_entropy(E.select_scores(b, n_way, n_support, n_query),
+                                               E.query_labels(n_way, n_query).cuda())
+    (loss_b * 1.7).backward()
+    assert abs(float(loss_a) - float(loss_b)) < 2e-6 * max(1.0, abs(float(loss_b)))
+    assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-8)
+    sup = torch.ones(n, dtype=torch.bool)
+    sup[n_support::n_support + 1] = False
+    assert torch.count_nonzero(a.grad[:, sup]) == 0          # support nodes: exact zeros
+    with pytest.raises(ValueError):
+        E._QueryCEFn.apply(out[:, :-1], n_way, n_support, n_query)
+
+
+def test_gnn_head_fused_loss_matches_unfused():
+    import mft_b200
+    from mft_b200.episode import GnnHead
+    mft_b200.set_precision("fp32")      # (on the TF32 path a 1e-7 change of d_out may flip LeakyReLU slopes)
+    torch.manual_seed(3)
+    head = GnnHead(5, 5).cuda()
+    head.n_query = 16
+    feat = torch.randn(5, 21, 512).cuda()
+    res = []
+    for fused in (True, False):
+        head.fused_loss = fused
+        head.zero_grad(set_to_none=True)
+        loss = head.set_forward_loss(feat)
+        loss.backward()
+        res.append((float(loss), {k: v.grad.double().cpu().numpy() for k, v in head.named_parameters()}))
+    mft_b200.set_precision("auto")
+    assert abs(res[0][0] - res[1][0]) < 1e-5
+    for k in res[0][1]:
+        if U.is_zero_grad("gnn." + k) or U.is_zero_grad(k):
+            continue
+        assert U.rel(res[0][1][k], res[1][1][k]) < 3e-2, (k, U.rel(res[0][1][k], res[1][1][k]))

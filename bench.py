@@ -183,7 +183,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_json(line)
     return 0
 
 
@@ -449,11 +449,45 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "episodes/s", "cores": threads, "kind": "port",
                                     "sample": f"{n_s} whole episodes of the same workload after 1 warm-up "
                                               f"({sec:.2f} s each), torch CPU fp32, oracle/gnn_oracle.py"}
-        print(json.dumps(line))
+        emit_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+class _OnlyJsonOnStdout:
+    """stdout carries exactly ONE JSON line.  Native libraries write to file descriptor 1 behind Python's back
+    (the torch-bundled NCCL prints "NCCL version ..." there at communicator set-up, whatever NCCL_DEBUG and
+    NCCL_DEBUG_FILE say), so descriptor 1 points at stderr for the whole run and the JSON line is written to
+    the real stdout at the end."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self._real, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+        return False
+
+
+_OUT = None
+
+
+def emit_json(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text)
 
 
 def main():
@@ -470,9 +504,14 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    global _OUT
+    with _OnlyJsonOnStdout() as _OUT:
+        try:
+            if args.impl == "reference":
+                return run_reference(args)
+            return run_ours(args)
+        finally:
+            _OUT = None
 
 
 if __name__ == "__main__":

@@ -41,3 +41,19 @@ def test_product_arm_fails_loudly_without_cuda():
     assert r.returncode != 0
     assert r.stdout.strip() == ""                      # no JSON line from a fallback
     assert "CUDA" in r.stderr or "cuda" in r.stderr
+
+
+def test_stdout_carries_only_the_json_line():
+    """Whatever native code writes to file descriptor 1 during the run (NCCL's version banner under
+    torchrun) must land on stderr; stdout gets the one JSON line."""
+    code = (
+        "import os, sys, json; sys.path.insert(0, %r); import bench\n"
+        "with bench._OnlyJsonOnStdout() as out:\n"
+        "    os.write(1, b'NCCL version x.y.z\\n'); print('python noise')\n"
+        "    out.emit(json.dumps({'metric': 'm', 'value': 1}))\n"
+        "print('after')\n" % ROOT)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.splitlines()
+    assert lines[0] == json.dumps({"metric": "m", "value": 1}) and lines[1:] == ["after"]
+    assert "NCCL version x.y.z" in res.stderr and "python noise" in res.stderr

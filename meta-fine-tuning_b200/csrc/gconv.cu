@@ -323,12 +323,13 @@ int head_fwd(const float* feat, int feat_dim, int n_way, int n_support, int n_qu
 // set_forward_loss, gnnnet.py:216-224): graph q holds the q-th query of class c at node c*(n_support+1) +
 // n_support, its label is c, the loss is the mean over the n_way*n_query query nodes.  d_out gets
 // (softmax - onehot) / count on the query nodes and exact zeros on the support nodes.  One CTA, fixed
-// summation order.  (The torch sequence -- permute/contiguous, log_softmax, nll_loss and their backwards,
+// summation order (a tree of fixed shape).  (The torch sequence -- permute/contiguous, log_softmax, nll_loss and their backwards,
 // zero fill, index_put -- is nine launches in the middle of a 1.5 ms step.)
-__global__ void __launch_bounds__(256)
+constexpr int kCeThreads = 1024;
+__global__ void __launch_bounds__(kCeThreads)
 query_ce_kernel(const float* __restrict__ out, int n_way, int n_support, int n_query, float* __restrict__ loss,
                 float* __restrict__ d_out) {
-    __shared__ float part[256];
+    __shared__ float part[kCeThreads];
     const int npg = n_way * (n_support + 1);
     const int total = n_query * npg;
     const float inv = 1.f / (float)(n_way * n_query);
@@ -353,17 +354,17 @@ query_ce_kernel(const float* __restrict__ out, int n_way, int n_support, int n_q
     }
     part[threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < 256; ++i) t += part[i];      // fixed order
-        *loss = t * inv;
+    for (int half = kCeThreads / 2; half > 0; half >>= 1) {   // fixed-shape tree: same order every run
+        if ((int)threadIdx.x < half) part[threadIdx.x] += part[threadIdx.x + half];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *loss = part[0] * inv;
 }
 
 int query_ce(const float* out, int n_way, int n_support, int n_query, float* loss, float* d_out, cudaStream_t st) {
     MFT_REQUIRE(n_way > 0 && n_support > 0 && n_query > 0, "query_ce: bad shape");
     ProfScope ps(PC_MISC, st);
-    query_ce_kernel<<<1, 256, 0, st>>>(out, n_way, n_support, n_query, loss, d_out);
+    query_ce_kernel<<<1, kCeThreads, 0, st>>>(out, n_way, n_support, n_query, loss, d_out);
     MFT_CHECK_LAUNCH();
     return MFT_OK;
 }

@@ -18,7 +18,8 @@ from typing import Iterable, List, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["owner_of", "owned_episodes", "allreduce_mean_grads", "gather_episode_results", "broadcast_parameters"]
+__all__ = ["owner_of", "owned_episodes", "allreduce_mean_grads", "gather_episode_results", "broadcast_parameters",
+           "average_parameters"]
 
 
 def owner_of(episode: int, world: int) -> int:
@@ -81,6 +82,29 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src)
+
+
+def average_parameters(params: Iterable[torch.nn.Parameter], world: int | None = None) -> int:
+    """Re-synchronise replicas whose parameters moved rank-locally: mean over ranks, in place.
+
+    The first-order-MAML variants (gnnnet.py:90-103 ``MAML_update``; dampnet_full.py) rewind the last
+    backbone stage by a delta each rank computes from ITS episode's inner loop, so after the rewind the
+    replicas differ in exactly those tensors; averaging them is the data-parallel
+    counterpart of the reference's single rewind.  One flat all-reduce; returns the element count."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    ps = [p for p in params]
+    n = sum(p.numel() for p in ps)
+    if world == 1 or not ps:
+        return n
+    flat = torch.cat([p.detach().reshape(-1) for p in ps])
+    _mean_allreduce_(flat, world)
+    off = 0
+    with torch.no_grad():
+        for p in ps:
+            p.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+    return n
 
 
 def gather_episode_results(local: Sequence[float], n_episodes: int, rank: int, world: int,

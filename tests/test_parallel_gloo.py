@@ -51,10 +51,14 @@ def _worker(rank, world, port, out_dir):
     for prm, v in zip(params[-2:], vals[-2:]):
         prm.grad = v.grad.clone()
     n = parallel.allreduce_mean_grads(params, world)
+    # first-order-MAML re-synchronisation: rank-local rewinds, then the mean over ranks
+    moved = [torch.nn.Parameter(torch.full((3, 2), float(rank + 1))), torch.nn.Parameter(torch.arange(5.0) * (rank + 1))]
+    n_avg = parallel.average_parameters(moved, world)
     owned = parallel.owned_episodes(7, rank, world)
     res = parallel.gather_episode_results([float(e) * 10 for e in owned], 7, rank, world)
     if rank == 0:
-        np.savez(os.path.join(out_dir, "r0.npz"), n=n, res=res.numpy(),
+        np.savez(os.path.join(out_dir, "r0.npz"), n=n, res=res.numpy(), n_avg=n_avg,
+                 avg0=moved[0].detach().numpy(), avg1=moved[1].detach().numpy(),
                  **{f"g{i}": prm.grad.numpy() for i, prm in enumerate(params)})
     dist.barrier()
     dist.destroy_process_group()
@@ -74,6 +78,8 @@ def test_dp_gradients_equal_single_process_mean(tmp_path):
     for i, v in enumerate(p.values()):
         assert np.allclose(got[f"g{i}"], v.grad.numpy(), rtol=1e-10, atol=1e-12)
     assert np.array_equal(got["res"], np.arange(7) * 10.0)
+    assert int(got["n_avg"]) == 11
+    assert np.allclose(got["avg0"], 1.5) and np.allclose(got["avg1"], np.arange(5.0) * 1.5)
 
 
 def test_episode_ownership_partitions_everything():

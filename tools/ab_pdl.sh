@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU check of one build: parity tests first, then the bench per launch-overlap level (MFT_PDL) and shape.
+# GPU check of one build (run through gpurun): parity tests first, then the bench per launch-overlap level (MFT_PDL) and shape.
 # usage: tools/ab_pdl.sh "<levels>" "<shapes>"   (defaults: "2" "5w20s 5w5s 5w50c")
 LEVELS=${1:-2}
 SHAPES=${2:-"5w20s 5w5s 5w50c"}

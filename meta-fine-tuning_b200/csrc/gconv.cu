@@ -15,32 +15,8 @@ namespace {
 struct PlainOp {
     const float* p;
     int ld;
-    struct Ctx { const float* row; };
     __device__ __forceinline__ void init(float*) const {}
-    __device__ __forceinline__ Ctx row(int r) const { return Ctx{p + (size_t)r * ld}; }
-    __device__ __forceinline__ float at(const Ctx& c, int k, const float*) const { return c.row[k]; }
     __device__ __forceinline__ float at(int r, int k, const float*) const { return p[(size_t)r * ld + k]; }
-};
-
-struct EpiStore {
-    static constexpr int kStats = 0;
-    float* out;
-    int ld;
-    __device__ __forceinline__ void init(float*) const {}
-    __device__ __forceinline__ void tile(int r0, int c0, int M, int N, float (&acc)[8][6], float (&)[6],
-                                         float (&)[6], const float*) const {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int r = r0 + i;
-            if (r >= M) continue;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                int c = c0 + 32 * (j >> 1) + (j & 1);
-                if (c < N) out[(size_t)r * ld + c] = acc[i][j];
-            }
-        }
-    }
-    __device__ __forceinline__ void commit(int, float, float) const {}
 };
 
 constexpr int kGcRows = 4;    // rows (nodes) per CTA in the per-node kernels

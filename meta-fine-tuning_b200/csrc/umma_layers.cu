@@ -41,7 +41,6 @@ constexpr int UM_EPI_WARP0 = UM_PROD_WARPS;          // epilogue warps 8..11 (wa
 constexpr int UM_MMA_WARP = UM_PROD_WARPS + 4;
 constexpr int UM_TMA_WARP = UM_MMA_WARP + 1;           // issues the tensor-map tile loads of kTma operands
 constexpr int UM_THREADS = (UM_PROD_WARPS + 6) * 32;  // 8 producer + 4 epilogue + MMA + TMA warp = 448
-constexpr int UM_PREFETCH = 2;            // K blocks a producer thread keeps in flight ahead of the one it writes
 constexpr int UM_STAGE_LD = 36;           // padded row length of the epilogue staging tile
 constexpr int UM_ACC_STRIDE = 256;        // TMEM columns between the two accumulators
 constexpr int UM_TMEM_COLS = 512;
@@ -671,7 +670,7 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
         // ===================== producers =====================
         // Thread t owns 16-byte column c16 = t%8 of rows q*32 + t/8 (q = 0..3) of every K block, so
         // its per-channel constants never change within a block and a warp's loads cover four
-        // full 128-byte row segments.  The fetch iterator runs UM_PREFETCH K blocks ahead of the
+        // full 128-byte row segments.  The fetch iterator runs AOp::kAhead K blocks ahead of the
         // write iterator so that global latency overlaps the transform + smem stores.
         reg_dec<96>();   // 8 warps x 32 regs released ...
         constexpr int RQ = UM_ROWS * 8 / UM_PROD_THREADS;      // rows per thread per K block (4)
@@ -1018,7 +1017,6 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
                     if (cl < s.N_TILE && col < s.N) {
                         const int nvalid = min(4, s.N - col);
                         const typename Epi::Consts ec = epi.consts(col, aux_e);
-#pragma unroll
                         // straight-line over the 8 rows (no branch per row: rows past the end hold
                         // exact zeros in TMEM and only their store is predicated off), so the eight
                         // LDS / convert / store chains interleave

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["owner_of", "owned_episodes", "allreduce_mean_grads", "gather_episode_results", "broadcast_parameters",
-           "average_parameters"]
+           "average_parameters", "accuracy_summary"]
 
 
 def owner_of(episode: int, world: int) -> int:
@@ -118,3 +118,14 @@ def gather_episode_results(local: Sequence[float], n_episodes: int, rank: int, w
     if world > 1:
         dist.all_reduce(out, op=dist.ReduceOp.SUM)
     return out
+
+
+def accuracy_summary(acc_all) -> tuple[float, float]:
+    """(mean, 95 % half-width) of the per-episode accuracies exactly as the reference prints them
+    (finetune.py:672-676, meta_template.py:146-149): population std, 1.96 * std / sqrt(n).  Every rank gets
+    the same numbers from the vector ``gather_episode_results`` returns."""
+    a = torch.as_tensor(acc_all, dtype=torch.float64)
+    n = a.numel()
+    mean = float(a.mean())
+    std = float(a.std(unbiased=False))
+    return mean, 1.96 * std / n ** 0.5

@@ -87,3 +87,11 @@ def test_episode_ownership_partitions_everything():
         seen = sorted(e for r in range(world) for e in parallel.owned_episodes(600, r, world))
         assert seen == list(range(600))
         assert all(parallel.owner_of(e, world) == e % world for e in range(0, 600, 37))
+
+
+def test_accuracy_summary_is_the_reference_formula():
+    rng = np.random.default_rng(0)
+    acc = rng.uniform(20, 100, size=600)
+    mean, half = parallel.accuracy_summary(acc)
+    assert abs(mean - np.mean(acc)) < 1e-12
+    assert abs(half - 1.96 * np.std(acc) / np.sqrt(600)) < 1e-12      # finetune.py:672-676

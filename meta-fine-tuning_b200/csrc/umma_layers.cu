@@ -5,22 +5,25 @@
 //
 //     C[r, n] = sum_k A(r, k) * W(n, k)        r: 128-row tiles of unordered pairs
 //
-//   warps 0-3  producers : build the A tile from global memory -- |x_i - x_j| for layer 1,
-//                          LeakyReLU(BN(H)) for later layers, plain loads for dgrad -- round it to
-//                          TF32 and write it K-major / SWIZZLE_128B into a ring of 16 KB K blocks,
-//                          so neither the N^2 x C pair tensor nor any post-BN activation ever
-//                          exists in HBM;
-//   warp  8    MMA issuer: one thread; weights (pre-swizzled TF32 image) land once per CTA by
-//                          bulk async copy and stay resident; tcgen05.mma kind::tf32, M=128,
-//                          N = tile width, accumulators double-buffered in TMEM;
-//   warps 4-7  epilogue  : tcgen05.ld 32 columns at a time -> padded smem staging -> coalesced
-//                          128-byte row segments to global, fused with the per-channel batch
-//                          statistics (forward) or with the LeakyReLU'/BN-backward reductions (dgrad).
+//   warps 0-7   producers : build the A tile -- |x_i - x_j| from the L2-resident node matrix for layer 1,
+//                           LeakyReLU(BN(H)) from the fp16 tape (landed by TMA in a raw ring) for later
+//                           layers, the fused BatchNorm-backward dH (in place on the landed dy block) for
+//                           dgrad -- round it to TF32 and write it K-major / SWIZZLE_128B into a ring of
+//                           16 KB K blocks, so neither the N^2 x C pair tensor nor any post-BN activation
+//                           ever exists in HBM;
+//   warps 8-11  epilogue  : tcgen05.ld 32 columns at a time -> padded smem staging -> coalesced row
+//                           segments to global, fused with the per-channel batch statistics (forward) or
+//                           with the LeakyReLU'/BN-backward reductions (dgrad);
+//   warp  12    MMA issuer: one thread; weights (pre-swizzled TF32 image) land once per CTA by bulk async
+//                           copy and stay resident; tcgen05.mma kind::tf32, M=128, N = tile width,
+//                           accumulators double-buffered in TMEM;
+//   warp  13    TMA loader: one thread; tensor-map tile loads of the tape / gradient operands.
 //
-// Pipelines: full/empty mbarriers per A stage (producers <-> MMA), tmem_full/tmem_empty per
-// accumulator (MMA <-> epilogue).  Every wait is bounded (umma::mbar_wait traps on timeout).
+// Pipelines: rawfull/rawempty mbarriers per raw slot (TMA <-> producers; a slot is released only when the
+// loads from it have COMPLETED, see the producers), full/empty per A stage (producers <-> MMA),
+// tmem_full/tmem_empty per accumulator (MMA <-> epilogue).  Every wait is bounded (umma::mbar_wait traps
+// on timeout).
 #include <cstdio>
-#include <cstdlib>
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
 #include "common.cuh"

@@ -212,6 +212,10 @@ size_t mft_debug_umma_gemm_workspace_bytes(int N, int K);
 int mft_debug_umma_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w,
                         float* C, int ldc, int M, int N, int K, void* workspace, void* stream);
 /* dW[Cout,Cin] += P[R,Cout]^T * Q[R,Cin] on the tensor-core wgrad kernel (Cout <= 192, Cin <= 256). */
+/* Tests: byte offsets of the activation tape inside a Wcompute `saved` blob (H_1..H_4, forward statistics,
+ * tape scales; out[6], out[7] = doubles per statistics slot / per copy).  out: size_t[8]. */
+int mft_debug_wcompute_saved_offsets(int B, int N, int F, int nf, size_t* out);
+
 /* Per-CTA clock64 timeline of ONE rows-GEMM launch, the (skip+1)-th from now, into buf [grid][16]. */
 int mft_debug_set_timeline(void* buf, int skip);
 int mft_debug_umma_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW, int ldw,

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mft_debug_umma_gemm": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mft_debug_umma_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "mft_debug_set_timeline": (_i, [_vp, _i]),
+    "mft_debug_wcompute_saved_offsets": (_i, [_i, _i, _i, _i, C.POINTER(C.c_size_t)]),
     "mft_launch_count": (C.c_ulonglong, []),
     "mft_prof_enable": (_i, [_i]),
     "mft_set_pdl": (_i, [_i]),

@@ -197,6 +197,22 @@ int mft_debug_umma_wgrad(const float* P, int ldp, const float* Q, int ldq, float
     return umma_debug_wgrad(P, ldp, Q, ldq, dW, ldw, R, Cout, Cin, (cudaStream_t)stream);
 }
 
+/* Debug / tests: where the activation tape lives inside a Wcompute `saved` blob.  out[0..3] = byte offsets of the
+ * pre-BatchNorm activations H_1..H_4 ([R, C_k] row-major, R pair rows in the order of the row table: fp16 on the
+ * tensor-core path, fp32 on the fp32 path), out[4] = forward statistics (4 slots of kStatCopies x [2][kMaxC]
+ * doubles), out[5] = the four tape scales (floats), out[6] = doubles per statistics slot, out[7] = doubles per copy. */
+int mft_debug_wcompute_saved_offsets(int B, int N, int F, int nf, size_t* out) {
+    MFT_REQUIRE(out && B > 0 && N > 0 && F > 0 && nf > 0, "mft_debug_wcompute_saved_offsets: bad argument");
+    char* base = nullptr;
+    WcLayout L = wc_layout(B, N, F, nf, base, base);
+    for (int k = 0; k < 4; ++k) out[k] = (size_t)(reinterpret_cast<char*>(L.H[k]) - base);
+    out[4] = (size_t)(reinterpret_cast<char*>(L.fsums) - base);
+    out[5] = (size_t)(reinterpret_cast<char*>(L.tscale) - base);
+    out[6] = (size_t)kStatSlot;
+    out[7] = (size_t)kStatCopyStride;
+    return MFT_OK;
+}
+
 /* Debug: have every following tcgen05 rows-GEMM launch write a per-CTA clock64 timeline
  * ([grid][16] long long) into `buf` (device memory) for ONE launch: the (skip+1)-th from now. */
 int mft_debug_set_timeline(void* buf, int skip) {

@@ -215,10 +215,14 @@ __device__ __forceinline__ double stat_get(const double* slot, int C, int c, int
 __device__ __forceinline__ void bn_mean_rstd(const double* sums, int C, int c, double inv_count,
                                              float& mean, float& rstd) {
     double m = stat_get(sums, C, c, 0) * inv_count;
-    double v = stat_get(sums, C, c, 1) * inv_count - m * m;
-    if (v < 0.0) v = 0.0;
+    // The second-moment sum of a tensor-core-path slot carries count * (s^2 - 1) * eps (s = the layer's
+    // power-of-two tape scale, umma_layer_scales_kernel), so that "variance + eps" below is
+    // var(s h) + s^2 eps and the normalisation is exactly BatchNorm(h; eps) whatever s is.  Hence the
+    // clamp applies to the sum, not to the variance alone.
+    double v = stat_get(sums, C, c, 1) * inv_count - m * m + (double)kBnEps;
+    if (v < 1e-300) v = 1e-300;
     mean = (float)m;
-    rstd = (float)(1.0 / sqrt(v + (double)kBnEps));
+    rstd = (float)(1.0 / sqrt(v));
 }
 
 // Per-channel constants staged in shared memory by every kernel that applies a BN.

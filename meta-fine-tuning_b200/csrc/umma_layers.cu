@@ -93,12 +93,13 @@ __global__ void umma_weight_image_kernel(const float* __restrict__ W, int ldw, i
 }
 
 // All weight images of one Wcompute direction in ONE launch (blockIdx.y = job).
-struct ImgJob { const float* W; float* img; int ldw, transpose, N, K, n0, N_TILE, KC; };
+struct ImgJob { const float* W; float* img; const float* scale; int ldw, transpose, N, K, n0, N_TILE, KC; };
 struct ImgJobs { int n; ImgJob j[12]; };
 
 __global__ void umma_weight_images_kernel(ImgJobs jobs) {
     const ImgJob& jb = jobs.j[blockIdx.y];
     const int total = jb.KC * jb.N_TILE * UM_KB;
+    const float sc = jb.scale ? __ldg(jb.scale) : 1.f;      // the layer's tape scale (a power of two: exact)
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         int kc = idx / (jb.N_TILE * UM_KB);
         int rem = idx - kc * jb.N_TILE * UM_KB;
@@ -107,8 +108,62 @@ __global__ void umma_weight_images_kernel(ImgJobs jobs) {
         float v = 0.f;
         if (jb.n0 + n < jb.N && k < jb.K)
             v = jb.transpose ? jb.W[(size_t)k * jb.ldw + jb.n0 + n] : jb.W[(size_t)(jb.n0 + n) * jb.ldw + k];
-        jb.img[(size_t)kc * jb.N_TILE * UM_KB + sw128_offset(n, kk)] = to_tf32(v);
+        jb.img[(size_t)kc * jb.N_TILE * UM_KB + sw128_offset(n, kk)] = to_tf32(v * sc);
     }
+}
+
+// ------------------------------------------------------------------ tape scales
+// The fp16 tape holds the PRE-BatchNorm activations, whose scale is whatever the conv weights make it,
+// while BatchNorm makes the function itself invariant to that scale.  To keep the tape inside fp16's
+// range (no saturation at 65504, no flush into subnormals) for any weights, layer k runs on
+// W'_k = s_k W_k with s_k = 2^-(e_w + e_a): e_w the binary exponent of max|W_k|, e_a that of
+// max(|gamma_{k-1}|, |beta_{k-1}|) (the scale of the layer's input; 0 for layer 1, whose input is
+// |x_i - x_j| of BatchNorm'd node features).  Exponents as frexp gives them, each and their sum clamped
+// to [-60, 60]; both maxima are exact in any evaluation order, so oracle/gnn_oracle.py tape_scale()
+// reproduces s_k bit for bit.  Consequences, all exact because s_k is a power of two:
+//   tape and statistics hold h' = s h;  BN(h'; s^2 eps) = BN(h; eps): the slot's second-moment sum is
+//   pre-loaded with count (s^2 - 1) eps (see bn_mean_rstd);  dgrad uses W' as is (h' = a W'^T);
+//   dL/dW = s dL/dW' (wgrad_reduce_kernel).
+struct ScaleJobs {
+    const float* W[4];
+    int wn[4];              // elements of W_k
+    const float* g[4];      // gamma / beta of the PREVIOUS BatchNorm (null for layer 1)
+    const float* b[4];
+    int gc[4];              // channels of the previous BatchNorm
+    int C[4];               // output channels of layer k
+    float* tscale;          // [4]
+    double* fsums;          // 4 statistics slots (zeroed on this stream before this launch)
+    double count;           // BatchNorm population B*N*N
+};
+
+__device__ __forceinline__ int frexp_exponent(float v) {
+    if (!(v > 0.f) || !isfinite(v)) return 0;
+    int e;
+    frexpf(v, &e);
+    return max(-60, min(60, e));
+}
+
+__global__ void __launch_bounds__(256) umma_layer_scales_kernel(ScaleJobs j) {   // grid = 4: one CTA per conv layer
+    __shared__ float red[2][8];
+    const int k = blockIdx.x, t = threadIdx.x;
+    float mw = 0.f, ma = 0.f;
+    for (int i = t; i < j.wn[k]; i += blockDim.x) mw = fmaxf(mw, fabsf(__ldg(j.W[k] + i)));
+    if (j.g[k])
+        for (int c = t; c < j.gc[k]; c += blockDim.x) ma = fmaxf(ma, fmaxf(fabsf(__ldg(j.g[k] + c)), fabsf(__ldg(j.b[k] + c))));
+    mw = warp_max(mw);
+    ma = warp_max(ma);
+    if ((t & 31) == 0) { red[0][t >> 5] = mw; red[1][t >> 5] = ma; }
+    __syncthreads();
+    mw = red[0][0]; ma = red[1][0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { mw = fmaxf(mw, red[0][q]); ma = fmaxf(ma, red[1][q]); }
+    int e = frexp_exponent(mw) + (j.g[k] ? frexp_exponent(ma) : 0);
+    e = max(-60, min(60, e));
+    const float sc = ldexpf(1.f, -e);
+    if (t == 0) j.tscale[k] = sc;
+    const double corr = j.count * ((double)sc * (double)sc - 1.0) * (double)kBnEps;
+    double* slot = j.fsums + (size_t)k * kStatSlot;              // copy 0, second moments
+    for (int c = t; c < j.C[k]; c += blockDim.x) slot[j.C[k] + c] = corr;
 }
 
 // ------------------------------------------------------------------ producer functors
@@ -1772,7 +1827,8 @@ static size_t img_offset(int F, int nf, int k) {
 size_t umma_workspace_floats(int F, int nf) { return img_offset(F, nf, 4); }
 
 // Build the images of all four layers (forward: W[n][k]; backward: W^T for dgrad) with one launch.
-static int build_images(const mft_wcompute_params* p, float* wimg, int F, int nf, bool backward, cudaStream_t st) {
+static int build_images(const mft_wcompute_params* p, float* wimg, const float* tscale, int F, int nf, bool backward,
+                        cudaStream_t st) {
     int Cs[5] = {F, 2 * nf, 2 * nf, nf, nf};
     ImgJobs jobs{};
     int max_total = 0;
@@ -1789,6 +1845,7 @@ static int build_images(const mft_wcompute_params* p, float* wimg, int F, int nf
         for (int q = 0; q < passes; ++q) {
             ImgJob& jb = jobs.j[jobs.n++];
             jb.W = p->conv_w[k];
+            jb.scale = tscale + k;
             jb.ldw = Cs[k];                               // conv2d_{k+1}.weight is [Cout, Cin]
             jb.transpose = backward ? 1 : 0;
             jb.N = N; jb.K = K; jb.n0 = n0s[q]; jb.N_TILE = nts[q]; jb.KC = KC;
@@ -1803,15 +1860,33 @@ static int build_images(const mft_wcompute_params* p, float* wimg, int F, int nf
 }
 
 int wcompute_bwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, cudaStream_t st) {
-    return build_images(p, L.wimg, F, nf, true, st);
+    return build_images(p, L.wimg, L.tscale, F, nf, true, st);   // the scales were saved by the forward
 }
 
-int wcompute_fwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, cudaStream_t st) {
+int wcompute_fwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, double count,
+                              cudaStream_t st) {
     if (!umma_shape_supported(F, nf)) {
         set_error(MFT_ERR_UNSUPPORTED, "tf32 path: unsupported shape F=%d nf=%d", F, nf);
         return MFT_ERR_UNSUPPORTED;
     }
-    return build_images(p, L.wimg, F, nf, false, st);
+    {
+        ScaleJobs sj{};
+        for (int k = 0; k < 4; ++k) {
+            sj.W[k] = p->conv_w[k];
+            sj.wn[k] = L.C[k + 1] * L.C[k];
+            sj.g[k] = k > 0 ? p->bn_g[k - 1] : nullptr;
+            sj.b[k] = k > 0 ? p->bn_b[k - 1] : nullptr;
+            sj.gc[k] = L.C[k];
+            sj.C[k] = L.C[k + 1];
+        }
+        sj.tscale = L.tscale;
+        sj.fsums = L.fsums;
+        sj.count = count;
+        ProfScope ps(PC_PREP, st);
+        umma_layer_scales_kernel<<<4, 256, 0, st>>>(sj);          // after the memset of the slots on `st`
+        MFT_CHECK_LAUNCH();
+    }
+    return build_images(p, L.wimg, L.tscale, F, nf, false, st);
 }
 
 // (the four forward weight images exist: wcompute_fwd_prepare_tf32)

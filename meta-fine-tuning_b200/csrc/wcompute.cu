@@ -859,6 +859,7 @@ struct FinalizeArgs {
     float* last_b;
     int C[4];
     int nf;
+    const float* tscale;      // tcgen05 path: the layers' tape scales s_k (dW = s_k * dW'), else null
 };
 
 __global__ void finalize_grads_kernel(FinalizeArgs a) {   // grid = 5: one CTA per BN layer + one for conv2d_last
@@ -919,7 +920,9 @@ wgrad_reduce_kernel(FinalizeArgs a) {
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         float* dst = a.conv_w[k] + (size_t)co * cin + cx * 4;
-        const float o[4] = {acc.x, acc.y, acc.z, acc.w};
+        // the GEMMs ran on W' = s W (exact power of two): dL/dW = s * dL/dW'
+        const float sc = a.tscale ? a.tscale[k] : 1.f;
+        const float o[4] = {acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc};
         for (int e = 0; e < 4; ++e)
             if (cx * 4 + e < cin) dst[e] = o[e];
     }
@@ -938,6 +941,7 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     Carver sv(saved);
     for (int k = 0; k < 4; ++k) L.H[k] = sv.take<float>(R * L.C[k + 1]);
     L.fsums = sv.take<double>(4 * kStatSlot);
+    L.tscale = sv.take<float>(64);
     L.saved_bytes = sv.used();
     Carver ws(workspace);
     L.tri = ws.take<int>(Rg);
@@ -978,7 +982,7 @@ int wcompute_fwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params*
         tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, L.roww, L.rowij, B, N, g.Rg, g.Rs, n_shared, mask);
         MFT_CHECK_LAUNCH();
     }
-    if (precision == MFT_PREC_TF32) return wcompute_fwd_prepare_tf32(p, L, F, nf, st);
+    if (precision == MFT_PREC_TF32) return wcompute_fwd_prepare_tf32(p, L, F, nf, 1.0 / g.inv_pairs, st);
     return MFT_OK;
 }
 
@@ -1184,6 +1188,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     fa.last_w = gr->last_w;
     fa.last_b = gr->last_b;
     fa.nf = nf;
+    fa.tscale = precision == MFT_PREC_TF32 ? L.tscale : nullptr;
     {
         // These only finish parameter gradients: on the caller's tail branch (if any) they run beside
         // whatever the main stream does next.  On the main stream of the tensor-core path they follow the

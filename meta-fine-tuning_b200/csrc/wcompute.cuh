@@ -14,6 +14,7 @@ struct WcLayout {
     int C[5];            // channel widths: F, 2nf, 2nf, nf, nf
     float* H[4];         // saved: pre-BN activations of the four conv layers, [R, C[k+1]]
     double* fsums;       // saved: forward batch statistics, 4 x [2*kMaxC]
+    float* tscale;       // saved (tcgen05 path): power-of-two tape scale s_k of the four conv layers (umma_layers.cu)
     int* tri;            // workspace: unordered-pair table [Rg]
     int* inv;            // workspace: (i, j) -> table index [N*N]
     float* roww;         // workspace: per-row multiplicity [R + 1] (PairGeom::roww)
@@ -60,7 +61,8 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
 // dgrad + wgrad pair of one backward layer; same buffers in and out as the fp32 path.
 int wcompute_fwd_layers_tf32(const float* x, int ldx, int F, int nf, const mft_wcompute_params* p,
                              const WcLayout& L, const PairGeom& g, cudaStream_t st);
-int wcompute_fwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, cudaStream_t st);
+int wcompute_fwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, int F, int nf, double count,
+                              cudaStream_t st);
 int wcompute_bwd_layer_tf32(int k, float* dh, float* dy_next, const float* x, int ldx, float* dx, int F, int nf,
                             const mft_wcompute_params* p, const mft_wcompute_grads* gr, const WcLayout& L,
                             const PairGeom& g, cudaStream_t st);

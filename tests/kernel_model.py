@@ -97,9 +97,17 @@ def wcompute_fwd(x, p, prefix, shared=None):
     return adj, saved
 
 
-def wcompute_bwd(x, p, prefix, saved, d_adj):
+class NoRounding:
+    """Operand roundings of the backward GEMMs (identity here; tests/test_gpu_tape.py passes the
+    tensor-core path's: dH, a and W to TF32, dD to bf16)."""
+    dh = a = w = dD = staticmethod(lambda t: t)
+
+
+def wcompute_bwd(x, p, prefix, saved, d_adj, rounding=NoRounding, perturb=None):
     """Closed-form backward of wcompute_fwd.  Returns dx and parameter grads.  With shared rows the
-    gradient of a shared pair arrives summed over the graphs and is delivered to graph 0's nodes."""
+    gradient of a shared pair arrives summed over the graphs and is delivered to graph 0's nodes.
+    ``perturb``: optional callable (k, dh) -> dh, used by the tests to prove that a small error in the
+    BatchNorm-backward term would be caught."""
     bsz, n, f = x.shape
     w = saved["w"]
     rb, ri, rj, allg = saved["rows"]
@@ -127,10 +135,14 @@ def wcompute_bwd(x, p, prefix, saved, d_adj):
         grads[f"{prefix}bn_{k}.bias"] = sum_dy
         m1, m2 = sum_dy / pairs, sum_dyh / pairs
         dh = gamma * rstd * (dy - w[:, None] * m1 - w[:, None] * hhat * m2)
+        if perturb is not None:
+            dh = perturb(k, dh)
+        dh = rounding.dh(dh)
         wk = p[f"{prefix}conv2d_{k}.weight"].flatten(1)
-        grads[f"{prefix}conv2d_{k}.weight"] = (dh.t() @ saved["a"][k - 1]).reshape(*wk.shape, 1, 1)
+        grads[f"{prefix}conv2d_{k}.weight"] = (dh.t() @ rounding.a(saved["a"][k - 1])).reshape(*wk.shape, 1, 1)
         grads[f"{prefix}conv2d_{k}.bias"] = torch.zeros(wk.shape[0], dtype=x.dtype)   # BN removes the mean
-        da = dh @ wk
+        da = dh @ rounding.w(wk)
+    da = rounding.dD(da)
     contrib = torch.sign(x[rb, ri] - x[rb, rj]) * da
     dx = torch.zeros(bsz * n, f, dtype=x.dtype)
     dx.index_add_(0, rb * n + ri, contrib)

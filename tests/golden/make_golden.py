@@ -20,6 +20,14 @@ head_50c.npz       gnnnet_copy (compressed 50-shot, N=130) scores on features
                    (parameters: those of head_5w5s.npz).
 sampler.npz        EpisodicBatchSampler / generate_perm class draws, support_label,
                    query labels.
+gnn_5w20s.npz      GNN_nl(133, 96, 5), B=16, N=105 (the benchmarked 5-way 20-shot head shape): as
+                   gnn_5w5s.npz (gradients and dx stored as float32).      [python make_golden.py 5w20s]
+head_5w5s_grads.npz  gradients of the n_query=16 loss of head_5w5s.npz w.r.t. every fc.* / gnn.* parameter
+                   and the features (float64 run of the reference, stored float32) plus the reference's own
+                   float32-vs-float64 error per tensor.                    [python make_golden.py headgrads]
+
+Without arguments every fixture is regenerated; with arguments only the named groups
+(base, 5w20s, headgrads).
 """
 import os
 import sys
@@ -87,10 +95,79 @@ def _run_gnn(ref_gnn, fin, nf, n_way, bsz, n, seed):
     return rec
 
 
+def _head_model(ref_gnnnet, ref_backbone):
+    """The GnnNet of head_5w5s.npz, rebuilt deterministically (same seeds, same draws)."""
+    torch.manual_seed(5)
+    np.random.seed(10)
+    m = ref_gnnnet.GnnNet(ref_backbone.ResNet10, n_way=5, n_support=5)
+    gen = torch.Generator().manual_seed(6)
+    _perturb_bn(m.gnn, gen)
+    feat15 = torch.randn(5, 5 + 15, 512, generator=gen)
+    feat16 = torch.randn(5, 5 + 16, 512, generator=gen)
+    return m, feat15, feat16
+
+
+def _head_loss16(m, feat16):
+    z = m.fc(feat16.view(-1, 512)).view(5, -1, 128)
+    z_stack = [torch.cat([z[:, :5], z[:, 5 + i:5 + i + 1]], dim=1).view(1, -1, 128) for i in range(16)]
+    s16 = m.forward_gnn(z_stack)
+    y = torch.from_numpy(np.repeat(range(5), 16))
+    return s16, m.loss_fn(s16, y)
+
+
+def make_5w20s(ref_gnn):
+    rec = _run_gnn(ref_gnn, 133, 96, 5, 16, 105, seed=2020)
+    for k in list(rec):
+        if k.startswith("g.") or k in ("dx64", "dx32"):
+            rec[k] = rec[k].astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "gnn_5w20s.npz"), **rec)
+
+
+def make_headgrads(ref_gnnnet, ref_backbone):
+    m, _, feat16 = _head_model(ref_gnnnet, ref_backbone)
+    stored = dict(np.load(os.path.join(HERE, "head_5w5s.npz")))
+    f32 = feat16.clone().requires_grad_(True)
+    s16, loss = _head_loss16(m, f32)
+    assert np.array_equal(s16.detach().numpy(), stored["scores16"]), "head model was not rebuilt identically"
+    loss.backward()
+    g32 = {k: v.grad.clone() for k, v in m.named_parameters() if k.startswith(("fc.", "gnn."))}
+    d32 = f32.grad.clone()
+    m.zero_grad()
+    m.support_label = m.support_label.double()
+    m.fc.double()
+    m.gnn.double()
+    f64 = feat16.double().requires_grad_(True)
+    _, loss64 = _head_loss16(m, f64)
+    loss64.backward()
+    rec = {"loss64": np.float64(loss64.item()), "dfeat": f64.grad.numpy().astype(np.float32)}
+    den = np.linalg.norm(f64.grad.numpy())
+    rec["e32.dfeat"] = np.float64(np.linalg.norm(d32.numpy() - f64.grad.numpy()) / den)
+    for k, v in m.named_parameters():
+        if not k.startswith(("fc.", "gnn.")):
+            continue
+        g64 = v.grad.numpy()
+        rec["g." + k] = g64.astype(np.float32)
+        den = np.linalg.norm(g64)
+        rec["e32." + k] = np.float64(np.linalg.norm(g32[k].numpy() - g64) / den if den > 0 else 0.0)
+    np.savez_compressed(os.path.join(HERE, "head_5w5s_grads.npz"), **rec)
+
+
 def main():
     ref_gnn, ref_gnnnet, ref_gnnnet_copy, ref_backbone = _import_reference()
     torch.set_num_threads(8)
+    groups = set(sys.argv[1:]) or {"base", "5w20s", "headgrads"}
+    if "5w20s" in groups:
+        make_5w20s(ref_gnn)
+    if "headgrads" in groups:
+        make_headgrads(ref_gnnnet, ref_backbone)
+    if "base" in groups:
+        make_base(ref_gnn, ref_gnnnet, ref_gnnnet_copy, ref_backbone)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
 
+
+def make_base(ref_gnn, ref_gnnnet, ref_gnnnet_copy, ref_backbone):
     rec = _run_gnn(ref_gnn, 13, 16, 3, 3, 7, seed=1234)
     np.savez_compressed(os.path.join(HERE, "gnn_tiny.npz"), **rec)
 
@@ -171,9 +248,6 @@ def main():
     s["y_query_5_16"] = np.repeat(range(5), 16)
     s["y_query_5_15"] = np.repeat(range(5), 15)
     np.savez_compressed(os.path.join(HERE, "sampler.npz"), **s)
-    for f in sorted(os.listdir(HERE)):
-        if f.endswith(".npz"):
-            print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
 if __name__ == "__main__":

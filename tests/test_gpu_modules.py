@@ -108,6 +108,35 @@ def test_gnn_head_matches_reference_scores(golden_dir, n_support, compress, fixt
     mft_b200.set_precision("auto")
 
 
+def test_gnn_head_gradients_match_reference(golden_dir):
+    """set_forward_loss + backward of GnnHead (fp32 path) against the gradients of the reference's GnnNet on
+    the same features and parameters (float64 run, tests/golden/head_5w5s_grads.npz): every fc.* / gnn.*
+    parameter and the features, within max(3 x the reference's own fp32 error, 3e-2) -- the fixture is not
+    kink-free, see tests/test_gpu_parity.py -- and the loss to 1e-5."""
+    import mft_b200
+    prm = dict(np.load(os.path.join(golden_dir, "head_5w5s.npz")))
+    gr = dict(np.load(os.path.join(golden_dir, "head_5w5s_grads.npz")))
+    mft_b200.set_precision("fp32")
+    for share in (True, False):
+        head = mft_b200.GnnHead(5, 5, share_support=share)
+        head.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in prm.items() if k.startswith("p.")})
+        head = head.cuda()
+        head.n_query = 16
+        feat = torch.from_numpy(prm["feat16"]).cuda().requires_grad_(True)
+        loss = head.set_forward_loss(feat)
+        loss.backward()
+        assert abs(float(loss.detach()) - float(gr["loss64"])) < 1e-5
+        assert U.rel(feat.grad.cpu().numpy(), gr["dfeat"]) < max(3 * float(gr["e32.dfeat"]), 3e-2)
+        for k, v in head.named_parameters():
+            want = gr["g." + k]
+            if np.abs(want).max() < 1e-9:
+                assert float(v.grad.abs().max()) <= 1e-6, k
+            else:
+                e = U.rel(v.grad.cpu().numpy(), want)
+                assert e < max(3 * float(gr["e32." + k]), 3e-2), (k, e, float(gr["e32." + k]))
+    mft_b200.set_precision("auto")
+
+
 def test_cuda_graph_replay_equals_eager():
     import mft_b200
     mft_b200.set_precision("tf32")

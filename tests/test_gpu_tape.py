@@ -11,11 +11,12 @@ and is, here -- is every kernel given the kernels' own upstream values ("teacher
 
   forward   layer k's tape H'_k, re-derived in float64 from the kernel's H'_{k-1} (BatchNorm from the
             tape's statistics, LeakyReLU, TF32 rounding, x W'^T, fp16 rounding), must equal the
-            kernel's H'_k up to fp16 rounding-boundary noise (rel-L2 <= 5e-4; a 0.1 % systematic
+            kernel's H'_k up to fp16 rounding-boundary noise (rel-L2 <= 2e-4, measured 1-3e-5; a 0.1 % systematic
             error fails); batch statistics <= 1e-5; adjacency <= 2e-5.
   backward  given the kernel's tape and adjacency the backward is a LINEAR map of the upstream gradient
             (no discontinuity left), so the float64 closed form (tests/kernel_model.py, with the
-            kernels' operand roundings) must match every gradient tensor to <= 2e-3 -- measured ~1e-4.
+            kernels' operand roundings) must match every gradient tensor to <= 2e-3 -- measured <= 3e-4 (dx, whose
+            dD is bf16), <= 1e-4 on every parameter gradient, median 2e-5 (profiles/r02/tf32_teacher_forced.txt).
             test_teacher_forced_check_is_sensitive proves that a 1 % error in the fused
             BatchNorm-backward term (DhInPlaceT / DhT in csrc/umma_layers.cu) would be caught.
 """
@@ -121,7 +122,7 @@ def _teacher_forced(p, x, d_adj, k_out, perturb=None):
         c = h.shape[1]
         s1 = (w[:, None] * h).sum(0)
         s2 = (w[:, None] * h * h).sum(0)
-        corr = pairs * (sk * sk - 1.0) * O.BN_EPS
+        corr = pairs * (sk * sk - 1.0) * float(np.float32(O.BN_EPS))     # the kernels hold eps as a float constant
         rep[f"sum{k}"] = U.rel(k_out["fsums"][k - 1, :c].numpy(), s1.numpy())
         rep[f"sumsq{k}"] = U.rel((k_out["fsums"][k - 1, c:2 * c] - corr).numpy(), s2.numpy())
         mean = s1 / pairs
@@ -189,7 +190,7 @@ def test_tf32_kernels_teacher_forced(bsz, n_way, n_support, fin, share):
     k_out = _run_kernels(p, x, d_adj, mask)
     rep, dx, g = _teacher_forced(p, x, d_adj, k_out)
     for k in (1, 2, 3, 4):
-        assert rep[f"H{k}"] < 5e-4, rep
+        assert rep[f"H{k}"] < 2e-4, rep
         assert rep[f"sum{k}"] < 1e-5 and rep[f"sumsq{k}"] < 1e-5, rep
     assert rep["adj"] < 2e-5, rep
     errs = _compare(k_out, dx, g, mask)
@@ -273,7 +274,7 @@ def test_tf32_kernels_teacher_forced_at_other_weight_scales(wscale):
     assert float(k_out["scales"][0]) != 1.0
     rep, dx, g = _teacher_forced(p, x, d_adj, k_out)
     for k in (1, 2, 3, 4):
-        assert rep[f"H{k}"] < 5e-4 and rep[f"sum{k}"] < 1e-5 and rep[f"sumsq{k}"] < 1e-5, rep
+        assert rep[f"H{k}"] < 2e-4 and rep[f"sum{k}"] < 1e-5 and rep[f"sumsq{k}"] < 1e-5, rep
     errs = _compare(k_out, dx, g, None)
     bad = {k: v for k, v in errs.items() if not v < 2e-3}
     assert not bad, (bad, errs)

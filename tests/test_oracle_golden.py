@@ -30,7 +30,8 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / (den if den > 0 else 1.0)
 
 
-@pytest.mark.parametrize("name,fin,nf,n_way", [("gnn_tiny.npz", 13, 16, 3), ("gnn_5w5s.npz", 133, 96, 5)])
+@pytest.mark.parametrize("name,fin,nf,n_way", [("gnn_tiny.npz", 13, 16, 3), ("gnn_5w5s.npz", 133, 96, 5),
+                                               ("gnn_5w20s.npz", 133, 96, 5)])
 def test_gnn_nl_forward_backward_fp64(golden_dir, name, fin, nf, n_way):
     rec = _load(golden_dir, name)
     p = _params(rec, torch.float64)
@@ -42,7 +43,7 @@ def test_gnn_nl_forward_backward_fp64(golden_dir, name, fin, nf, n_way):
     proj = torch.from_numpy(rec["proj"]).double()
     out, dx, grads = O.loss_and_grads(x, p, proj)
     assert _rel(out.numpy(), rec["out64"]) < 1e-10
-    assert _rel(dx.numpy(), rec["dx64"]) < 1e-7
+    assert _rel(dx.numpy(), rec["dx64"]) < (1e-7 if rec["dx64"].dtype == np.float64 else 2e-6)
     zero_grad = [n for n in names if (".conv2d_" in n and n.endswith("bias")) or
                  n in ("layer_l0.fc.bias", "layer_l1.fc.bias")]
     for n in names:
@@ -76,6 +77,58 @@ def test_head_scores_and_loss(golden_dir):
     loss = O.head_loss(torch.from_numpy(rec["feat16"]), p, 5, 5, 16)
     assert abs(loss.item() - float(rec["loss16"])) < 1e-5
     assert np.array_equal(O.query_labels(5, 16).numpy(), rec["y16"])
+
+
+def test_head_gradients(golden_dir):
+    """Gradients of the n_query = 16 loss w.r.t. every fc.* / gnn.* parameter and the features, against the
+    float64 run of the reference's GnnNet (tests/golden/make_golden.py headgrads)."""
+    rec = _load(golden_dir, "head_5w5s.npz")
+    gr = _load(golden_dir, "head_5w5s_grads.npz")
+    p = {k: v.requires_grad_(True) for k, v in _params(rec, torch.float64).items()}
+    feat = torch.from_numpy(rec["feat16"]).double().requires_grad_(True)
+    loss = O.head_loss(feat, p, 5, 5, 16)
+    assert abs(loss.item() - float(gr["loss64"])) < 1e-9
+    loss.backward()
+    assert _rel(feat.grad.numpy(), gr["dfeat"]) < 2e-6
+    for k, v in p.items():
+        g_ref = gr["g." + k]
+        if np.abs(g_ref).max() < 1e-9:          # analytically zero (conv biases under BN, fc.0.bias, ...)
+            assert np.abs(v.grad.numpy()).max() < 1e-9, k
+        else:
+            assert _rel(v.grad.numpy(), g_ref) < 2e-6, k
+
+
+def test_tf32_emulation_is_close_in_value_and_chaotic_in_gradient(golden_dir):
+    """The emulating mode (emulate="tf32": TF32 operands, fp16 tape, bf16 dD -- the tensor-core path's
+    rounding points) stays within 1e-3 of the reference's logits, but its GRADIENT is not a continuous
+    function at that resolution: evaluating the same emulation in float32 instead of float64 moves
+    ~1e-3 of the rounding decisions, each by one unit in the 11th bit, and the LeakyReLU kinks downstream
+    amplify that to percents of the parameter gradients.  This is the measured ground for the protocol of
+    tests/test_gpu_tape.py (sharp parity per kernel, teacher-forced) and for the yardstick tolerance of
+    the end-to-end gradient test in tests/test_gpu_parity.py."""
+    rec = _load(golden_dir, "gnn_5w5s.npz")
+    x, proj = torch.from_numpy(rec["x"]), torch.from_numpy(rec["proj"])
+    o64, _, g64 = O.loss_and_grads(x.double(), _params(rec, torch.float64), proj.double(), emulate="tf32")
+    o32, _, g32 = O.loss_and_grads(x, _params(rec, torch.float32), proj, emulate="tf32")
+    assert _rel(o64.numpy(), rec["out64"]) < 1e-3
+    assert _rel(o32.numpy(), o64.numpy()) < 1e-3
+    zero = tuple(f"conv2d_{k}.bias" for k in (1, 2, 3, 4, "last")) + ("layer_l0.fc.bias", "layer_l1.fc.bias")
+    worst = max(_rel(g32[k].numpy(), g64[k].numpy()) for k in g64 if not k.endswith(zero))
+    assert 2e-3 < worst < 0.15, worst          # measured 4e-2: far above fp32 resolution, hence the protocol
+    # the emulation changes values, not structure: analytically-zero gradients stay zero
+    for k in g64:
+        if ".conv2d_" in k and k.endswith("bias"):
+            assert float(g64[k].abs().max()) < 1e-12     # (conv2d_last.bias: softmax shift invariance, rounding noise)
+
+
+def test_tape_scale_rule():
+    """Power-of-two tape scales (csrc/umma_layers.cu umma_layer_scales_kernel, restated in tape_scale)."""
+    w = torch.full((4, 3), 0.07)
+    assert O.tape_scale(w) == 8.0                     # frexp(0.07) = 0.56 * 2^-3
+    assert O.tape_scale(w * 1e4) == 2.0 ** -10        # frexp(700) = 0.68 * 2^10
+    assert O.tape_scale(w, torch.ones(3), torch.zeros(3)) == 4.0      # gamma = 1 = 0.5 * 2^1
+    assert O.tape_scale(torch.zeros(2, 2)) == 1.0
+    assert O.tape_scale(w * 1e30) == 2.0 ** -60
 
 
 def test_head_compressed_50shot(golden_dir):

@@ -8,14 +8,18 @@ on the query nodes, and the full backward (input + all 64 parameter gradients).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--shape 5w5s|5w20s|5w50c] [--precision auto|fp32|tf32]
+                    [--mode train|eval] [--dp-bytes MB] [--no-share] [--no-graph]
 
 Multi-GPU: launched under torchrun, one rank per GPU; every rank runs its own episodes
-(weak scaling, episodes are independent) and the GNN gradients are averaged with one NCCL
-all-reduce per step (the episode-parallel meta-training path).
+(weak scaling, episodes are independent) and the gradients are averaged with one NCCL
+all-reduce per step (the episode-parallel meta-training path).  ``--dp-bytes 21.2``
+adds a flat buffer standing for the backbone + fc gradients (5 307 706 floats in total with the GNN's)
+to that all-reduce.  ``--mode eval``: the episode-sharded evaluation path (finetune.py:634-682): 600
+forward-only episodes of B=15 graphs, episode e on rank e % G, one gather of the accuracies at the end.
 
-``--impl reference`` times the CPU restatement of the reference (oracle/gnn_oracle.py --
-the reference is Python/PyTorch and /root/reference does not exist on the GPU box) on the
-host cores, same workload, same metric.
+``--impl reference`` times the reference's OWN head code (oracle/_ref: methods/gnn.py + gnnnet.py taken
+verbatim from the reference by oracle/make_ref.py; the CPU port oracle/gnn_oracle.py when that is absent)
+on the host cores, same workload, same metric.
 """
 from __future__ import annotations
 
@@ -40,6 +44,8 @@ SHAPES = {
     "5w50c": (5, 50, 16, True),
 }
 NF = 96
+METRIC = "gnn_head_episodes_per_sec_fwd_bwd"
+BACKBONE_FC_FLOATS = 4905792 + 65920      # ResNet10 + fc of GnnNet; the GNN adds 335 994
 
 
 def head_flops(bsz, n, backward=True):
@@ -49,28 +55,38 @@ def head_flops(bsz, n, backward=True):
 
 def gemm_traffic(shape, share, prec):
     """DRAM bytes per edge-MLP GEMM launch from the committed `ncu` capture of this workload
-    (profiles/r01_gemm_traffic.json, written by tools/ncu_traffic.py), or None."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_traffic.json")
-    try:
-        rec = json.load(open(path))
-    except (OSError, ValueError):
-        return None
-    same = rec.get("config") == {"shape": shape, "share_support": bool(share), "precision": prec}
-    return rec.get("bytes_per_launch") if same else None   # the capture describes ONE configuration
+    (profiles/r02_gemm_traffic.json, else round 1's; written by tools/ncu_traffic.py), or None."""
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            rec = json.load(open(path))
+        except (OSError, ValueError):
+            continue
+        if rec.get("config") == {"shape": shape, "share_support": bool(share), "precision": prec}:
+            return rec.get("bytes_per_launch")   # the capture describes ONE configuration
+    return None
 
 
-def shape_dims(shape):
-    n_way, n_shot, n_query, compress = SHAPES[shape]
+def shape_dims(shape, n_query=None):
+    n_way, n_shot, nq, compress = SHAPES[shape]
     k = round(n_shot / 2) if compress else n_shot
-    return n_way, n_shot, n_query, compress, n_way * (k + 1)
+    return n_way, n_shot, (n_query or nq), compress, n_way * (k + 1)
 
 
-def synthetic_features(shape, seed, device="cpu"):
+def workload(shape, n_query=None, backward=True):
+    """ONE sentence for both arms (the driver compares the arms' config)."""
+    n_way, n_shot, nq, compress, n = shape_dims(shape, n_query)
+    what = "fwd+bwd" if backward else "fwd"
+    tail = "CE on the query nodes; input + 64 parameter gradients" if backward else "scores of the query nodes"
+    return (f"GnnNet head {what}, {shape}: GNN_nl on B={nq} graphs x N={n} nodes, F=133, nf=96, n_way={n_way}; " + tail)
+
+
+def synthetic_features(shape, seed, device="cpu", n_query=None):
     """Backbone features of one episode: [n_way, n_shot+n_query, 512] ~ N(0,1) (synthetic; the
     ResNet10 backbone is outside the hot path and stays on cuDNN)."""
-    n_way, n_shot, n_query, _, _ = shape_dims(shape)
+    n_way, n_shot, nq, _, _ = shape_dims(shape, n_query)
     g = torch.Generator().manual_seed(seed)
-    return torch.randn(n_way, n_shot + n_query, 512, generator=g).to(device)
+    return torch.randn(n_way, n_shot + nq, 512, generator=g).to(device)
 
 
 def measured_peaks():
@@ -83,8 +99,46 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def measure_tf32_peak(seconds=2.0, n=8192):
+    """Dense TF32 matmul peak of THIS GPU, measured the way MEASURED_PEAKS.json measured bf16 (SURVEY.md 8d:
+    "measure with a TF32 8192^3 matmul"): torch.matmul on fp32 inputs with allow_tf32 (cuBLAS), best of 10
+    (burst) and back to back for `seconds` (sustained)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device="cuda")
+        b = torch.randn(n, n, device="cuda")
+        c = torch.empty(n, n, device="cuda")
+        fl = 2.0 * n ** 3
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters, t0 = 0, time.perf_counter()
+        e0.record()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(20):
+                torch.matmul(a, b, out=c)
+            iters += 20
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        return {"burst": fl / (best * 1e-3) / 1e12, "sustained": fl * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the run (started before the warm-up so that short
+    timed regions still see samples; stopped after the end-to-end region)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -96,7 +150,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -110,53 +164,122 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        rows, reasons = [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                rows.append((float(f[1]), float(f[2]), float(f[3])))
             except ValueError:
                 continue
             for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        pmax = max(r[2] for r in rows)
+        load = [r for r in rows if r[2] >= 0.6 * pmax] or rows     # samples taken while the GPU was working
+        return {"sm_mhz": statistics.median(r[0] for r in load), "sm_max_mhz": max(r[1] for r in rows),
+                "reasons": sorted(reasons), "samples": len(rows), "samples_under_load": len(load),
+                "power_w_max": pmax}
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm: CPU restatement of the reference on the host cores
+# the reference's own head code on the CPU (oracle/_ref), or the port when it is absent
 # ------------------------------------------------------------------------------------------
 
-def cpu_reference_episode_seconds(shape, steps, warmup, threads):
-    """fwd + bwd of the head on CPU (oracle port of methods/gnn.py + gnnnet.py glue)."""
-    from oracle import gnn_oracle as O
+class ReferenceHead:
+    """fc -> graphs -> forward_gnn -> CE of the reference's GnnNet / gnnnet_copy.GnnNet on features, driven
+    through the reference's own modules (the few glue lines of gnnnet.py:79-83 / gnnnet_copy.py:67-72 are
+    restated because set_forward(is_feature=True) hard-codes 15 queries, gnnnet.py:73)."""
+
+    def __init__(self, shape, device="cpu", variant="reference"):
+        from oracle import ref_loader as R
+        self.ns = R.load(variant)
+        n_way, n_shot, n_query, compress, n = shape_dims(shape)
+        mod = self.ns.gnnnet_copy if compress else self.ns.gnnnet
+        torch.manual_seed(0)
+        self.m = mod.GnnNet(self.ns.backbone.ResNet10, n_way, n_shot)
+        self.m.n_query = n_query
+        self.compress = compress
+        self.n_shot = n_shot
+        self.device = torch.device(device)
+        self.m.fc.to(self.device)
+        self.m.gnn.to(self.device)
+        self.m.support_label = self.m.support_label.to(self.device)
+        self.y = torch.from_numpy(np.repeat(range(n_way), n_query)).to(self.device)
+        self.params = list(self.m.fc.parameters()) + list(self.m.gnn.parameters())
+
+    def loss(self, feat):
+        m = self.m
+        z = m.fc(feat.reshape(-1, feat.size(-1)))
+        z = z.view(m.n_way, -1, z.size(1))
+        ns = m.n_support                                  # already halved by gnnnet_copy (:34)
+        if self.compress:
+            sup = z[:, :2 * ns].reshape(m.n_way, 2, ns, -1).mean(dim=1)
+            q0 = 2 * ns
+        else:
+            sup, q0 = z[:, :ns], ns
+        zs = [torch.cat([sup, z[:, q0 + i:q0 + i + 1]], dim=1).reshape(1, -1, z.size(2)) for i in range(m.n_query)]
+        return m.loss_fn(m.forward_gnn(zs), self.y)
+
+    def step(self, feat):
+        for p in self.params:
+            p.grad = None
+        loss = self.loss(feat)
+        loss.backward()
+        return loss
+
+
+def cpu_reference_episode_seconds(shape, steps, warmup, threads, budget_s=200.0):
+    """(kind, [seconds per episode]) of fwd + bwd of the head on the host cores."""
     torch.set_num_threads(threads)
-    n_way, n_shot, n_query, compress, n = shape_dims(shape)
-    p = O.random_params(128 + n_way, NF, n_way, seed=0, dtype=torch.float32, perturb_bn=False)
-    params = {("gnn." + k): v.requires_grad_(True) for k, v in p.items()}
-    g = torch.Generator().manual_seed(1)
-    params["fc.0.weight"] = ((torch.rand(128, 512, generator=g) * 2 - 1) / 512 ** 0.5).requires_grad_(True)
-    params["fc.0.bias"] = torch.zeros(128, requires_grad=True)
-    params["fc.1.weight"] = torch.ones(128, requires_grad=True)
-    params["fc.1.bias"] = torch.zeros(128, requires_grad=True)
-    times = []
+    kind = "port"
+    try:
+        from oracle import ref_loader as R
+        if R.available():
+            head = ReferenceHead(shape, "cpu")
+            kind = "reference"
+    except Exception as e:                                   # noqa: BLE001
+        print(f"bench.py: oracle/_ref unusable ({e}); timing the CPU port instead", file=sys.stderr)
+        kind = "port"
+    if kind == "port":
+        from oracle import gnn_oracle as O
+        n_way, n_shot, n_query, compress, n = shape_dims(shape)
+        p = O.random_params(128 + n_way, NF, n_way, seed=0, dtype=torch.float32, perturb_bn=False)
+        params = {("gnn." + k): v.requires_grad_(True) for k, v in p.items()}
+        g = torch.Generator().manual_seed(1)
+        params["fc.0.weight"] = ((torch.rand(128, 512, generator=g) * 2 - 1) / 512 ** 0.5).requires_grad_(True)
+        params["fc.0.bias"] = torch.zeros(128, requires_grad=True)
+        params["fc.1.weight"] = torch.ones(128, requires_grad=True)
+        params["fc.1.bias"] = torch.zeros(128, requires_grad=True)
+    times, t_start = [], time.perf_counter()
     for it in range(warmup + steps):
         feat = synthetic_features(shape, 100 + it)
-        for v in params.values():
-            v.grad = None
         t0 = time.perf_counter()
-        loss = O.head_loss(feat, params, n_way, n_shot, n_query, compress)
-        loss.backward()
+        if kind == "reference":
+            head.step(feat)
+        else:
+            for v in params.values():
+                v.grad = None
+            O.head_loss(feat, params, n_way, n_shot, n_query, compress).backward()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return times
+        if time.perf_counter() - t_start > budget_s and times:     # bounded: never more than a few minutes
+            break
+    return kind, times
+
+
+def cpu_baseline_record(kind, times, threads, warmup):
+    sec = sum(times) / len(times)
+    what = ("oracle/_ref: the reference's own methods/gnn.py + gnnnet.py head code (verbatim copies made by "
+            "oracle/make_ref.py)") if kind == "reference" else "oracle/gnn_oracle.py (port of methods/gnn.py + gnnnet.py head)"
+    return {"value": 1.0 / sec, "unit": "episodes/s", "cores": threads, "kind": kind,
+            "sample": f"{len(times)} whole episodes of the same workload after {warmup} warm-up "
+                      f"({sec:.2f} s each), torch CPU fp32, {what}"}
 
 
 def run_reference(args):
@@ -164,22 +287,16 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    # bounded sample: whole episodes of the same workload, few enough to end within minutes
-    steps = max(1, min(args.steps, 3 if args.shape != "5w5s" else 20))
-    warmup = 1
-    times = cpu_reference_episode_seconds(args.shape, steps, warmup, threads)
+    kind, times = cpu_reference_episode_seconds(args.shape, args.steps, args.warmup, threads)
     sec = sum(times) / len(times)
-    n_way, n_shot, n_query, compress, n = shape_dims(args.shape)
     val = 1.0 / sec
     line = {
-        "impl": "reference", "metric": "gnn_head_episodes_per_sec_fwd_bwd", "value": val, "unit": "episodes/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"GnnNet head fwd+bwd, {args.shape} (B={n_query} graphs, N={n} nodes, F=133, nf=96), "
-                               f"features->fc->graphs->GNN_nl->CE->backward", "shape": args.shape},
-        "cpu_baseline": {"value": val, "unit": "episodes/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} whole episodes after {warmup} warm-up, torch CPU fp32, "
-                                   f"oracle/gnn_oracle.py (port of methods/gnn.py + gnnnet.py head)"},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "episodes/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload(args.shape), "shape": args.shape,
+                   "arm": "host CPU, all cores; features -> fc -> graphs -> GNN_nl -> CE -> backward"},
+        "cpu_baseline": cpu_baseline_record(kind, times, threads, args.warmup),
         "e2e": {"value": val, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -188,8 +305,112 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+# the reference's head run with torch eager on the SAME GPU (cuDNN / cuBLAS): the unfused-GPU yardstick
+# ------------------------------------------------------------------------------------------
+
+def gpu_eager_reference(shape, dev, steps=10, warmup=3):
+    from oracle import ref_loader as R
+    if not R.available():
+        return None
+    out = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    try:
+        for label, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            head = ReferenceHead(shape, dev)
+            feats = [synthetic_features(shape, 300 + i, dev) for i in range(warmup + steps)]
+            for i in range(warmup):
+                head.step(feats[i])
+            torch.cuda.synchronize()
+            ms = 0.0
+            for i in range(steps):
+                flush.fill_(i & 0xff)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                head.step(feats[warmup + i])
+                e1.record()
+                torch.cuda.synchronize()
+                ms += e0.elapsed_time(e1)
+            out[label] = {"episodes_per_s": steps / (ms / 1e3), "ms_per_step": ms / steps}
+            del head
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["what"] = ("the reference's own head (oracle/_ref: fc -> graphs -> methods/gnn.py GNN_nl -> CE -> backward) with "
+                   "torch eager on this GPU: cuDNN 1x1 convs + cuBLAS, allow_tf32 off / on; same features, L2 flushed "
+                   f"between steps, {steps} steps after {warmup} warm-up, CUDA events")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+
+def run_eval(args, world, rank, dev, lib, mft_b200):
+    """Episode-sharded evaluation (finetune.py:634-682, configs C2/C5): forward only, B=15 graphs."""
+    import torch.distributed as dist
+    from mft_b200 import parallel
+    n_episodes = args.episodes
+    n_way, n_shot, n_query, compress, n = shape_dims(args.shape, 15)
+    torch.manual_seed(0)
+    head = mft_b200.GnnHead(n_way, n_shot, compress=compress, share_support=not args.no_share).to(dev)
+    head.n_query = n_query
+    parallel.broadcast_parameters(head)
+    y = mft_b200.query_labels(n_way, n_query).to(dev)
+    mine = parallel.owned_episodes(n_episodes, rank, world)
+    feats = [synthetic_features(args.shape, 10 + e, "cpu", n_query).pin_memory() for e in mine[:64]]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def episode(f):
+        with torch.no_grad():
+            scores = head.set_forward(f.to(dev, non_blocking=True))
+            return (scores.argmax(1) == y).float().mean()
+
+    for i in range(max(args.warmup, 3)):
+        episode(feats[i % len(feats)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    l0 = lib.mft_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    accs = []
+    for i, _ in enumerate(mine):
+        if i % 8 == 0:
+            flush.fill_(i & 0xff)
+        accs.append(episode(feats[i % len(feats)]))
+    acc_local = torch.stack(accs).double().cpu().tolist() if accs else []
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.mft_launch_count() - l0
+    clocks = sampler.stop()
+    acc_all = parallel.gather_episode_results(acc_local, n_episodes, rank, world, device=dev)
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+    if rank == 0:
+        mean, ci = parallel.accuracy_summary(acc_all.cpu())
+        emit_json({
+            "metric": "gnn_head_eval_episodes_per_sec_fwd", "value": n_episodes / (float(t[0]) / 1e3),
+            "unit": "episodes/s", "n_gpus": world, "steps": n_episodes, "warmup": max(args.warmup, 3),
+            "ms_per_step": float(t[0]) / max(1, len(mine)), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": workload(args.shape, 15, backward=False), "shape": args.shape,
+                       "episodes": n_episodes, "parallelism": f"episode-sharded eval, episode e on rank e % {world}, "
+                       "no data-path collective; one all-reduce gather of the accuracies at the end",
+                       "l2": "256 MiB fill every 8 episodes", "timing": "CUDA events around the rank's share, "
+                       "host features -> H2D -> fc -> graphs -> GNN_nl -> argmax, accuracies read back once; max over ranks"},
+            "clocks": clocks, "gpu_launches": int(t[1]),
+            "accuracy": {"mean": mean, "ci95": ci, "note": "synthetic features, random-init weights: chance level"},
+        })
+    return 0
+
 
 def run_ours(args):
     import torch.distributed as dist
@@ -208,6 +429,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load_library()
     mft_b200.set_precision(args.precision)
+    if args.mode == "eval":
+        rc = run_eval(args, world, rank, dev, lib, mft_b200)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return rc
 
     n_way, n_shot, n_query, compress, n = shape_dims(args.shape)
     torch.manual_seed(0)
@@ -215,9 +442,22 @@ def run_ours(args):
     head.n_query = n_query
     parallel.broadcast_parameters(head)
     gnn_params = list(head.gnn.parameters())
-    y = mft_b200.query_labels(n_way, n_query).to(dev)
     from mft_b200.gnn import _resolve_precision
     prec = "tf32" if _resolve_precision([133, 181, 229], NF) == _lib.PREC_TF32 else "fp32"
+    # data-parallel payload: the GNN gradients (and, end to end, the fc's) are the head's own; --dp-bytes adds
+    # a flat buffer that stands for the rest of the model's gradients (backbone: outside the head)
+    extra = None
+    if world > 1 and args.dp_bytes > 0:
+        extra_floats = max(0, int(args.dp_bytes * 1e6 / 4) - sum(p.numel() for p in gnn_params))
+        extra = torch.zeros(extra_floats, dtype=torch.float32, device=dev)
+
+    def allreduce(params):
+        parallel.allreduce_mean_grads(params, world)
+        if extra is not None:
+            dist.all_reduce(extra, op=dist.ReduceOp.AVG)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
 
     # Episode inputs.  Kernel-resident arm: the node tensors of every step already sit in HBM.
     total = args.warmup + args.steps
@@ -248,12 +488,9 @@ def run_ours(args):
         gstep = mft_b200.GraphedStep(fwd_bwd, [nodes_dev[0]], gnn_params)
 
     def step(nodes):
-        if use_graph:
-            loss = gstep(nodes)
-        else:
-            loss = eager_step(nodes)
+        loss = gstep(nodes) if use_graph else eager_step(nodes)
         if world > 1:
-            parallel.allreduce_mean_grads(gnn_params, world)
+            allreduce(gnn_params)
         return loss
 
     def barrier():
@@ -266,8 +503,6 @@ def run_ours(args):
     for it in range(args.warmup):
         step(nodes_dev[it])
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = lib.mft_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
@@ -279,7 +514,6 @@ def run_ours(args):
     launches = lib.mft_launch_count() - launches0
     if use_graph:
         launches = launches_per_step * args.steps
-    clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(ms)
 
@@ -328,7 +562,7 @@ def run_ours(args):
             loss.backward()
             consumed_ev[k & 1].record()
         if world > 1:
-            parallel.allreduce_mean_grads(all_params, world)
+            allreduce(all_params)
         slot = k & 1
         if k >= 2:                                # the copy issued two steps ago into this slot has landed?
             loss_ev[slot].synchronize()
@@ -358,6 +592,7 @@ def run_ours(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     assert len(losses) == args.steps and all(l == l for l in losses), "end-to-end arm lost a loss value"
+    clocks = sampler.stop()
 
     # ---- per-category device time of the library's kernels (same steps, events around each launch).
     # Every rank runs the steps (they contain the gradient all-reduce); only rank 0 records.
@@ -368,7 +603,7 @@ def run_ours(args):
     for k in range(nprof):
         eager_step(nodes_dev[args.warmup + k])
         if world > 1:
-            parallel.allreduce_mean_grads(gnn_params, world)
+            allreduce(gnn_params)
     if rank == 0:
         raw = _lib.profile_collect()
         lib.mft_prof_enable(0)
@@ -380,9 +615,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
+    if world > 1:                               # the other ranks are done: rank 0 alone measures peaks below
+        dist.barrier()
+        dist.destroy_process_group()
 
     if rank == 0:
         peaks = measured_peaks()
+        tf32 = measure_tf32_peak()
         ms_per_step = total_ms / args.steps
         eps = world * args.steps / (total_ms / 1e3)
         e2e_eps = world * args.steps / (e2e_ms / 1e3)
@@ -391,7 +630,6 @@ def run_ours(args):
         gemm_ms = sum(v[0] for k, v in prof.items() if k.startswith(("fwd_gemm", "dgrad", "wgrad")))
         gemm_n = sum(v[1] for k, v in prof.items() if k.startswith(("fwd_gemm", "dgrad", "wgrad")))
         lib_ms = sum(v[0] for v in prof.values())
-        tf32_peak = peaks["bf16_sustained"] / 2.0
         achieved = alg / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         rows_exec = n_query * n * (n + 1) // 2           # unordered pairs of every graph
         n_sup = n - n_way                                 # support nodes: the same rows in every graph
@@ -399,19 +637,22 @@ def run_ours(args):
                                                    + n_query * (n * (n + 1) // 2 - n_sup * (n_sup + 1) // 2))
         pair_fl = [2 * (f * 192 + 192 * 192 + 192 * 96 + 96 * 96 + 96) for f in (133, 181, 229)]
         executed = 3.0 * (pair_fl[0] * rows_w0 + (pair_fl[1] + pair_fl[2]) * rows_exec)
+        dp_floats = sum(p.numel() for p in gnn_params) + (extra.numel() if extra is not None else 0)
         line = {
-            "metric": "gnn_head_episodes_per_sec_fwd_bwd", "value": eps, "unit": "episodes/s",
+            "metric": METRIC, "value": eps, "unit": "episodes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32" if prec == "tf32" else "f32", "data": "synthetic",
             "config": {
-                "workload": f"GnnNet head fwd+bwd, {args.shape}: GNN_nl on B={n_query} graphs x N={n} nodes, F=133, "
-                            f"nf=96, n_way={n_way}; CE on the query nodes; input + 64 parameter gradients",
-                "shape": args.shape, "precision": prec,
+                "workload": workload(args.shape), "shape": args.shape,
+                "arm": "B200: device-resident nodes -> GNN_nl -> CE -> backward (value); host features -> ... (e2e)",
+                "precision": prec,
                 "share_support": (not args.no_share),
                 "rows_layer_w0": rows_w0, "rows_other_layers": rows_exec,
-                "tape": "fp16 pre-BN activations, fp32 gradients (tensor-core path)" if prec == "tf32" else "fp32",
-                "parallelism": f"episode-dp{world}" + (" + nccl allreduce(gnn grads, 1.34 MB)" if world > 1 else ""),
+                "tape": ("fp16 pre-BN activations with per-layer power-of-two scales, fp32 gradients (tensor-core path)"
+                         if prec == "tf32" else "fp32"),
+                "parallelism": f"episode-dp{world}" + (f" + nccl allreduce(avg) of {dp_floats} fp32 gradients "
+                                                       f"({dp_floats * 4 / 1e6:.2f} MB) per step" if world > 1 else ""),
                 "l2": "256 MiB fill between timed steps (L2 flushed); activation tape per step is 620 MB > L2",
                 "timing": "CUDA events per step on torch's current stream, summed over K steps, max over ranks",
                 "launch": "CUDA graph replay of fwd+bwd (captured once)" if use_graph else "eager launches",
@@ -425,34 +666,42 @@ def run_ours(args):
                             "step later, so the queue never drains)"},
             "gpu_launches": int(launches),
             "roofline": {
-                "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": (achieved / tf32_peak) if achieved else None, "traffic": gemm_traffic(args.shape, not args.no_share, prec),
+                "bound": "tensor", "achieved": achieved, "peak": tf32["burst"], "unit": "TFLOP/s",
+                "frac": (achieved / tf32["burst"]) if achieved else None,
+                "traffic": gemm_traffic(args.shape, not args.no_share, prec),
                 "kernel": "edge-MLP GEMM launches (4 fwd + 4 dgrad + 4 wgrad per Wcompute, x3)",
                 "launches_per_step": gemm_n, "avg_launch_ms": (gemm_ms / gemm_n) if gemm_n else None,
                 "algorithmic_flops_per_step": alg,
                 "executed_flops_per_step": executed,
-                "peak_source": f"{peaks['source']}: bf16 sustained {peaks['bf16_sustained']} TF/s / 2 (dense TF32 "
-                               f"is half the bf16 rate; no TF32 figure is driver-measured)",
-                "note": "achieved counts the reference's dense B*N^2 pair FLOPs; the kernels execute the "
-                        "N(N+1)/2 unordered pairs only and (share_support) the support-support pairs of "
-                        "layer_w0 once for all graphs (executed_flops_per_step)",
+                "executed_tflops": (executed / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else None,
+                "frac_executed": (executed / (gemm_ms / 1e3) / 1e12 / tf32["burst"]) if gemm_ms > 0 else None,
+                "achieved_on_step": alg / (ms_per_step / 1e3) / 1e12,
+                "frac_on_step": alg / (ms_per_step / 1e3) / 1e12 / tf32["burst"],
+                "peak_sustained": tf32["sustained"],
+                "peak_source": f"measured in this run: torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS), best of 10 = "
+                               f"{tf32['burst']:.1f} TF/s (burst: the GEMM launches are event-timed one by one), 2 s back to "
+                               f"back = {tf32['sustained']:.1f} TF/s; {peaks['source']} has bf16 {peaks['bf16_burst']} / "
+                               f"{peaks['bf16_sustained']} TF/s (half of it would be {peaks['bf16_burst'] / 2:.0f})",
+                "note": "achieved counts the reference's dense B*N^2 pair FLOPs over the summed device time of the GEMM "
+                        "launches (CUDA events around every launch, eager run of the same steps); the kernels execute "
+                        "the N(N+1)/2 unordered pairs only and (share_support) the support-support pairs of layer_w0 once "
+                        "for all graphs (executed_*); *_on_step divide by the whole graph-replayed step instead",
             },
             "head_tflops_algorithmic": alg * eps / world / 1e12,
             "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "library_kernel_ms_per_step": lib_ms,
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if world == 1 and not args.no_gpu_reference:
+            try:
+                line["gpu_eager_reference"] = gpu_eager_reference(args.shape, dev)
+            except Exception as e:                       # noqa: BLE001  (a yardstick, never fatal)
+                line["gpu_eager_reference"] = {"error": str(e)[:200]}
+        if world == 1 and not args.no_cpu_baseline:      # contract: rank 0 at N = 1 only
             threads = os.cpu_count() or 1
-            n_s = 2 if args.shape != "5w5s" else 10
-            tms = cpu_reference_episode_seconds(args.shape, n_s, 1, threads)
-            sec = sum(tms) / len(tms)
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "episodes/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n_s} whole episodes of the same workload after 1 warm-up "
-                                              f"({sec:.2f} s each), torch CPU fp32, oracle/gnn_oracle.py"}
+            n_s = 3 if args.shape != "5w5s" else 10
+            kind, tms = cpu_reference_episode_seconds(args.shape, n_s, 1, threads, budget_s=60.0)
+            line["cpu_baseline"] = cpu_baseline_record(kind, tms, threads, 1)
         emit_json(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     return 0
 
 
@@ -498,7 +747,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="5w20s", choices=sorted(SHAPES))
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32"])
+    ap.add_argument("--mode", default="train", choices=["train", "eval"])
+    ap.add_argument("--episodes", type=int, default=600, help="--mode eval: episodes of the sweep (finetune.py: 600)")
+    ap.add_argument("--dp-bytes", type=float, default=0.0,
+                    help="MB of fp32 gradients all-reduced per step at N > 1 (default: the GNN's own 1.34 MB; 21.2 = "
+                         "GNN + fc + ResNet10, SURVEY.md 8e)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-share", action="store_true",
                     help="evaluate the support-support pairs of layer_w0 in every graph (GnnHead(share_support=False))")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")

@@ -143,27 +143,44 @@ __device__ __forceinline__ int frexp_exponent(float v) {
     return max(-60, min(60, e));
 }
 
-__global__ void __launch_bounds__(256) umma_layer_scales_kernel(ScaleJobs j) {   // grid = 4: one CTA per conv layer
-    __shared__ float red[2][8];
+__global__ void __launch_bounds__(1024) umma_layer_scales_kernel(ScaleJobs j) {   // grid = 4: one CTA per conv layer
+    __shared__ float red[2][32];
     const int k = blockIdx.x, t = threadIdx.x;
-    float mw = 0.f, ma = 0.f;
-    for (int i = t; i < j.wn[k]; i += blockDim.x) mw = fmaxf(mw, fabsf(__ldg(j.W[k] + i)));
+    // max |W_k|: a latency-bound sweep of <= 45k floats -- 1024 threads, four independent 16-byte loads each
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, ma = 0.f;
+    const float* W = j.W[k];
+    const int n = j.wn[k];
+    if ((reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+        const float4* W4 = reinterpret_cast<const float4*>(W);
+        const int n4 = n >> 2;
+        auto amax4 = [](float4 v) { return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))); };
+        int i = t;
+        for (; i + 3 * 1024 < n4; i += 4 * 1024) {
+            const float4 a = __ldg(W4 + i), b = __ldg(W4 + i + 1024), c = __ldg(W4 + i + 2048), d = __ldg(W4 + i + 3072);
+            m0 = fmaxf(m0, amax4(a)); m1 = fmaxf(m1, amax4(b)); m2 = fmaxf(m2, amax4(c)); m3 = fmaxf(m3, amax4(d));
+        }
+        for (; i < n4; i += 1024) m0 = fmaxf(m0, amax4(__ldg(W4 + i)));
+        for (int q = (n4 << 2) + t; q < n; q += 1024) m1 = fmaxf(m1, fabsf(__ldg(W + q)));
+    } else {
+        for (int i = t; i < n; i += 1024) m0 = fmaxf(m0, fabsf(__ldg(W + i)));
+    }
+    float mw = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     if (j.g[k])
-        for (int c = t; c < j.gc[k]; c += blockDim.x) ma = fmaxf(ma, fmaxf(fabsf(__ldg(j.g[k] + c)), fabsf(__ldg(j.b[k] + c))));
+        for (int c = t; c < j.gc[k]; c += 1024) ma = fmaxf(ma, fmaxf(fabsf(__ldg(j.g[k] + c)), fabsf(__ldg(j.b[k] + c))));
     mw = warp_max(mw);
     ma = warp_max(ma);
     if ((t & 31) == 0) { red[0][t >> 5] = mw; red[1][t >> 5] = ma; }
     __syncthreads();
     mw = red[0][0]; ma = red[1][0];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) { mw = fmaxf(mw, red[0][q]); ma = fmaxf(ma, red[1][q]); }
+    for (int q = 1; q < 32; ++q) { mw = fmaxf(mw, red[0][q]); ma = fmaxf(ma, red[1][q]); }
     int e = frexp_exponent(mw) + (j.g[k] ? frexp_exponent(ma) : 0);
     e = max(-60, min(60, e));
     const float sc = ldexpf(1.f, -e);
     if (t == 0) j.tscale[k] = sc;
     const double corr = j.count * ((double)sc * (double)sc - 1.0) * (double)kBnEps;
     double* slot = j.fsums + (size_t)k * kStatSlot;              // copy 0, second moments
-    for (int c = t; c < j.C[k]; c += blockDim.x) slot[j.C[k] + c] = corr;
+    for (int c = t; c < j.C[k]; c += 1024) slot[j.C[k] + c] = corr;
 }
 
 // ------------------------------------------------------------------ producer functors
@@ -1883,7 +1900,7 @@ int wcompute_fwd_prepare_tf32(const mft_wcompute_params* p, const WcLayout& L, i
         sj.fsums = L.fsums;
         sj.count = count;
         ProfScope ps(PC_PREP, st);
-        umma_layer_scales_kernel<<<4, 256, 0, st>>>(sj);          // after the memset of the slots on `st`
+        umma_layer_scales_kernel<<<4, 1024, 0, st>>>(sj);          // after the memset of the slots on `st`
         MFT_CHECK_LAUNCH();
     }
     return build_images(p, L.wimg, L.tscale, F, nf, false, st);

@@ -90,6 +90,7 @@ class _HeadFn(torch.autograd.Function):
         return nodes
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, d_nodes):
         lib = _lib.load_library()
         feat, saved, *params = ctx.saved_tensors
@@ -130,6 +131,7 @@ class _QueryCEFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         (d_out,) = ctx.saved_tensors
         return d_out * g, None, None, None
@@ -182,9 +184,14 @@ class GnnHead(nn.Module):
         supports then the one query)."""
         return ([True] * self.n_support + [False]) * self.n_way
 
+    def _set_sharing(self) -> None:
+        # the head knows which nodes its graphs share: an explicit promise, no detection (GNN_nl.auto_share)
+        self.gnn.shared_nodes = self.shared_mask() if self.share_support else None
+        self.gnn.auto_share = False
+
     def forward_gnn_nodes(self, nodes: torch.Tensor) -> torch.Tensor:
         """``nodes`` must come from ``self.nodes`` / ``build_graphs`` (supports replicated)."""
-        self.gnn.shared_nodes = self.shared_mask() if self.share_support else None
+        self._set_sharing()
         return select_scores(self.gnn(nodes), self.n_way, self.n_support, self.n_query)
 
     def set_forward(self, feat: torch.Tensor) -> torch.Tensor:
@@ -200,7 +207,7 @@ class GnnHead(nn.Module):
     def loss_from_nodes(self, nodes: torch.Tensor) -> torch.Tensor:
         """Cross-entropy of the query nodes of graphs made by ``self.nodes`` (gnnnet.py:210-224)."""
         if self.fused_loss and nodes.is_cuda and type(self.loss_fn) is nn.CrossEntropyLoss:
-            self.gnn.shared_nodes = self.shared_mask() if self.share_support else None
+            self._set_sharing()
             return _QueryCEFn.apply(self.gnn(nodes), self.n_way, self.n_support, self.n_query)
         return self.loss_fn(self.forward_gnn_nodes(nodes), self._labels(nodes.device))
 

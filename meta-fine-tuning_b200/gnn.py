@@ -79,6 +79,22 @@ def _eff(p: torch.Tensor) -> torch.Tensor:
     return p if fast is None else fast
 
 
+def _require_identity(W_id: torch.Tensor, what: str) -> None:
+    """The kernels hard-wire what GNN_nl always passes (gnn.py:155): operator 0 / the -1e8 mask is the
+    identity.  The reference API would accept any W_id, so anything else is refused loudly instead of being
+    silently ignored.  One comparison + host read per call of the STANDALONE modules (GNN_nl's fused path
+    never materialises W_id); skipped under CUDA-graph capture; MFT_CHECK_IDENTITY=0 switches it off."""
+    if os.environ.get("MFT_CHECK_IDENTITY", "1") == "0" or not W_id.is_cuda:
+        return
+    if torch.cuda.is_current_stream_capturing():
+        return
+    n = W_id.size(1)
+    eye = torch.eye(n, device=W_id.device, dtype=W_id.dtype).view(1, n, n, 1)
+    if W_id.dim() != 4 or W_id.size(2) != n or not bool((W_id == eye).all()):
+        raise RuntimeError(f"{what} is not the identity operator; only the identity (what GNN_nl builds, "
+                           f"gnn.py:155) is implemented")
+
+
 def _blob(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -184,6 +200,7 @@ class _WcomputeFn(torch.autograd.Function):
         return adj
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, d_adj):
         lib = _lib.load_library()
         x, adj, saved, *params = ctx.saved_tensors
@@ -231,6 +248,7 @@ class _GconvFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, d_out):
         lib = _lib.load_library()
         adj, x, saved, *params = ctx.saved_tensors
@@ -275,6 +293,7 @@ class _GnnFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, d_out):
         lib = _lib.load_library()
         saved, *params = ctx.saved_tensors
@@ -371,10 +390,7 @@ class Gconv(nn.Module):
         W, x = input[0], input[1]
         if self.J != 2 or W.size(3) != 2:
             raise NotImplementedError("Gconv: only J=2 (identity + adjacency) is implemented")
-        if os.environ.get("MFT_CHECK_IDENTITY") == "1":
-            eye = torch.eye(W.size(1), device=W.device).expand_as(W[..., 0])
-            if not torch.equal(W[..., 0], eye):
-                raise RuntimeError("Gconv: operator 0 is not the identity")
+        _require_identity(W[..., :1], "Gconv: operator 0")
         adj = W[..., 1]
         out = _GconvFn.apply(adj, x, bool(_lrelu), *_gc_tensors(self))
         return W, out
@@ -438,6 +454,7 @@ class Wcompute(nn.Module):
 
         The -1e8 mask of gnn.py:106 is applied on the diagonal, i.e. W_id is taken to
         be the identity GNN_nl builds (gnn.py:155).  ``shared_nodes``: see GNN_nl.shared_nodes."""
+        _require_identity(W_id, "Wcompute: W_id")
         adj = self.adjacency(x, shared_nodes)
         return torch.cat([W_id, adj.unsqueeze(3)], 3)
 
@@ -470,6 +487,14 @@ class GNN_nl(nn.Module):
         # of the caller's replication adds up anyway.  None (default) = no assumption.
         self.shared_nodes = None
         self.check_shared = False   # debug: verify the promise on every call (device sync)
+        # Without a promise the module looks for itself (eager calls only): node n is treated as shared when
+        # x[b, n, :] is bitwise the same row in every graph b -- true for exactly the support nodes of the
+        # graphs the reference's forward_gnn builds (gnnnet.py:83,212), so the unchanged scripts get the
+        # shared-pair speed-up too.  One tiny comparison + a host read per call (the reference's loops
+        # synchronise every step anyway, meta_template.py:88); skipped while a CUDA graph is being captured and
+        # for leaf inputs that require grad (their .grad is per graph by definition).  MFT_AUTO_SHARE=0 or
+        # auto_share = False switches it off.
+        self.auto_share = os.environ.get("MFT_AUTO_SHARE", "1") != "0"
 
     def _all_tensors(self) -> List[torch.Tensor]:
         t: List[torch.Tensor] = []
@@ -481,6 +506,12 @@ class GNN_nl(nn.Module):
         return t
 
     def _shared(self, x):
+        if (self.shared_nodes is None and self.auto_share and x.is_cuda and x.size(0) >= 2
+                and not (x.requires_grad and x.is_leaf) and not torch.cuda.is_current_stream_capturing()):
+            with torch.no_grad():
+                same = (x == x[:1]).all(dim=2).all(dim=0)
+            same = same.cpu().tolist()
+            return bytes(1 if v else 0 for v in same) if sum(same) >= 2 else None
         mask = _shared_mask(self.shared_nodes, x)
         if mask is not None and self.check_shared:
             sel = torch.tensor([bool(v) for v in mask], device=x.device)

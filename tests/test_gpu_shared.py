@@ -157,3 +157,73 @@ def test_gnn_head_shares_support_by_default_and_matches_unshared():
         if den > 1e-6:
             assert float((a - b).norm()) / den < 3e-2, k
     mft_b200.set_precision("auto")
+
+
+def test_auto_share_finds_the_replicated_supports_of_the_reference_graphs():
+    """Unchanged reference callers never set shared_nodes: GNN_nl then detects (eager calls only) the nodes
+    whose rows are bitwise identical in every graph -- exactly the supports of forward_gnn's graphs
+    (gnnnet.py:83,212) -- and gets the same logits / parameter gradients as with sharing off."""
+    import mft_b200
+    mft_b200.set_precision("fp32")
+    n_way, n_support, n_query, fin = 5, 5, 16, 133
+    torch.manual_seed(3)
+    net = mft_b200.GNN_nl(fin, 96, n_way).cuda()
+    z = torch.randn(n_way, n_support + n_query, fin, device="cuda", requires_grad=True)
+    res = []
+    for auto in (True, False):
+        net.auto_share = auto
+        net.zero_grad(set_to_none=True)
+        z.grad = None
+        nodes = torch.cat([torch.cat([z[:, :n_support], z[:, n_support + i:n_support + i + 1]], dim=1)
+                           .reshape(1, -1, fin) for i in range(n_query)], dim=0)      # gnnnet.py:83
+        mask = net._shared(nodes)
+        if auto:
+            assert mask == bytes(([1] * n_support + [0]) * n_way)
+        else:
+            assert mask is None
+        out = net(nodes)
+        out.square().sum().backward()
+        res.append((out.detach().clone(), z.grad.clone(), {k: v.grad.clone() for k, v in net.named_parameters()}))
+    (o1, dz1, g1), (o0, dz0, g0) = res
+    assert U.rel(o1.cpu().numpy(), o0.cpu().numpy()) < 2e-5
+    assert U.rel(dz1.cpu().numpy(), dz0.cpu().numpy()) < 3e-2
+    for k in g0:
+        if not U.is_zero_grad(k):
+            assert U.rel(g1[k].cpu().numpy(), g0[k].cpu().numpy()) < 3e-2, k
+    # a leaf input that requires grad keeps per-graph gradients: no detection
+    net.auto_share = True
+    leaf = nodes.detach().clone().requires_grad_(True)
+    assert net._shared(leaf) is None
+    mft_b200.set_precision("auto")
+
+
+def test_non_identity_operator_is_refused():
+    import mft_b200
+    mft_b200.set_precision("fp32")
+    m = mft_b200.Wcompute(13, 8).cuda()
+    x = torch.randn(2, 5, 13, device="cuda")
+    eye = torch.eye(5, device="cuda").view(1, 5, 5, 1).repeat(2, 1, 1, 1)
+    W = m(x, eye)
+    assert W.shape == (2, 5, 5, 2)
+    with pytest.raises(RuntimeError, match="not the identity"):
+        m(x, 2 * eye)
+    gc = mft_b200.Gconv(13, 4, 2).cuda()
+    gc([W, x])
+    bad = W.clone()
+    bad[..., 0] = 0.5
+    with pytest.raises(RuntimeError, match="not the identity"):
+        gc([bad, x])
+    mft_b200.set_precision("auto")
+
+
+def test_double_backward_is_refused():
+    """The hand-written backward is first order (the reference's FO-MAML needs no more): asking autograd to
+    differentiate through it raises instead of silently treating the gradient as a constant."""
+    import mft_b200
+    mft_b200.set_precision("fp32")
+    net = mft_b200.GNN_nl(13, 16, 3).cuda()
+    x = torch.randn(2, 6, 13, device="cuda", requires_grad=True)
+    (gx,) = torch.autograd.grad(net(x).sum(), x, create_graph=True)
+    with pytest.raises(RuntimeError):
+        gx.sum().backward()
+    mft_b200.set_precision("auto")

@@ -26,8 +26,13 @@ head_5w5s_grads.npz  gradients of the n_query=16 loss of head_5w5s.npz w.r.t. ev
                    and the features (float64 run of the reference, stored float32) plus the reference's own
                    float32-vs-float64 error per tensor.                    [python make_golden.py headgrads]
 
+loader.npz         which IMAGES form each episode: index streams recorded from the reference's own loaders
+                   (CropDisease_few_shot.SetDataManager2 with num_aug=2, seed 10, num_workers=0;
+                   miniImageNet_few_shot.SetDataManager with aug=False, 12 workers) run over a synthetic image
+                   folder whose constant-colour images encode (class, index).   [python make_golden.py loader]
+
 Without arguments every fixture is regenerated; with arguments only the named groups
-(base, 5w20s, headgrads).
+(base, 5w20s, headgrads, loader).
 """
 import os
 import sys
@@ -152,10 +157,82 @@ def make_headgrads(ref_gnnnet, ref_backbone):
     np.savez_compressed(os.path.join(HERE, "head_5w5s_grads.npz"), **rec)
 
 
+def loader_image_size(cl, idx):
+    """(w, h) of synthetic image `idx` of class `cl` (tests/test_host_logic.py uses the same rule)."""
+    return 40 + (7 * idx + 3 * cl) % 50, 40 + (5 * idx + cl) % 50
+
+
+def _synthetic_folder(root, class_sizes):
+    from PIL import Image
+    for cl, n in enumerate(class_sizes):
+        d = os.path.join(root, "c%03d" % cl)
+        os.makedirs(d)
+        for idx in range(n):
+            Image.new("RGB", loader_image_size(cl, idx), (cl, idx, 128)).save(os.path.join(d, "i%03d.png" % idx))
+
+
+def _decode(x):
+    """[n_way, batch, 3, H, W] un-augmented views -> (class, index) of every image (colour = (cl, idx, 128))."""
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 1, 3)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 1, 3)
+    px = ((x[:, :, :, 0, 0] * std + mean) * 255.0).round().long()
+    assert (px[:, :, 2] == 128).all()
+    return px[:, :, 0].numpy(), px[:, :, 1].numpy()
+
+
+def make_loader():
+    import tempfile
+    import torchvision.transforms as T
+    # the reference pins torchvision 0.8.2, where these are (deprecated) aliases; later releases dropped them
+    if not hasattr(T, "Scale"):
+        T.Scale = T.Resize
+    if not hasattr(T, "RandomSizedCrop"):
+        T.RandomSizedCrop = T.RandomResizedCrop
+    sys.path.insert(0, REF)
+    from datasets import CropDisease_few_shot as crop
+    from datasets import miniImageNet_few_shot as mini
+    rec = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        crop_sizes = [24 + (cl * 5) % 17 for cl in range(38)]
+        _synthetic_folder(os.path.join(tmp, "crop", "dataset", "train"), crop_sizes)
+        crop.CropDisease_path = os.path.join(tmp, "crop")
+        mgr = crop.SetDataManager2(64, n_eposide=6, n_query=15, n_way=5, n_support=5)
+        loader = mgr.get_data_loader(num_aug=2)
+        classes, indices = [], []
+        for elem in loader:
+            assert len(elem) == 4 and torch.equal(elem[0][0], elem[1][0])        # finetune.py:606
+            cl, idx = _decode(elem[0][0])
+            assert (cl == cl[:, :1]).all() and (cl[:, 0] == elem[0][1][:, 0].numpy()).all()
+            classes.append(cl[:, 0])
+            indices.append(idx)
+        rec["crop_class_sizes"] = np.array(crop_sizes)
+        rec["crop_classes"] = np.stack(classes)
+        rec["crop_indices"] = np.stack(indices)
+        rec["crop_rng_after"] = torch.rand(4).numpy()          # the global stream position after the 6 episodes
+        mini_sizes = [22 + cl % 9 for cl in range(64)]
+        _synthetic_folder(os.path.join(tmp, "mini"), mini_sizes)
+        mini.miniImageNet_path = os.path.join(tmp, "mini")
+        torch.manual_seed(10)
+        loader = mini.SetDataManager(64, n_query=16, n_way=5, n_support=5, n_eposide=8).get_data_loader(aug=False)
+        classes, indices = [], []
+        for x, y in loader:
+            cl, idx = _decode(x)
+            assert (cl == y.numpy()).all()
+            classes.append(cl[:, 0])
+            indices.append(idx)
+        rec["mini_class_sizes"] = np.array(mini_sizes)
+        rec["mini_classes"] = np.stack(classes)
+        rec["mini_indices"] = np.stack(indices)
+        rec["mini_rng_after"] = torch.rand(4).numpy()
+    np.savez_compressed(os.path.join(HERE, "loader.npz"), **rec)
+
+
 def main():
     ref_gnn, ref_gnnnet, ref_gnnnet_copy, ref_backbone = _import_reference()
     torch.set_num_threads(8)
-    groups = set(sys.argv[1:]) or {"base", "5w20s", "headgrads"}
+    groups = set(sys.argv[1:]) or {"base", "5w20s", "headgrads", "loader"}
+    if "loader" in groups:
+        make_loader()
     if "5w20s" in groups:
         make_5w20s(ref_gnn)
     if "headgrads" in groups:

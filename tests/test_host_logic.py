@@ -116,3 +116,64 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_LIB_NAME", "libmft_gnn_missing.so")
     with pytest.raises(_lib.LibraryMissing, match="no other compute path"):
         _lib.load_library()
+
+
+# ------------------------------------------------------------------------------------------
+# row S, second half: WHICH images form each episode (index streams of the reference's loaders)
+# ------------------------------------------------------------------------------------------
+
+def _loader_image_size(cl, idx):       # the rule of tests/golden/make_golden.py loader_image_size
+    return 40 + (7 * idx + 3 * cl) % 50, 40 + (5 * idx + cl) % 50
+
+
+def test_target_domain_image_indices_match_the_reference_loader(golden_dir):
+    """SetDataManager2(n_query=15, n_support=5).get_data_loader(num_aug=2) of CropDisease_few_shot.py run
+    over a synthetic image folder (tests/golden/loader.npz): class subsets, the images of every class (each
+    a fresh shuffled DataLoader whose seeds come from the global stream) AND the amount of randomness the
+    augmentation transforms consume in between are reproduced bit for bit -- the global RNG is at the same
+    position after the six episodes."""
+    from mft_b200 import sampling
+    rec = dict(np.load(os.path.join(golden_dir, "loader.npz")))
+    eps = list(sampling.target_domain_episode_indices(rec["crop_class_sizes"].tolist(), seed=10, n_way=5,
+                                                      batch_size=20, n_episodes=6, num_aug=2,
+                                                      image_size_fn=_loader_image_size))
+    assert np.array_equal(np.array([e[0] for e in eps]), rec["crop_classes"])
+    assert np.array_equal(np.array([e[1] for e in eps]), rec["crop_indices"])
+    assert np.array_equal(torch.rand(4).numpy(), rec["crop_rng_after"])
+    # without modelling the transforms' consumption the very first episode already diverges
+    eps0 = list(sampling.target_domain_episode_indices(rec["crop_class_sizes"].tolist(), seed=10, n_way=5,
+                                                       batch_size=20, n_episodes=2, num_aug=0))
+    assert np.array_equal(np.array(eps0[0][0]), rec["crop_classes"][0])
+    assert not np.array_equal(np.array([e[1] for e in eps0]), rec["crop_indices"][:2])
+
+
+def test_training_image_indices_match_the_reference_loader(golden_dir):
+    """miniImageNet_few_shot.SetDataManager(...).get_data_loader(aug=False) (12 worker processes): class
+    subsets from the main process's stream, per-class shuffles from the workers' (base_seed + worker_id)."""
+    from mft_b200 import sampling
+    rec = dict(np.load(os.path.join(golden_dir, "loader.npz")))
+    torch.manual_seed(10)
+    eps = list(sampling.train_episode_indices(rec["mini_class_sizes"].tolist(), n_way=5, batch_size=21,
+                                              n_episodes=8, num_workers=12))
+    assert np.array_equal(np.array([e[0] for e in eps]), rec["mini_classes"])
+    assert np.array_equal(np.array([e[1] for e in eps]), rec["mini_indices"])
+    assert np.array_equal(torch.rand(4).numpy(), rec["mini_rng_after"])
+
+
+def test_inner_loop_batches_follow_the_numpy_stream():
+    """finetune.py:271-284 / gnnnet.py:153-161: np.random.permutation per epoch, consecutive batches; a rank
+    that skips an episode it does not own leaves the stream where the owner's replay leaves it."""
+    from mft_b200 import sampling
+    np.random.seed(10)
+    want = []
+    for _ in range(3):
+        rand_id = np.random.permutation(25)
+        want += [rand_id[j:min(j + 4, 25)] for j in range(0, 25, 4)]
+    after = np.random.permutation(5)
+    np.random.seed(10)
+    got = list(sampling.inner_loop_batches(25, 4, 3))
+    assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+    assert np.array_equal(np.random.permutation(5), after)
+    np.random.seed(10)
+    sampling.skip_inner_loop(25, 3)
+    assert np.array_equal(np.random.permutation(5), after)

@@ -19,6 +19,7 @@ static const char* kNames[PC_COUNT] = {
     "finalize_grads",
     "gconv_fwd", "gconv_bwd",
     "prep",
+    "bwd_gemm_region",
 };
 
 const char* prof_name(int cat) { return (cat >= 0 && cat < PC_COUNT) ? kNames[cat] : "?"; }
@@ -46,8 +47,8 @@ int pdl_level() {
 }
 void set_pdl_level(int v) { g_pdl.store(v < 0 ? 0 : v); }
 
-ProfScope::ProfScope(int cat, cudaStream_t stream) : slot(-1), st(stream) {
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+ProfScope::ProfScope(int cat, cudaStream_t stream, bool count_launch) : slot(-1), st(stream) {
+    if (count_launch) g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!g_enabled.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_used >= kMaxSlots) return;

@@ -20,6 +20,7 @@ enum ProfCat {
     PC_FINALIZE,
     PC_GCONV_FWD, PC_GCONV_BWD,
     PC_PREP,
+    PC_BWD_REGION,      // main-stream span of one Wcompute's wgrad + dgrad launches (they overlap on two streams)
     PC_COUNT
 };
 
@@ -29,7 +30,7 @@ void set_pdl_level(int v);
 struct ProfScope {
     int slot;
     cudaStream_t st;
-    ProfScope(int cat, cudaStream_t stream);
+    ProfScope(int cat, cudaStream_t stream, bool count_launch = true);
     ~ProfScope();
 };
 

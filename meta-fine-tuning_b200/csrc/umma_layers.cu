@@ -1630,6 +1630,11 @@ static int num_sms() {
     return g_num_sms;
 }
 
+static int g_grid_limit = 0;
+void umma_set_grid_limit(int ctas) { g_grid_limit = ctas; }
+int umma_num_sms() { return num_sms(); }
+static int grid_cap() { return g_grid_limit > 0 ? min(g_grid_limit, num_sms()) : num_sms(); }
+
 constexpr size_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA on sm_100
 
 static bool plan_pass(int N_TILE, int K, UmmaShape& s) {
@@ -1684,7 +1689,7 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
         return MFT_ERR_UNSUPPORTED;
     }
     const int ntiles = cdiv(R, UM_ROWS);
-    const int grid = min(ntiles, num_sms());
+    const int grid = min(ntiles, grid_cap());
     for (int p = 0; p < passes; ++p) {
         const int dir = next_direction();
         UmmaShape s{};
@@ -1783,7 +1788,7 @@ static int umma_wgrad(const POp& pop, const QOp& qop, float* dW, int ldw, int R,
         return MFT_ERR_UNSUPPORTED;
     }
     const int nchunks = cdiv(R, WG_ROWS);
-    const int grid = min(nchunks, min(num_sms(), kWgMaxCopies));
+    const int grid = min(nchunks, min(grid_cap(), kWgMaxCopies));
     s.chunks_per_cta = cdiv(nchunks, grid);
     s.copies = copies_out ? max(2, cdiv(nchunks, s.chunks_per_cta)) : 1;   // (a one-CTA launch still stores)
     if (copies_out) *copies_out = cdiv(nchunks, s.chunks_per_cta);

@@ -3,6 +3,7 @@
 // autograd graph PyTorch builds behind it.  Algorithm: tests/kernel_model.py
 // (unordered pairs with multiplicities, BN-cancelled conv biases dropped,
 // closed-form backward -- SURVEY.md Appendix A).
+#include <cstdlib>
 #include "common.cuh"
 #include "simt_gemm.cuh"
 #include "wcompute.cuh"
@@ -951,6 +952,7 @@ WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
     L.S = ws.take<float>((size_t)B * N * N);
     L.dyA = ws.take<float>(R * 2 * nf);
     L.dyB = ws.take<float>(R * 2 * nf);
+    L.dyC = ws.take<float>(umma_shape_supported(F, nf) ? R * 2 * nf : 0);
     L.bsums = ws.take<double>(5 * kStatSlot);
     L.wimg = ws.take<float>(umma_workspace_floats(F, nf) + 64);
     L.dD = ws.take<float>(umma_shape_supported(F, nf) ? R * (size_t)((F + 3) & ~3) : 0);
@@ -1123,6 +1125,23 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         MFT_CHECK_LAUNCH();
     }
 
+    // Tensor-core path: wgrad_k and dgrad_k both consume dy_k and nothing of each other, and a persistent
+    // GEMM pays a fixed fill + drain (one tile's producer time before, one tile's epilogue after: a third of
+    // a 4.7-tiles-per-CTA launch).  So the wgrad of a layer runs on a side stream beside the dgrad chain, each
+    // kernel on part of the SMs: twice the tiles per CTA amortise the fixed part, one kernel's fill hides
+    // under the other's steady state, and both read dy_k / H_k at about the same time (L2).  Three dy
+    // buffers rotate so that dgrad_{k-1} never writes what wgrad_k is still reading; wgrads alternate between
+    // two side streams and dgrad_{k-2} joins the one wgrad_k ran on.  MFT_BWD_SPLIT=0 restores the serial order.
+    static const int split_env = [] { const char* e = getenv("MFT_BWD_SPLIT"); return e ? atoi(e) : 1; }();
+    const bool split = precision == MFT_PREC_TF32 && split_env != 0 && g.R >= 16 * 128 * 4;
+    // SMs of the wgrad kernels (the dgrad chain gets the rest): half by default, MFT_BWD_SPLIT=<count> overrides
+    // (measured on B200, 5w20s / 5w50c: 40 % of the SMs for the wgrads is the optimum -- the dgrad chain is the
+    // critical path, the wgrads only have to keep up: profiles/r02_summary.md)
+    const int wg_sms = split_env >= 8 ? min(split_env, umma_num_sms() - 8) : (umma_num_sms() * 2) / 5;
+    ProfScope* region = precision == MFT_PREC_TF32 ? new ProfScope(PC_BWD_REGION, st, false) : nullptr;
+    Branches wb(st);
+    float* bufs[3] = {L.dyA, L.dyB, L.dyC};
+    int bi = 0;
     float* cur = L.dyA;
     float* nxt = L.dyB;
     for (int k = 3; k >= 0; --k) {   // layer k+1 of the reference (conv2d_{k+1}, bn_{k+1})
@@ -1138,8 +1157,16 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             PlainA dh{cur, Cout};
             // wgrad: d conv2d_{k+1}.weight [Cout, Cin] = dH^T a_k
             if (precision == MFT_PREC_TF32) {
-                int rc = wcompute_wgrad_layer_tf32(k, cur, x, ldx, F, p, gr, L, g, &wg_copies[k], st);
-                if (rc != MFT_OK) return rc;
+                cudaStream_t wst = st;
+                if (split) {
+                    const int slot = k & 1;
+                    wb.join(slot);                    // dy buffer (k+2) % 3 .. is about to be rewritten by this level's dgrad
+                    wst = wb.fork(slot);              // ordered after the kernel that produced dy_k
+                    umma_set_grid_limit(wg_sms);
+                }
+                int rc = wcompute_wgrad_layer_tf32(k, cur, x, ldx, F, p, gr, L, g, &wg_copies[k], wst);
+                if (split) umma_set_grid_limit(umma_num_sms() - wg_sms);
+                if (rc != MFT_OK) { umma_set_grid_limit(0); delete region; return rc; }
             } else if (k == 0) {
                 ProfScope ps(PC_WGRAD_L1, st);
                 AbsDiffA q{x, ldx, g};
@@ -1152,8 +1179,10 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             }
             // dgrad: dL/d a_k = dH W
             if (precision == MFT_PREC_TF32) {
+                if (split) nxt = bufs[(bi + 1) % 3];
                 int rc = wcompute_bwd_layer_tf32(k, cur, nxt, x, ldx, dx, F, nf, p, gr, L, g, st);
-                if (rc != MFT_OK) return rc;
+                umma_set_grid_limit(0);
+                if (rc != MFT_OK) { delete region; return rc; }
             } else {
                 WView wv = wview_nn(p->conv_w[k], Cin);
                 ProfScope psd(PC_DGRAD_L1 + k, st);
@@ -1168,8 +1197,13 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
                 }
             }
         }
-        float* tmp = cur; cur = nxt; nxt = tmp;
+        if (split) { bi = (bi + 1) % 3; cur = bufs[bi]; }
+        else { float* tmp = cur; cur = nxt; nxt = tmp; }
     }
+    wb.join(0);
+    wb.join(1);
+    delete region;
+    MFT_REQUIRE(wb.ok(), "wcompute_bwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
 
     FinalizeArgs fa;
     for (int k = 0; k < 4; ++k) {

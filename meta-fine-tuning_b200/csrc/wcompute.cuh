@@ -22,6 +22,7 @@ struct WcLayout {
     float* S;            // workspace: scores / dS, [B,N,N]
     float* dyA;          // workspace: ping-pong gradient buffers [R, 2nf]
     float* dyB;
+    float* dyC;          // third buffer: lets wgrad_k (side stream) read dy_k while dgrad_{k-1} writes dy_{k-2}
     double* bsums;       // workspace: backward reductions, 5 x [2*kMaxC] (last = d conv2d_last.weight)
     float* wimg;         // workspace: swizzled TF32 weight image of the tcgen05 path
     float* dD;           // workspace (tcgen05 path): dL/d|x_i-x_j| per unordered pair, [R, roundup4(F)]
@@ -32,6 +33,10 @@ struct WcLayout {
 };
 
 size_t umma_workspace_floats(int F, int nf);
+// Upper bound on the CTAs of the next tcgen05 GEMM launches (0 = all SMs): wcompute_bwd runs the wgrad of a
+// layer beside its dgrad, each on half of the SMs (persistent kernels loop over their tiles whatever the grid).
+void umma_set_grid_limit(int ctas);
+int umma_num_sms();
 bool umma_shape_supported(int F, int nf);
 int umma_debug_gemm(const float* A, int lda, const float* W, int ldw, int transpose_w, float* C, int ldc, int M,
                     int N, int K, float* wimg, cudaStream_t st);

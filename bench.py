@@ -630,6 +630,7 @@ def run_ours(args):
         # (wgrad and dgrad launches of a layer overlap on two streams, each on part of the SMs: their summed
         # durations would count that time twice, so the backward enters with the main-stream span of each
         # Wcompute's wgrad + dgrad region -- which also contains the dx gather -- the forward with its launches)
+        spans = {k: round(prof.pop(k)[0], 4) for k in list(prof) if k.startswith("span_")}
         region = prof.pop("bwd_gemm_region", None)
         if region is not None:
             gemm_ms = sum(v[0] for k, v in prof.items() if k.startswith("fwd_gemm")) + region[0]
@@ -699,6 +700,7 @@ def run_ours(args):
             "head_tflops_algorithmic": alg * eps / world / 1e12,
             "kernel_ms_per_step": {k: round(v[0], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "bwd_gemm_region_ms_per_step": round(region[0], 4) if region is not None else None,
+            "main_stream_span_ms_per_step": spans,
             "library_kernel_ms_per_step": lib_ms,
         }
         if world == 1 and not args.no_gpu_reference:

@@ -108,6 +108,8 @@ int mft_tf32_supported(int F, int nf);
 
 /* Bytes of the activation tape kept from forward to backward / of scratch. */
 size_t mft_wcompute_saved_bytes(int B, int N, int F, int nf);
+/* The same for a known precision (MFT_PREC_TF32 keeps an fp16 activation tape: half the bytes). */
+size_t mft_wcompute_saved_bytes_for(int B, int N, int F, int nf, int precision);
 size_t mft_wcompute_workspace_bytes(int B, int N, int F, int nf);
 
 /* x [B*N, ldx] (first F columns used) -> adj [B,N,N]: adj[b,i,:] =
@@ -147,6 +149,7 @@ int mft_gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F
 /* ---- GNN_nl: replaces GNN_nl.forward (gnn.py:154-166) in one call ---------- */
 
 size_t mft_gnn_saved_bytes(int B, int N, int F0, int nf, int n_way);
+size_t mft_gnn_saved_bytes_for(int B, int N, int F0, int nf, int n_way, int precision);
 size_t mft_gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way);
 
 /* x [B,N,F0] contiguous -> out [B,N,n_way] contiguous. */
@@ -214,7 +217,7 @@ int mft_debug_umma_gemm(const float* A, int lda, const float* W, int ldw, int tr
 /* dW[Cout,Cin] += P[R,Cout]^T * Q[R,Cin] on the tensor-core wgrad kernel (Cout <= 192, Cin <= 256). */
 /* Tests: byte offsets of the activation tape inside a Wcompute `saved` blob (H_1..H_4, forward statistics,
  * tape scales; out[6], out[7] = doubles per statistics slot / per copy).  out: size_t[8]. */
-int mft_debug_wcompute_saved_offsets(int B, int N, int F, int nf, size_t* out);
+int mft_debug_wcompute_saved_offsets(int B, int N, int F, int nf, int precision, size_t* out);
 
 /* Per-CTA clock64 timeline of ONE rows-GEMM launch, the (skip+1)-th from now, into buf [grid][16]. */
 int mft_debug_set_timeline(void* buf, int skip);

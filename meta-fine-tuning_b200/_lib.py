@@ -57,6 +57,7 @@ SIGNATURES = {
     "mft_device_check": (_i, [_i]),
     "mft_tf32_supported": (_i, [_i, _i]),
     "mft_wcompute_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "mft_wcompute_saved_bytes_for": (_sz, [_i, _i, _i, _i, _i]),
     "mft_wcompute_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mft_wcompute_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(WcomputeParams), _vp, _vp, _vp, _i, C.c_char_p,
                               _vp]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "mft_gconv_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(GconvParams), _i, _vp, _i, _vp, _vp,
                            C.POINTER(GconvGrads), _vp, _vp, _vp]),
     "mft_gnn_saved_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "mft_gnn_saved_bytes_for": (_sz, [_i, _i, _i, _i, _i, _i]),
     "mft_gnn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mft_gnn_fwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, _vp, _vp, _i, C.c_char_p, _vp]),
     "mft_gnn_bwd": (_i, [_vp, _i, _i, _i, _i, _i, C.POINTER(GnnParams), _vp, C.POINTER(GnnGrads), _vp, _vp,
@@ -82,7 +84,7 @@ SIGNATURES = {
     "mft_debug_umma_gemm": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mft_debug_umma_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "mft_debug_set_timeline": (_i, [_vp, _i]),
-    "mft_debug_wcompute_saved_offsets": (_i, [_i, _i, _i, _i, C.POINTER(C.c_size_t)]),
+    "mft_debug_wcompute_saved_offsets": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_size_t)]),
     "mft_launch_count": (C.c_ulonglong, []),
     "mft_prof_enable": (_i, [_i]),
     "mft_set_pdl": (_i, [_i]),

@@ -20,7 +20,7 @@ void set_error(int code, const char* fmt, ...) {
 }
 int last_code() { return g_code; }
 
-size_t gnn_saved_bytes(int B, int N, int F0, int nf, int n_way);
+size_t gnn_saved_bytes(int B, int N, int F0, int nf, int n_way, int precision);
 size_t gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way);
 int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
             void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st);
@@ -80,7 +80,10 @@ int mft_device_check(int device) {
 int mft_tf32_supported(int F, int nf) { return umma_shape_supported(F, nf) ? 1 : 0; }
 
 size_t mft_wcompute_saved_bytes(int B, int N, int F, int nf) {
-    return wc_layout(B, N, F, nf, nullptr, nullptr).saved_bytes;
+    return wc_layout(B, N, F, nf, nullptr, nullptr).saved_bytes;      // fp32 tape: enough for either precision
+}
+size_t mft_wcompute_saved_bytes_for(int B, int N, int F, int nf, int precision) {
+    return wc_layout(B, N, F, nf, nullptr, nullptr, precision).saved_bytes;
 }
 size_t mft_wcompute_workspace_bytes(int B, int N, int F, int nf) {
     return wc_layout(B, N, F, nf, nullptr, nullptr).workspace_bytes;
@@ -128,7 +131,10 @@ int mft_gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F
                      (cudaStream_t)stream);
 }
 
-size_t mft_gnn_saved_bytes(int B, int N, int F0, int nf, int n_way) { return gnn_saved_bytes(B, N, F0, nf, n_way); }
+size_t mft_gnn_saved_bytes(int B, int N, int F0, int nf, int n_way) { return gnn_saved_bytes(B, N, F0, nf, n_way, MFT_PREC_FP32); }
+size_t mft_gnn_saved_bytes_for(int B, int N, int F0, int nf, int n_way, int precision) {
+    return gnn_saved_bytes(B, N, F0, nf, n_way, precision);
+}
 size_t mft_gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way) {
     return gnn_workspace_bytes(B, N, F0, nf, n_way);
 }
@@ -201,10 +207,10 @@ int mft_debug_umma_wgrad(const float* P, int ldp, const float* Q, int ldq, float
  * pre-BatchNorm activations H_1..H_4 ([R, C_k] row-major, R pair rows in the order of the row table: fp16 on the
  * tensor-core path, fp32 on the fp32 path), out[4] = forward statistics (4 slots of kStatCopies x [2][kMaxC]
  * doubles), out[5] = the four tape scales (floats), out[6] = doubles per statistics slot, out[7] = doubles per copy. */
-int mft_debug_wcompute_saved_offsets(int B, int N, int F, int nf, size_t* out) {
+int mft_debug_wcompute_saved_offsets(int B, int N, int F, int nf, int precision, size_t* out) {
     MFT_REQUIRE(out && B > 0 && N > 0 && F > 0 && nf > 0, "mft_debug_wcompute_saved_offsets: bad argument");
     char* base = nullptr;
-    WcLayout L = wc_layout(B, N, F, nf, base, base);
+    WcLayout L = wc_layout(B, N, F, nf, base, base, precision);
     for (int k = 0; k < 4; ++k) out[k] = (size_t)(reinterpret_cast<char*>(L.H[k]) - base);
     out[4] = (size_t)(reinterpret_cast<char*>(L.fsums) - base);
     out[5] = (size_t)(reinterpret_cast<char*>(L.tscale) - base);

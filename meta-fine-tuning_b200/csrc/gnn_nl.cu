@@ -27,7 +27,8 @@ struct GnnLayout {
     size_t saved_bytes, workspace_bytes;
 };
 
-static GnnLayout gnn_layout(int B, int N, int F0, int nf, int n_way, void* saved, void* workspace) {
+static GnnLayout gnn_layout(int B, int N, int F0, int nf, int n_way, void* saved, void* workspace,
+                            int precision = MFT_PREC_FP32) {
     GnnLayout G;
     G.L = MFT_MAX_LAYERS;
     const int half = nf / 2;
@@ -43,7 +44,7 @@ static GnnLayout gnn_layout(int B, int N, int F0, int nf, int n_way, void* saved
     size_t wc_ws = 0, gc_ws = 0;
     for (int l = 0; l < G.L; ++l) {
         G.adj[l] = sv.take<float>((size_t)B * N * N);
-        WcLayout w = wc_layout(B, N, G.F[l], nf, nullptr, nullptr);
+        WcLayout w = wc_layout(B, N, G.F[l], nf, nullptr, nullptr, precision);
         GcLayout c = gc_layout(B, N, G.F[l], G.nout[l], nullptr, nullptr);
         G.wc_saved[l] = sv.take<char>(w.saved_bytes);
         G.gc_saved[l] = sv.take<char>(c.saved_bytes);
@@ -60,8 +61,8 @@ static GnnLayout gnn_layout(int B, int N, int F0, int nf, int n_way, void* saved
     return G;
 }
 
-size_t gnn_saved_bytes(int B, int N, int F0, int nf, int n_way) {
-    return gnn_layout(B, N, F0, nf, n_way, nullptr, nullptr).saved_bytes;
+size_t gnn_saved_bytes(int B, int N, int F0, int nf, int n_way, int precision) {
+    return gnn_layout(B, N, F0, nf, n_way, nullptr, nullptr, precision).saved_bytes;
 }
 size_t gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way) {
     return gnn_layout(B, N, F0, nf, n_way, nullptr, nullptr).workspace_bytes;
@@ -70,7 +71,7 @@ size_t gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way) {
 int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
             void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st) {
     MFT_REQUIRE(B > 0 && N > 0 && F0 > 0 && nf >= 2 && (nf % 2) == 0 && n_way > 0, "gnn_fwd: bad shape");
-    GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace);
+    GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace, precision);
     const int rows = B * N;
     MFT_CHECK_CUDA(cudaMemcpy2DAsync(G.xcat, sizeof(float) * G.ldx, x, sizeof(float) * F0, sizeof(float) * F0,
                                      rows, cudaMemcpyDeviceToDevice, st));
@@ -83,8 +84,11 @@ int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_g
     if (rc != MFT_OK) return rc;
     Branches br(st);
     for (int l = 0; l < G.L; ++l) {
-        rc = wcompute_fwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.wc_saved[l], G.wc_ws,
-                          precision, l == 0 ? shared_nodes : nullptr, st, true);
+        {
+            ProfScope span(PC_SPAN_WC_FWD, st, false);
+            rc = wcompute_fwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.wc_saved[l], G.wc_ws,
+                              precision, l == 0 ? shared_nodes : nullptr, st, true);
+        }
         if (rc != MFT_OK) return rc;
         const bool last = (l == G.L - 1);
         if (!last) {
@@ -94,10 +98,13 @@ int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_g
         }
         float* dst = last ? out : G.xcat + G.F[l];
         int ldo = last ? n_way : G.ldx;
-        rc = gconv_fwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, dst, ldo,
-                       G.gc_saved[l], G.gc_ws, st);
-        if (rc != MFT_OK) return rc;
-        br.join(2);
+        {
+            ProfScope span(PC_SPAN_GC_FWD, st, false);
+            rc = gconv_fwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, dst, ldo,
+                           G.gc_saved[l], G.gc_ws, st);
+            if (rc != MFT_OK) return rc;
+            br.join(2);
+        }
     }
     MFT_REQUIRE(br.ok(), "gnn_fwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
     return MFT_OK;
@@ -107,7 +114,7 @@ int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const m
             const mft_gnn_grads* g, void* saved, void* workspace, int precision, const unsigned char* shared_nodes,
             cudaStream_t st) {
     MFT_REQUIRE(B > 0 && N > 0 && F0 > 0 && nf >= 2 && (nf % 2) == 0 && n_way > 0, "gnn_bwd: bad shape");
-    GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace);
+    GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace, precision);
     const int rows = B * N;
     MFT_CHECK_CUDA(cudaMemsetAsync(G.dxcat, 0, sizeof(float) * (size_t)rows * G.ldx, st));
     Branches tail(st);   // slot 2: parameter-gradient finalisation of layer l beside the Gconv backward of layer l-1
@@ -117,12 +124,19 @@ int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const m
         // (every later layer has already accumulated its dx there)
         const float* up = last ? d_out : G.dxcat + G.F[l];
         int ldu = last ? n_way : G.ldx;
-        int rc = gconv_bwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, up, ldu,
+        int rc;
+        {
+            ProfScope span(PC_SPAN_GC_BWD, st, false);
+            rc = gconv_bwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, up, ldu,
                            G.dxcat, G.d_adj, &g->l[l], G.gc_saved[l], G.gc_ws, st);
-        if (rc != MFT_OK) return rc;
-        tail.join(2);      // the Wcompute workspace (partial dW copies, reductions) is about to be reused
-        rc = wcompute_bwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.d_adj, G.dxcat, &g->w[l],
-                          G.wc_saved[l], G.wc_ws, precision, l == 0 ? shared_nodes : nullptr, st, &tail, 2);
+            if (rc != MFT_OK) return rc;
+            tail.join(2);      // the Wcompute workspace (partial dW copies, reductions) is about to be reused
+        }
+        {
+            ProfScope span(PC_SPAN_WC_BWD, st, false);
+            rc = wcompute_bwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.d_adj, G.dxcat, &g->w[l],
+                              G.wc_saved[l], G.wc_ws, precision, l == 0 ? shared_nodes : nullptr, st, &tail, 2);
+        }
         if (rc != MFT_OK) return rc;
     }
     MFT_CHECK_CUDA(cudaMemcpy2DAsync(dx, sizeof(float) * F0, G.dxcat, sizeof(float) * G.ldx, sizeof(float) * F0,

@@ -20,6 +20,7 @@ static const char* kNames[PC_COUNT] = {
     "gconv_fwd", "gconv_bwd",
     "prep",
     "bwd_gemm_region",
+    "span_wcompute_fwd", "span_gconv_fwd", "span_gconv_bwd", "span_wcompute_bwd",
 };
 
 const char* prof_name(int cat) { return (cat >= 0 && cat < PC_COUNT) ? kNames[cat] : "?"; }

@@ -20,7 +20,8 @@ enum ProfCat {
     PC_FINALIZE,
     PC_GCONV_FWD, PC_GCONV_BWD,
     PC_PREP,
-    PC_BWD_REGION,      // main-stream span of one Wcompute's wgrad + dgrad launches (they overlap on two streams)
+    PC_BWD_REGION,
+    PC_SPAN_WC_FWD, PC_SPAN_GC_FWD, PC_SPAN_GC_BWD, PC_SPAN_WC_BWD,   // main-stream spans of the phases of gnn_fwd / gnn_bwd      // main-stream span of one Wcompute's wgrad + dgrad launches (they overlap on two streams)
     PC_COUNT
 };
 

@@ -24,6 +24,8 @@
 // tmem_full/tmem_empty per accumulator (MMA <-> epilogue).  Every wait is bounded (umma::mbar_wait traps
 // on timeout).
 #include <cstdio>
+#include <cstring>
+#include <cstdlib>
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 
 #include "common.cuh"
@@ -48,6 +50,7 @@ constexpr int UM_STAGE_LD = 36;           // padded row length of the epilogue s
 constexpr int UM_ACC_STRIDE = 256;        // TMEM columns between the two accumulators
 constexpr int UM_TMEM_COLS = 512;
 constexpr int UM_MAX_STAGES = 4;
+constexpr int UM_MAX_PSTAGES = 8;          // A ring depth of the CTA-pair kernel
 constexpr int UM_MAX_RAW = 8;              // raw fp16 K blocks a TMA operand may have in flight
 constexpr int UM_RAW_BYTES = UM_ROWS * UM_KB * 2;   // [128 rows x 32 ch] fp16 = 8 KB
 constexpr unsigned WG_ROWS_C = 32;        // rows per wgrad K chunk (declared early for the TMA functors)
@@ -69,6 +72,12 @@ struct UmmaShape {
     int reverse;      // walk the row tiles from the last to the first (see next_direction())
     unsigned zero;    // always 0; unknown to the compiler (see the raw-ring release in the producers)
 };
+
+// CTA-pair kernel: half of the weight rows per CTA, a longer barrier block
+static inline size_t umma_smem_bytes_pair(const UmmaShape& s) {
+    return 1024 + (size_t)s.KC * (s.N_TILE / 2) * 128 + (size_t)s.stages * UM_BLOCK_FLOATS * 4 +
+           (size_t)UM_ROWS * UM_STAGE_LD * 4 + (3 + 4) * kMaxC * 4 + (size_t)s.raw_stages * UM_RAW_BYTES + 48 * 8 + 16;
+}
 
 static inline size_t umma_smem_bytes(const UmmaShape& s) {
     return 1024 + (size_t)s.KC * s.N_TILE * 128 + (size_t)s.stages * UM_BLOCK_FLOATS * 4 +
@@ -1160,6 +1169,853 @@ umma_rows_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi ep
     }
 }
 
+// ------------------------------------------------------------------ the rows kernel with A in TENSOR MEMORY
+// What paces umma_rows_kernel is shared-memory bandwidth (128 B / clock / SM), not the roles' instruction
+// streams: one M=128, N=192, K=8 kind::tf32 MMA reads 4 KB of A and 6 KB of B from shared memory in its 96
+// cycles, i.e. 107 B / clock by itself; per 128 x 192 x 192 tile the MMA reads 245 KB, the producers write the
+// 98 KB A tile (after reading 48 KB of raw tape that the TMA wrote), and the epilogue pushes 196 KB through its
+// transposing slab: 635 KB = 5.0k cycles of a 7.3k-cycle tile (profiles/r02_summary.md; neither deeper rings,
+// nor producer groups, nor CTA pairs moved it).  Here the A operand never touches shared memory: a producer
+// thread owns one ROW of the tile, builds its 32 K-values of a block in registers and writes them to tensor
+// memory (tcgen05.st.32x32b), and the MMA takes A from there ([a_tmem] operand form).  Saves the 98 KB of A
+// stores and the 98 KB of A operand reads per tile (31 % of the traffic) and the A ring's 32-64 KB of shared memory.
+//
+// Tensor memory (512 columns): accumulator a at column 256 a (N_TILE <= 224 columns), A slots of 32 columns
+// (one K block of 32 tf32 words for all 128 lanes) packed downwards from the top of each half:
+// NS = 2 * floor((256 - N_TILE) / 32) <= 8 slots (4 at N = 192).  Producer warps 0-3 and 4-7 form two groups
+// (warp % 4 = tensor-memory lane quadrant = rows 32 (warp % 4) ..); group g builds K blocks g, g + 2, ...
+// Barriers: rawfull / rawempty per raw slot (TMA <-> producers), full / empty per A slot (producers <-> MMA),
+// tfull / tempty per accumulator (MMA <-> epilogue).
+constexpr int UM_TS_MAX_SLOTS = 8;
+constexpr int UM_TS_MAX_NTILE = 224;
+
+__host__ __device__ inline int ts_slots(int N_TILE) {
+    const int n = 2 * ((256 - N_TILE) / 32);
+    return n > UM_TS_MAX_SLOTS ? UM_TS_MAX_SLOTS : n;
+}
+__device__ __forceinline__ uint32_t ts_slot_col(int slot) {      // slot j: half j & 1, (j >> 1)-th from the top
+    return (uint32_t)((slot & 1) * 256 + 256 - 32 * ((slot >> 1) + 1));
+}
+
+template <class AOp> __host__ __device__ constexpr int ts_raw_bytes() {
+    if constexpr (tma_in_place<AOp>()) return UM_BLOCK_FLOATS * 4 + UM_RAW_BYTES;   // dy fp32 block + H fp16 block
+    else if constexpr (AOp::kTma) return UM_RAW_BYTES;
+    else return 0;
+}
+
+template <class AOp>
+static inline size_t umma_smem_bytes_ts(const UmmaShape& s, int epi_warps = 4) {
+    return 1024 + (size_t)s.KC * s.N_TILE * 128 + (size_t)epi_warps * 32 * UM_STAGE_LD * 4 + (3 + 4) * kMaxC * 4 +
+           (size_t)s.raw_stages * ts_raw_bytes<AOp>() + 48 * 8 + 16;
+}
+
+// EW = 4 or 8 epilogue warps.  With eight, the two warps of a lane quadrant take alternate 32-column chunks of
+// the accumulator (each has its own staging slab): the source-level profile shows the epilogue warp alone on
+// its scheduler, stalled on fixed-latency dependencies a third of the time and issuing a fifth of it, and the
+// whole kernel paced by it -- a second warp per scheduler fills those slots.
+template <class AOp, class Epi, int EW>
+__global__ void __launch_bounds__((UM_PROD_WARPS + EW + 2) * 32, 1)
+umma_rows_ts_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi epi, const float* __restrict__ wimg,
+                    const __grid_constant__ UmmaShape s) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t w_bytes = (uint32_t)s.KC * s.N_TILE * 128;
+    constexpr int kRawBytes = ts_raw_bytes<AOp>();
+    constexpr int kThreads = (UM_PROD_WARPS + EW + 2) * 32;
+    constexpr int kMmaWarp = UM_PROD_WARPS + EW, kTmaWarp = kMmaWarp + 1;
+    float* Wsm = reinterpret_cast<float*>(smem);
+    float* stage = reinterpret_cast<float*>(smem + w_bytes);
+    float* aux_a = stage + EW * 32 * UM_STAGE_LD;
+    float* aux_e = aux_a + 3 * kMaxC;
+    uint8_t* rawring = reinterpret_cast<uint8_t*>(aux_e + 4 * kMaxC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rawring + (size_t)s.raw_stages * kRawBytes);
+    uint64_t* full = bars;            // [8] A slot written
+    uint64_t* empty = bars + 8;       // [8] A slot consumed by the MMA
+    uint64_t* tfull = bars + 16;      // [2]
+    uint64_t* tempty = bars + 18;     // [2]
+    uint64_t* wbar = bars + 20;
+    uint64_t* rawfull = bars + 22;    // [8]
+    uint64_t* rawempty = bars + 30;   // [8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (s.R + UM_ROWS - 1) / UM_ROWS;
+    auto phys = [&](int t) { return s.reverse ? ntiles - 1 - t : t; };
+    const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int NS = s.stages;          // A slots in tensor memory
+
+    if (tid == 0) {
+        for (int i = 0; i < UM_TS_MAX_SLOTS; ++i) {
+            mbar_init(&full[i], 4);                 // the four warps (lane quadrants) of a producer group
+            mbar_init(&empty[i], 1);
+            mbar_init(&rawfull[i], 1);
+            mbar_init(&rawempty[i], 4);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], EW);
+        }
+        mbar_init(wbar, 1);
+        fence_mbar_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, UM_TMEM_COLS);
+    __syncthreads();
+    if (warp == kMmaWarp && lane == 0) {
+        mbar_arrive_expect_tx(wbar, w_bytes);
+        const uint32_t blk = (uint32_t)s.N_TILE * 128;
+        for (int kc = 0; kc < s.KC; ++kc)
+            bulk_g2s(reinterpret_cast<uint8_t*>(Wsm) + (size_t)kc * blk,
+                     reinterpret_cast<const uint8_t*>(wimg) + (size_t)kc * blk, blk, wbar);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    aop.init(aux_a, tid, kThreads);
+    epi.init(aux_e, tid, kThreads);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    long long* dbg = s.dbg ? s.dbg + (size_t)blockIdx.x * 16 : nullptr;   // clock64 timeline (tools/umma_timeline.py)
+#define MFT_MARK(slot) do { if (dbg && lane == 0) dbg[slot] = clock64(); } while (0)
+    if (dbg && tid == 0) dbg[0] = clock64();
+
+    if (warp < UM_PROD_WARPS) {
+        // ===================== producers: one row per thread, 32 K-values per block, into tensor memory
+        // Register pool of the CTA = threads x the kernel's register count: 448 x 128 with four epilogue warps
+        // (producers 96, epilogue 192), 576 x 96 with eight (producers 72, epilogue 120, the MMA / TMA warps keep
+        // their 96 -- they are half a warpgroup and setmaxnreg is a warpgroup instruction: 18432 + 30720 + 6144 =
+        // 55296; setmaxnreg.inc blocks until the CTA's own warps have released enough).
+        if constexpr (EW == 8) reg_dec<72>(); else reg_dec<96>();
+        const int grp = warp >> 2, quad = warp & 3;
+        const int rl = quad * 32 + lane;                       // row of the tile = tensor-memory lane
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+        const int nblocks = my_tiles * s.KC;
+        int cur_ti = -1;
+        bool ok = false;
+        [[maybe_unused]] float wrow = 0.f;
+        [[maybe_unused]] typename AOp::Row rrow{};
+        for (int b = grp; b < nblocks; b += 2) {
+            const int ti = b / s.KC, kc = b - ti * s.KC;
+            const int row0 = phys((int)blockIdx.x + ti * (int)gridDim.x) * UM_ROWS;
+            if (ti != cur_ti) {
+                cur_ti = ti;
+                ok = row0 + rl < s.R;
+                if constexpr (tma_in_place<AOp>()) wrow = aop.row_weight(min(row0 + rl, s.R));
+                if constexpr (!AOp::kTma) rrow = aop.row(ok ? row0 + rl : 0);
+            }
+            const int slot = b % NS;
+            const uint32_t ph = (uint32_t)(b / NS) & 1u;
+            const int k0 = kc * UM_KB;
+            uint32_t v[32];
+            if constexpr (tma_in_place<AOp>()) {
+                const int rs = b % s.raw_stages;
+                const uint32_t rph = (uint32_t)(b / s.raw_stages) & 1u;
+                mbar_wait(&rawfull[rs], rph);
+                const uint8_t* rb = rawring + (size_t)rs * kRawBytes;
+                // dy: [128 rows x 32 fp32], SWIZZLE_128B as the TMA wrote it; H: [128 rows x 32 fp16], plain
+                const float* dyrow = reinterpret_cast<const float*>(rb) + (rl >> 3) * 256 + (rl & 7) * 32;
+                const uint4* hrow = reinterpret_cast<const uint4*>(rb + UM_BLOCK_FLOATS * 4 + rl * 64);
+                float4 d[8];
+                uint4 h[4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) d[j] = *reinterpret_cast<const float4*>(dyrow + ((j ^ (rl & 7)) << 2));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = hrow[j];
+                {   // release the raw slot on COMPLETION of the loads (see umma_rows_kernel)
+                    unsigned t = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t |= __float_as_uint(d[j].x) | __float_as_uint(d[j].w);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) t |= h[j].x | h[j].w;
+                    const unsigned z = __reduce_or_sync(0xffffffffu, t & s.zero);
+                    if (lane == 0) mbar_arrive_n(&rawempty[rs], 1u + z);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const typename AOp::Consts c = aop.consts(k0 + 4 * j, aux_a);
+                    const uint2 hp = (j & 1) ? make_uint2(h[j >> 1].z, h[j >> 1].w) : make_uint2(h[j >> 1].x, h[j >> 1].y);
+                    float4 o = aop.transform2(d[j], hp, wrow, c);
+                    if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[4 * j] = __float_as_uint(to_tf32_fast(o.x)); v[4 * j + 1] = __float_as_uint(to_tf32_fast(o.y));
+                    v[4 * j + 2] = __float_as_uint(to_tf32_fast(o.z)); v[4 * j + 3] = __float_as_uint(to_tf32_fast(o.w));
+                }
+            } else if constexpr (AOp::kTma) {
+                const int rs = b % s.raw_stages;
+                const uint32_t rph = (uint32_t)(b / s.raw_stages) & 1u;
+                mbar_wait(&rawfull[rs], rph);
+                const uint4* hrow = reinterpret_cast<const uint4*>(rawring + (size_t)rs * kRawBytes + rl * 64);
+                uint4 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = hrow[j];
+                {
+                    unsigned t = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) t |= h[j].x | h[j].y | h[j].z | h[j].w;
+                    const unsigned z = __reduce_or_sync(0xffffffffu, t & s.zero);
+                    if (lane == 0) mbar_arrive_n(&rawempty[rs], 1u + z);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const typename AOp::Consts c = aop.consts(k0 + 4 * j, aux_a);
+                    const uint2 hp = (j & 1) ? make_uint2(h[j >> 1].z, h[j >> 1].w) : make_uint2(h[j >> 1].x, h[j >> 1].y);
+                    float4 o = aop.transform(hp, c);
+                    if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[4 * j] = __float_as_uint(to_tf32_fast(o.x)); v[4 * j + 1] = __float_as_uint(to_tf32_fast(o.y));
+                    v[4 * j + 2] = __float_as_uint(to_tf32_fast(o.z)); v[4 * j + 3] = __float_as_uint(to_tf32_fast(o.w));
+                }
+            } else {
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {                // two batches of loads: 32 registers in flight
+                    typename AOp::Raw raw[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) aop.fetch(rrow, k0 + 4 * (4 * hq + j), raw[j]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int jj = 4 * hq + j;
+                        float4 o = aop.finish(raw[j], rrow, k0 + 4 * jj, aux_a);
+                        if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[4 * jj] = __float_as_uint(to_tf32_fast(o.x)); v[4 * jj + 1] = __float_as_uint(to_tf32_fast(o.y));
+                        v[4 * jj + 2] = __float_as_uint(to_tf32_fast(o.z)); v[4 * jj + 3] = __float_as_uint(to_tf32_fast(o.w));
+                    }
+                }
+            }
+            mbar_wait(&empty[slot], ph ^ 1);                    // the MMAs that read this slot last have completed
+            tc_fence_after_sync();
+            tmem_st_32x32(tmem_base + lane_base + ts_slot_col(slot), v);
+            tmem_st_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[slot]);
+            if (warp == 0 && ti == 0 && kc + 2 >= s.KC) MFT_MARK(2);          // first tile written
+        }
+        if (warp == 0) MFT_MARK(3);                                           // producers done
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer (one thread): A from tensor memory, B = resident weight image
+        if (lane == 0) {
+            const uint32_t blk = (uint32_t)s.N_TILE * 128;
+            mbar_wait(wbar, 0);
+            MFT_MARK(1);                                                   // weights resident
+            const uint32_t idesc = make_idesc_tf32(UM_ROWS, s.N_TILE);
+            const int ksteps = (s.K + 7) / 8;
+            const uint32_t b0 = smem_u32(Wsm);
+            int b = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int acc = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], aph ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * UM_ACC_STRIDE;
+                for (int kc = 0; kc < s.KC; ++kc, ++b) {
+                    const int slot = b % NS;
+                    const uint32_t ph = (uint32_t)(b / NS) & 1u;
+                    mbar_wait(&full[slot], ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_tmem = tmem_base + ts_slot_col(slot);
+                    const uint32_t bb = b0 + (uint32_t)kc * blk;
+                    const int nks = min(4, ksteps - kc * 4);
+                    for (int ks = 0; ks < nks; ++ks)
+                        mma_tf32_ts(d_tmem, a_tmem + ks * 8, make_desc_sw128(bb + ks * 32, 1024, 16), idesc,
+                                    (kc | ks) != 0 ? 1u : 0u);
+                    mma_commit(&empty[slot]);
+                }
+                mma_commit(&tfull[acc]);
+                if (it == 0) MFT_MARK(4);                                  // first tile issued
+            }
+            MFT_MARK(5);                                                   // all MMAs issued
+        }
+        __syncwarp();
+    } else if (warp == kTmaWarp) {
+        // ===================== TMA loader (one thread): raw blocks of the tape / gradient operands
+        if constexpr (AOp::kTma) {
+            if (lane == 0) {
+                tma_prefetch_desc(&aop.tmap);
+                if constexpr (tma_in_place<AOp>()) tma_prefetch_desc(&aop.tmap_dy);
+                int b = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int row0 = phys((int)blockIdx.x + it * (int)gridDim.x) * UM_ROWS;
+                    for (int kc = 0; kc < s.KC; ++kc, ++b) {
+                        const int rs = b % s.raw_stages;
+                        const uint32_t rph = (uint32_t)(b / s.raw_stages) & 1u;
+                        mbar_wait(&rawempty[rs], rph ^ 1);
+                        uint8_t* rb = rawring + (size_t)rs * kRawBytes;
+                        mbar_arrive_expect_tx(&rawfull[rs], kRawBytes);
+                        if constexpr (tma_in_place<AOp>()) {
+                            tma_load_2d(rb, &aop.tmap_dy, kc * UM_KB, row0, &rawfull[rs]);
+                            tma_load_2d(rb + UM_BLOCK_FLOATS * 4, &aop.tmap, kc * UM_KB, row0, &rawfull[rs]);
+                        } else {
+                            tma_load_2d(rb, &aop.tmap, kc * UM_KB, row0, &rawfull[rs]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: EW warps; warp (quadrant ew, half hsel) owns chunks ch % (EW/4) == hsel
+        if constexpr (EW == 8) reg_inc<120>(); else reg_inc<192>();
+        constexpr int kSplit = EW / 4;                            // warps per lane quadrant
+        constexpr int kOwn = (UM_STAT_CHUNKS + kSplit) / kSplit;  // chunks a warp may own (N_TILE <= 224: 7 chunks)
+        const int ewi = warp - UM_EPI_WARP0;
+        const int ew = ewi & 3, hsel = ewi >> 2;
+        float* slab = stage + ewi * 32 * UM_STAGE_LD;
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        const int nchunks = (s.N_TILE + 31) / 32;
+        float s0[kOwn][4], s1[kOwn][4];
+#pragma unroll
+        for (int o = 0; o < kOwn; ++o)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s0[o][e] = 0.f; s1[o][e] = 0.f; }
+        float wq[8], wq_next[8];
+        auto load_weights = [&](int it, float (&dst)[8]) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int tile = (int)blockIdx.x + min(it, max(my_tiles - 1, 0)) * (int)gridDim.x;
+                const int r = phys(min(tile, ntiles - 1)) * UM_ROWS + ew * 32 + q * 4 + rsub;
+                dst[q] = Epi::kRowWeight ? epi.row_weight(it < my_tiles ? min(r, s.R) : s.R) : 0.f;
+            }
+        };
+        load_weights(0, wq_next);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int row0 = phys((int)blockIdx.x + it * (int)gridDim.x) * UM_ROWS + ew * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) wq[q] = wq_next[q];
+            if (Epi::kRowWeight) load_weights(it + 1, wq_next);
+            unsigned roff[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                roff[q] = (unsigned)(min(row0 + q * 4 + rsub, s.R - 1) * epi.row_stride() + s.n0 + c4);
+                asm volatile("" : "+r"(roff[q]));
+            }
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after_sync();
+            if (ewi == 0 && it == 0) MFT_MARK(12);                         // first accumulator ready
+            const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * UM_ACC_STRIDE;
+            uint32_t v[32];
+            uint2 pre[Epi::kPrefetch ? 2 : 1][8];
+            auto chunk_live = [&](int ch) { return ch * 32 + c4 < s.N_TILE && s.n0 + ch * 32 + c4 < s.N; };
+            auto load_pre = [&](int ch, uint2 (&dst)[8]) {
+                if (Epi::kPrefetch && chunk_live(ch)) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dst[q] = epi.prefetch(roff[q], ch * 32);
+                }
+            };
+            if (hsel < nchunks) {
+                tmem_ld_32x32(tbase + hsel * 32, v);
+                load_pre(hsel, pre[0]);
+            }
+#pragma unroll
+            for (int o = 0; o < kOwn; ++o) {
+                const int ch = o * kSplit + hsel;                 // this warp's o-th chunk
+                if (ch < nchunks) {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(slab + lane * UM_STAGE_LD + q * 4) =
+                            make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    __syncwarp();
+                    if (ch + kSplit < nchunks) {
+                        tmem_ld_32x32(tbase + (ch + kSplit) * 32, v);
+                        load_pre(ch + kSplit, pre[Epi::kPrefetch ? ((o + 1) & 1) : 0]);
+                    }
+                    const int cl = ch * 32 + c4;
+                    const int col = s.n0 + cl;
+                    if (cl < s.N_TILE && col < s.N) {
+                        const int nvalid = min(4, s.N - col);
+                        const typename Epi::Consts ec = epi.consts(col, aux_e);
+                        float4 a[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            a[q] = *reinterpret_cast<const float4*>(slab + (q * 4 + rsub) * UM_STAGE_LD + c4);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int r = row0 + q * 4 + rsub;
+                            epi.apply(roff[q], ch * 32, r < s.R, wq[q], col, a[q], pre[Epi::kPrefetch ? (o & 1) : 0][q],
+                                      nvalid, s0[o], s1[o], ec);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (ewi == 0 && it < 4) MFT_MARK(8 + it);                      // epilogue finished tile `it`
+        }
+        if (ewi == 0) MFT_MARK(6);
+        if (Epi::kStats) {
+            // every (quadrant, column) pair is owned by exactly one warp: [4][256] partials, no atomics
+            float* part0 = stage;
+            float* part1 = stage + 4 * 256;
+            named_bar_sync(1, EW * 32);                  // every epilogue warp is done with its slab
+#pragma unroll
+            for (int o = 0; o < kOwn; ++o) {
+                const int ch = o * kSplit + hsel;
+                if (ch < nchunks) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a0 = s0[o][e], a1 = s1[o][e];
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+                        const int cl = ch * 32 + c4 + e;
+                        if (lane < 8 && cl < 256) {
+                            part0[ew * 256 + cl] = a0;
+                            part1[ew * 256 + cl] = a1;
+                        }
+                    }
+                }
+            }
+            named_bar_sync(1, EW * 32);
+            for (int cl = tid - UM_EPI_WARP0 * 32; cl < s.N_TILE; cl += EW * 32)
+                if (s.n0 + cl < s.N)
+                    epi.commit(s.n0 + cl, part0[cl] + part0[256 + cl] + part0[512 + cl] + part0[768 + cl],
+                               part1[cl] + part1[256 + cl] + part1[512 + cl] + part1[768 + cl], aux_e);
+        }
+    }
+
+    if (warp == UM_EPI_WARP0) MFT_MARK(7);
+#undef MFT_MARK
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, UM_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ the rows kernel on CTA pairs
+// Same GEMM, same roles, same operand / epilogue functors as umma_rows_kernel, but the two CTAs of a cluster
+// share every tcgen05.mma (cta_group::2, M = 256: 128 rows of A per CTA, HALF of the weight rows per CTA).
+// What that buys is shared memory: the resident weight image -- 147 KB of the 227 KB for the 192 x 192 layers,
+// the reason those kernels had two A stages and the in-place dgrad 48 KB of loads in flight per SM -- halves, and
+// the freed 74 KB go into deeper rings (dgrad: five 24 KB stages in flight instead of two: that kernel is bound
+// by bytes in flight x HBM latency, profiles/r02_summary.md) and into producer GROUPS: the eight producer warps
+// form PG groups, group g builds K blocks g, g + PG, ... so that PG of the serial wait / LDS / transform / STS /
+// fence / arrive chains overlap (PG <= ring depth: a group may not run two barrier phases ahead).
+//
+// Protocol differences: `full` and `tempty` live in the LEADER's shared memory and count arrivals of both CTAs
+// (the peer arrives through the cluster window, release / acquire at cluster scope); `empty` and `tfull` are
+// per CTA and are signalled by the multicast commit; each CTA loads its weight half itself, the peer reports it
+// on `wpeer`.  Both CTAs walk the same number of 256-row super-tiles; a 128-row half past the end is produced
+// as zeros and stores nothing.
+template <class AOp, class Epi, int PG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
+umma_rows_pair_kernel(const __grid_constant__ AOp aop, const __grid_constant__ Epi epi, const float* __restrict__ wimg,
+                      const __grid_constant__ UmmaShape s) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int NH = s.N_TILE / 2;                              // weight rows held by this CTA
+    const uint32_t w_bytes = (uint32_t)s.KC * NH * 128;
+    float* Wsm = reinterpret_cast<float*>(smem);
+    float* Asm = reinterpret_cast<float*>(smem + w_bytes);
+    float* stage = Asm + (size_t)s.stages * UM_BLOCK_FLOATS;
+    float* aux_a = stage + UM_ROWS * UM_STAGE_LD;
+    float* aux_e = aux_a + 3 * kMaxC;
+    uint8_t* rawring = reinterpret_cast<uint8_t*>(aux_e + 4 * kMaxC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rawring + (size_t)s.raw_stages * UM_RAW_BYTES);
+    uint64_t* full = bars;            // [UM_MAX_PSTAGES]  leader's copy is the live one
+    uint64_t* empty = bars + 8;       // [UM_MAX_PSTAGES]  per CTA
+    uint64_t* tfull = bars + 16;      // [2] per CTA
+    uint64_t* tempty = bars + 18;     // [2] leader's copy is the live one
+    uint64_t* wbar = bars + 20;       // this CTA's weight half
+    uint64_t* wpeer = bars + 21;      // leader: the peer's weight half has landed
+    uint64_t* rawfull = bars + 22;    // [UM_MAX_RAW]
+    uint64_t* rawempty = bars + 30;   // [UM_MAX_RAW]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int nst = (s.R + 2 * UM_ROWS - 1) / (2 * UM_ROWS);          // 256-row super-tiles
+    const int my_tiles = pair < nst ? (nst - 1 - pair) / npairs + 1 : 0;
+    // first row of this CTA's half of the pair's i-th super-tile (serpentine direction as in umma_rows_kernel)
+    auto tile_row0 = [&](int i) {
+        const int t = 2 * (pair + i * npairs) + (int)rank;
+        return (s.reverse ? 2 * nst - 1 - t : t) * UM_ROWS;
+    };
+    constexpr int GW = UM_PROD_WARPS / PG;
+
+    if (tid == 0) {
+        for (int i = 0; i < UM_MAX_PSTAGES; ++i) {
+            mbar_init(&full[i], 2 * GW);            // one elected arrival per producer warp of the group, both CTAs
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < UM_MAX_RAW; ++i) {
+            mbar_init(&rawfull[i], 1);
+            mbar_init(&rawempty[i], GW);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 8);               // four epilogue warps in each CTA
+        }
+        mbar_init(wbar, 1);
+        mbar_init(wpeer, 1);
+        fence_mbar_init();
+    }
+    if (warp == UM_MMA_WARP) tmem_alloc2(tmem_slot, UM_TMEM_COLS);
+    tc_fence_before_sync();
+    cluster_sync_all();                                 // barrier inits of BOTH CTAs visible before any remote arrive
+    tc_fence_after_sync();
+    if (warp == UM_MMA_WARP && lane == 0) {
+        mbar_arrive_expect_tx(wbar, w_bytes);
+        const uint32_t blk = (uint32_t)NH * 128;         // this CTA's rows of one K block: a contiguous range of the image
+        for (int kc = 0; kc < s.KC; ++kc)
+            bulk_g2s(reinterpret_cast<uint8_t*>(Wsm) + (size_t)kc * blk,
+                     reinterpret_cast<const uint8_t*>(wimg) + ((size_t)kc * s.N_TILE + (size_t)rank * NH) * 128, blk, wbar);
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    aop.init(aux_a, tid, UM_THREADS);
+    epi.init(aux_e, tid, UM_THREADS);
+    __syncthreads();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < UM_PROD_WARPS) {
+        // ===================== producers (PG groups, see the header comment) =====================
+        reg_dec<96>();
+        constexpr int GT = UM_PROD_THREADS / PG;
+        constexpr int RQ = UM_ROWS * 8 / GT;
+        constexpr int RSTEP = GT / 8;
+        const int grp = tid / GT, gtid = tid - grp * GT;
+        const int rsub = gtid >> 3, c16 = gtid & 7;
+        const int sw = rsub & 7;
+        const int sw_off = sw * 32 + ((c16 ^ sw) << 2);
+        const int nblocks = my_tiles * s.KC;
+        const uint32_t full0 = mapa_shared(full, 0);         // the leader's `full` array in the cluster window
+        if constexpr (tma_in_place<AOp>()) {
+            constexpr int QB = RQ < 8 ? RQ : 8;
+            float wq[RQ];
+            int cur_ti = -1;
+            for (int b = grp; b < nblocks; b += PG) {
+                const int ti = b / s.KC, kc = b - ti * s.KC;
+                const int row0 = tile_row0(ti);
+                const bool partial = row0 + UM_ROWS > s.R;
+                if (ti != cur_ti) {
+                    cur_ti = ti;
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q) wq[q] = aop.row_weight(min(row0 + q * RSTEP + rsub, s.R));
+                }
+                const int st = b % s.stages;
+                const uint32_t ph = (uint32_t)(b / s.stages) & 1u;
+                mbar_wait(&rawfull[st], ph);
+                const uint8_t* rawb = rawring + (size_t)st * UM_RAW_BYTES;
+                float* blk = Asm + (size_t)st * UM_BLOCK_FLOATS;
+                const int k = kc * UM_KB + c16 * 4;
+                const typename AOp::Consts kc4 = aop.consts(k, aux_a);
+#pragma unroll
+                for (int q0 = 0; q0 < RQ; q0 += QB) {
+                    uint2 hraw[QB];
+                    float4 d[QB];
+#pragma unroll
+                    for (int q = 0; q < QB; ++q) {
+                        const int rl = (q0 + q) * RSTEP + rsub;
+                        hraw[q] = *reinterpret_cast<const uint2*>(rawb + rl * 64 + c16 * 8);
+                        d[q] = *reinterpret_cast<const float4*>(blk + (rl >> 3) * 256 + sw_off);
+                    }
+#pragma unroll
+                    for (int q = 0; q < QB; ++q) {
+                        const int rl = (q0 + q) * RSTEP + rsub;
+                        float4 v = aop.transform2(d[q], hraw[q], wq[q0 + q], kc4);
+                        if (partial && row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
+                        *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw_off) = v;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full0 + (uint32_t)st * 8u);
+            }
+        } else if constexpr (AOp::kTma) {
+            for (int b = grp; b < nblocks; b += PG) {
+                const int ti = b / s.KC, kc = b - ti * s.KC;
+                const int row0 = tile_row0(ti);
+                const bool partial = row0 + UM_ROWS > s.R;
+                const int rs = b % s.raw_stages;
+                const uint32_t rph = (uint32_t)(b / s.raw_stages) & 1u;
+                const int st = b % s.stages;
+                const uint32_t ph = (uint32_t)(b / s.stages) & 1u;
+                mbar_wait(&rawfull[rs], rph);
+                const uint8_t* rawb = rawring + (size_t)rs * UM_RAW_BYTES;
+                uint2 raw[RQ];
+#pragma unroll
+                for (int q = 0; q < RQ; ++q)
+                    raw[q] = *reinterpret_cast<const uint2*>(rawb + (q * RSTEP + rsub) * 64 + c16 * 8);
+                {   // release the raw slot on COMPLETION of the loads (see umma_rows_kernel)
+                    unsigned t = 0;
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q) t |= raw[q].x | raw[q].y;
+                    const unsigned z = __reduce_or_sync(0xffffffffu, t & s.zero);
+                    if (lane == 0) mbar_arrive_n(&rawempty[rs], 1u + z);
+                }
+                mbar_wait(&empty[st], ph ^ 1);
+                float* blk = Asm + (size_t)st * UM_BLOCK_FLOATS;
+                const int k = kc * UM_KB + c16 * 4;
+                const typename AOp::Consts kc4 = aop.consts(k, aux_a);
+#pragma unroll
+                for (int q = 0; q < RQ; ++q) {
+                    const int rl = q * RSTEP + rsub;
+                    float4 v = aop.transform(raw[q], kc4);
+                    if (partial && row0 + rl >= s.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
+                    *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw_off) = v;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full0 + (uint32_t)st * 8u);
+            }
+        } else {
+            constexpr int QB = RQ <= 4 ? RQ : 2;
+            constexpr int NB = RQ / QB;
+            typename AOp::Row rc[RQ];
+            uint32_t vrows = 0;
+            int cur_ti = -1;
+            for (int b = grp; b < nblocks; b += PG) {
+                const int ti = b / s.KC, kc = b - ti * s.KC;
+                const int row0 = tile_row0(ti);
+                if (ti != cur_ti) {
+                    cur_ti = ti;
+                    vrows = 0;
+#pragma unroll
+                    for (int q = 0; q < RQ; ++q) {
+                        const int r = row0 + q * RSTEP + rsub;
+                        const bool ok = r < s.R;
+                        vrows |= (ok ? 1u : 0u) << q;
+                        rc[q] = aop.row(ok ? r : 0);
+                    }
+                }
+                const int st = b % s.stages;
+                const uint32_t ph = (uint32_t)(b / s.stages) & 1u;
+                const int k = kc * UM_KB + c16 * 4;
+                typename AOp::Raw raw[2][QB];
+#pragma unroll
+                for (int q = 0; q < QB; ++q) aop.fetch(rc[q], k, raw[0][q]);
+                mbar_wait(&empty[st], ph ^ 1);
+                float* blk = Asm + (size_t)st * UM_BLOCK_FLOATS;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    if (i + 1 < NB) {
+#pragma unroll
+                        for (int q = 0; q < QB; ++q) aop.fetch(rc[(i + 1) * QB + q], k, raw[(i + 1) & 1][q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < QB; ++q) {
+                        const int qq = i * QB + q;
+                        const int rl = qq * RSTEP + rsub;
+                        float4 v = aop.finish(raw[i & 1][q], rc[qq], k, aux_a);
+                        if (!((vrows >> qq) & 1u)) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v.x = to_tf32_fast(v.x); v.y = to_tf32_fast(v.y); v.z = to_tf32_fast(v.z); v.w = to_tf32_fast(v.w);
+                        *reinterpret_cast<float4*>(blk + (rl >> 3) * 256 + sw_off) = v;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full0 + (uint32_t)st * 8u);
+            }
+        }
+    } else if (warp == UM_MMA_WARP) {
+        // ===================== MMA issuer: one thread of the LEADER =====================
+        if (lane == 0) {
+            mbar_wait(wbar, 0);                                            // own weight half
+            if (rank != 0) {
+                mbar_arrive_cluster(mapa_shared(wpeer, 0));                // tell the leader
+            } else {
+                mbar_wait_cluster(wpeer, 0);
+                const uint32_t blk = (uint32_t)NH * 128;
+                const uint32_t idesc = make_idesc_tf32(2 * UM_ROWS, s.N_TILE);
+                const int ksteps = (s.K + 7) / 8;
+                const uint32_t a0 = smem_u32(Asm), b0 = smem_u32(Wsm);
+                int b = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int acc = it & 1;
+                    const uint32_t aph = (it >> 1) & 1;
+                    mbar_wait_cluster(&tempty[acc], aph ^ 1);
+                    tc_fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + acc * UM_ACC_STRIDE;
+                    for (int kc = 0; kc < s.KC; ++kc, ++b) {
+                        const int st = b % s.stages;
+                        const uint32_t ph = (uint32_t)(b / s.stages) & 1u;
+                        mbar_wait_cluster(&full[st], ph);
+                        tc_fence_after_sync();
+                        const uint32_t ab = a0 + (uint32_t)st * (UM_BLOCK_FLOATS * 4);
+                        const uint32_t bb = b0 + (uint32_t)kc * blk;
+                        const int nks = min(4, ksteps - kc * 4);
+                        for (int ks = 0; ks < nks; ++ks)
+                            mma_tf32_ss2(d_tmem, make_desc_sw128(ab + ks * 32, 1024, 16),
+                                         make_desc_sw128(bb + ks * 32, 1024, 16), idesc, (kc | ks) != 0 ? 1u : 0u);
+                        mma_commit2(&empty[st]);
+                    }
+                    mma_commit2(&tfull[acc]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == UM_TMA_WARP) {
+        // ===================== TMA loader (one thread per CTA, its own rows) =====================
+        if constexpr (tma_in_place<AOp>()) {
+            if (lane == 0) {
+                tma_prefetch_desc(&aop.tmap);
+                tma_prefetch_desc(&aop.tmap_dy);
+                int b = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int row0 = tile_row0(it);
+                    for (int kc = 0; kc < s.KC; ++kc, ++b) {
+                        const int st = b % s.stages;
+                        const uint32_t ph = (uint32_t)(b / s.stages) & 1u;
+                        mbar_wait(&empty[st], ph ^ 1);
+                        mbar_arrive_expect_tx(&rawfull[st], UM_RAW_BYTES + UM_BLOCK_FLOATS * 4);
+                        tma_load_2d(Asm + (size_t)st * UM_BLOCK_FLOATS, &aop.tmap_dy, kc * UM_KB, row0, &rawfull[st]);
+                        tma_load_2d(rawring + (size_t)st * UM_RAW_BYTES, &aop.tmap, kc * UM_KB, row0, &rawfull[st]);
+                    }
+                }
+            }
+        } else if constexpr (AOp::kTma) {
+            if (lane == 0) {
+                tma_prefetch_desc(&aop.tmap);
+                int b = 0;
+                for (int it = 0; it < my_tiles; ++it) {
+                    const int row0 = tile_row0(it);
+                    for (int kc = 0; kc < s.KC; ++kc, ++b) {
+                        const int rs = b % s.raw_stages;
+                        const uint32_t rph = (uint32_t)(b / s.raw_stages) & 1u;
+                        mbar_wait(&rawempty[rs], rph ^ 1);
+                        mbar_arrive_expect_tx(&rawfull[rs], UM_RAW_BYTES);
+                        tma_load_2d(rawring + (size_t)rs * UM_RAW_BYTES, &aop.tmap, kc * UM_KB, row0, &rawfull[rs]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (as in umma_rows_kernel; tempty is the leader's) =====================
+        reg_inc<192>();
+        const int ew = warp & 3;
+        float* slab = stage + ew * 32 * UM_STAGE_LD;
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        const int nchunks = (s.N_TILE + 31) / 32;
+        const uint32_t tempty0 = mapa_shared(tempty, 0);
+        float s0[UM_STAT_CHUNKS][4], s1[UM_STAT_CHUNKS][4];
+#pragma unroll
+        for (int ch = 0; ch < UM_STAT_CHUNKS; ++ch)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s0[ch][e] = 0.f; s1[ch][e] = 0.f; }
+        float wq[8], wq_next[8];
+        auto load_weights = [&](int it, float (&dst)[8]) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = tile_row0(min(it, max(my_tiles - 1, 0))) + ew * 32 + q * 4 + rsub;
+                dst[q] = Epi::kRowWeight ? epi.row_weight(it < my_tiles ? min(r, s.R) : s.R) : 0.f;
+            }
+        };
+        load_weights(0, wq_next);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int row0 = tile_row0(it) + ew * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) wq[q] = wq_next[q];
+            if (Epi::kRowWeight) load_weights(it + 1, wq_next);
+            unsigned roff[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                roff[q] = (unsigned)(min(row0 + q * 4 + rsub, s.R - 1) * epi.row_stride() + s.n0 + c4);
+                asm volatile("" : "+r"(roff[q]));
+            }
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after_sync();
+            const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * UM_ACC_STRIDE;
+            uint32_t v[32];
+            uint2 pre[Epi::kPrefetch ? 2 : 1][8];
+            auto chunk_live = [&](int ch) { return ch * 32 + c4 < s.N_TILE && s.n0 + ch * 32 + c4 < s.N; };
+            auto load_pre = [&](int ch, uint2 (&dst)[8]) {
+                if (Epi::kPrefetch && chunk_live(ch)) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dst[q] = epi.prefetch(roff[q], ch * 32);
+                }
+            };
+            tmem_ld_32x32(tbase, v);
+            load_pre(0, pre[0]);
+#pragma unroll
+            for (int ch = 0; ch < UM_MAX_CHUNKS; ++ch) {
+                if (ch < nchunks) {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(slab + lane * UM_STAGE_LD + q * 4) =
+                            make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    __syncwarp();
+                    if (ch + 1 < nchunks) {
+                        tmem_ld_32x32(tbase + (ch + 1) * 32, v);
+                        load_pre(ch + 1, pre[Epi::kPrefetch ? ((ch + 1) & 1) : 0]);
+                    }
+                    const int cl = ch * 32 + c4;
+                    const int col = s.n0 + cl;
+                    if (cl < s.N_TILE && col < s.N) {
+                        const int nvalid = min(4, s.N - col);
+                        const typename Epi::Consts ec = epi.consts(col, aux_e);
+                        float4 a[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            a[q] = *reinterpret_cast<const float4*>(slab + (q * 4 + rsub) * UM_STAGE_LD + c4);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int r = row0 + q * 4 + rsub;
+                            epi.apply(roff[q], ch * 32, r < s.R, wq[q], col, a[q], pre[Epi::kPrefetch ? (ch & 1) : 0][q],
+                                      nvalid, s0[ch < UM_STAT_CHUNKS ? ch : 0], s1[ch < UM_STAT_CHUNKS ? ch : 0], ec);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty0 + (uint32_t)acc * 8u);
+        }
+        if (Epi::kStats) {
+            float* part0 = stage;
+            float* part1 = stage + 4 * 256;
+            named_bar_sync(1, 128);
+#pragma unroll
+            for (int ch = 0; ch < UM_STAT_CHUNKS; ++ch) {
+                if (ch < nchunks) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float a0 = s0[ch][e], a1 = s1[ch][e];
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 8);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+                        const int cl = ch * 32 + c4 + e;
+                        if (lane < 8 && cl < 256) {
+                            part0[ew * 256 + cl] = a0;
+                            part1[ew * 256 + cl] = a1;
+                        }
+                    }
+                }
+            }
+            named_bar_sync(1, 128);
+            for (int cl = tid - UM_EPI_WARP0 * 32; cl < s.N_TILE; cl += 128)
+                if (s.n0 + cl < s.N)
+                    epi.commit(s.n0 + cl, part0[cl] + part0[256 + cl] + part0[512 + cl] + part0[768 + cl],
+                               part1[cl] + part1[256 + cl] + part1[512 + cl] + part1[768 + cl], aux_e);
+        }
+    }
+
+    // neither CTA may leave (or free its TMEM) while the other can still reach into it
+    tc_fence_before_sync();
+    cluster_sync_all();
+    if (warp == UM_MMA_WARP) {
+        tc_fence_after_sync();
+        tmem_dealloc2(tmem_base, UM_TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------ wgrad kernel
 // dW[co, ci] = sum_r P(r, co) * Q(r, ci) over the CTA's slice of pair rows, accumulated in TMEM
 // for the whole kernel and added into global dW once at the end.
@@ -1637,13 +2493,44 @@ static int grid_cap() { return g_grid_limit > 0 ? min(g_grid_limit, num_sms()) :
 
 constexpr size_t kSmemLimit = 232448;   // 227 KB opt-in maximum per CTA on sm_100
 
+// Which rows kernel runs (MFT_ROWS_KERNEL): "base" (default) = umma_rows_kernel, "ts" = A operand in tensor memory
+// (umma_rows_ts_kernel), "pair" = CTA pairs (umma_rows_pair_kernel).  All three pass the same parity tests; on
+// B200 the base kernel is the fastest by 3-5 % (profiles/r02_summary.md: the three share their bottleneck, the
+// issue rate of the CUDA-core work around the MMA, ~23k warp instructions per 128-row tile).  Read once: the pass split of a layer
+// (and with it the layout of its weight image) depends on it.  A pass the chosen kernel cannot take (ts: more
+// than 224 output columns) is never planned: plan_pass() refuses it and the layer is split further.
+enum { ROWS_BASE = 0, ROWS_PAIR = 1, ROWS_TS = 2 };
+static int g_rows_mode = -1;
+static int rows_mode() {
+    if (g_rows_mode < 0) {
+        const char* e = getenv("MFT_ROWS_KERNEL");
+        g_rows_mode = ROWS_BASE;
+        if (e && !strcmp(e, "pair")) g_rows_mode = ROWS_PAIR;
+        if (e && !strcmp(e, "ts")) g_rows_mode = ROWS_TS;
+    }
+    return g_rows_mode;
+}
+static bool pair_mode() { return rows_mode() == ROWS_PAIR; }
+static inline size_t rows_smem_bytes(const UmmaShape& s) { return pair_mode() ? umma_smem_bytes_pair(s) : umma_smem_bytes(s); }
+
 static bool plan_pass(int N_TILE, int K, UmmaShape& s) {
     s.N_TILE = N_TILE;
     s.KC = (K + UM_KB - 1) / UM_KB;
     if (s.KC > UM_MAX_KC || N_TILE > UM_MAX_NTILE || (N_TILE % 16) != 0) return false;
+    s.raw_stages = 0;
+    if (rows_mode() == ROWS_TS) {
+        // resident weights + two raw slots of the widest operand (dy fp32 + H fp16 blocks of the dgrad)
+        if (N_TILE > UM_TS_MAX_NTILE) return false;
+        s.stages = ts_slots(N_TILE);
+        s.raw_stages = 2;
+        return umma_smem_bytes_ts<DhInPlaceT>(s) <= kSmemLimit;
+    }
     for (int st = UM_MAX_STAGES; st >= 2; --st) {
         s.stages = st;
-        if (umma_smem_bytes(s) <= kSmemLimit) return true;
+        // (the in-place dgrad operand needs a raw slot per stage: plan for at least two such pairs)
+        UmmaShape t = s;
+        if (pair_mode()) { t.stages = 2; t.raw_stages = 2; if (rows_smem_bytes(t) > kSmemLimit) return false; }
+        if (rows_smem_bytes(s) <= kSmemLimit) return true;
     }
     return false;
 }
@@ -1694,13 +2581,65 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
         const int dir = next_direction();
         UmmaShape s{};
         plan_pass(nts[p], K, s);
+        if (rows_mode() == ROWS_TS) {
+            s.R = R; s.N = N; s.n0 = n0s[p]; s.K = K; s.reverse = dir; s.zero = 0u; s.dbg = nullptr;
+            if (g_umma_dbg && g_umma_dbg_skip-- == 0) { s.dbg = g_umma_dbg; g_umma_dbg = nullptr; }
+            s.stages = ts_slots(s.N_TILE);
+            s.raw_stages = 0;
+            // eight epilogue warps where their second set of staging slabs still leaves room for the raw ring
+            // (the in-place dgrad operand: two 24 KB slots; the fp16 tape: four 8 KB slots) and the producers'
+            // register budget allows it (MFT_EPI_WARPS=4 forces four)
+            static const int ew_env = [] { const char* e = getenv("MFT_EPI_WARPS"); return e ? atoi(e) : 8; }();
+            int ew = (ew_env == 4 || tma_in_place<AOp>()) ? 4 : 8;
+            if (AOp::kTma) {
+                for (;;) {
+                    s.raw_stages = 0;
+                    for (int rs = UM_MAX_RAW; rs >= (ew == 8 ? 4 : 2); --rs) {
+                        s.raw_stages = rs;
+                        if (umma_smem_bytes_ts<AOp>(s, ew) <= kSmemLimit) break;
+                        s.raw_stages = 0;
+                    }
+                    if (s.raw_stages != 0 || ew == 4) break;
+                    ew = 4;
+                }
+                if (s.raw_stages == 0) {
+                    set_error(MFT_ERR_UNSUPPORTED, "umma_rows_gemm: no room for the raw ring (N=%d K=%d)", N, K);
+                    return MFT_ERR_UNSUPPORTED;
+                }
+            } else if (umma_smem_bytes_ts<AOp>(s, ew) > kSmemLimit) {
+                ew = 4;
+            }
+            float* img = wimg + (size_t)p * s.N_TILE * s.KC * UM_KB;
+            if (!prebuilt) {
+                ProfScope ps(PC_PREP, st);
+                int total = s.KC * s.N_TILE * UM_KB;
+                umma_weight_image_kernel<<<cdiv(total, 256), 256, 0, st>>>(W, ldw, transpose, N, K, s.n0, s.N_TILE,
+                                                                           s.KC, img);
+                MFT_CHECK_LAUNCH();
+            }
+            const size_t smem = umma_smem_bytes_ts<AOp>(s, ew);
+            ProfScope ps(cat, st);
+            const bool use_pdl = prebuilt && pdl_level() >= 1 && (pdl || p > 0);
+            if (ew == 8) {
+                MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_rows_ts_kernel<AOp, Epi, 8>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                MFT_CHECK_CUDA(launch_kernel(umma_rows_ts_kernel<AOp, Epi, 8>, dim3(grid), dim3((UM_PROD_WARPS + 10) * 32),
+                                             smem, st, use_pdl, aop, epi, (const float*)img, s));
+            } else {
+                MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_rows_ts_kernel<AOp, Epi, 4>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                MFT_CHECK_CUDA(launch_kernel(umma_rows_ts_kernel<AOp, Epi, 4>, dim3(grid), dim3(UM_THREADS), smem, st,
+                                             use_pdl, aop, epi, (const float*)img, s));
+            }
+            continue;
+        }
         if (tma_in_place<AOp>()) {
             // stage st and raw slot st travel together: as many as fit
             bool fit = false;
-            for (int stg = UM_MAX_STAGES; stg >= 2 && !fit; --stg) {
+            for (int stg = pair_mode() ? UM_MAX_PSTAGES : UM_MAX_STAGES; stg >= 2 && !fit; --stg) {
                 s.stages = stg;
                 s.raw_stages = stg;
-                fit = umma_smem_bytes(s) <= kSmemLimit;
+                fit = rows_smem_bytes(s) <= kSmemLimit;
             }
             if (!fit) {
                 set_error(MFT_ERR_UNSUPPORTED, "umma_rows_gemm: no room for in-place TMA stages (N=%d K=%d)", N, K);
@@ -1711,9 +2650,15 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
             // rest of shared memory to raw blocks in flight
             s.stages = 2;
             s.raw_stages = 0;
+            if (pair_mode()) {                       // four A stages (one per producer group) when four raw slots still fit
+                s.stages = 4;
+                s.raw_stages = 4;
+                if (rows_smem_bytes(s) > kSmemLimit) s.stages = 2;
+                s.raw_stages = 0;
+            }
             for (int rs = UM_MAX_RAW; rs >= 2; --rs) {
                 s.raw_stages = rs;
-                if (umma_smem_bytes(s) <= kSmemLimit) break;
+                if (rows_smem_bytes(s) <= kSmemLimit) break;
                 s.raw_stages = 0;
             }
             if (s.raw_stages == 0) {
@@ -1732,15 +2677,35 @@ static int umma_rows_gemm(const AOp& aop, const Epi& epi, const float* W, int ld
                                                                        s.KC, img);
             MFT_CHECK_LAUNCH();
         }
-        size_t smem = umma_smem_bytes(s);
+        size_t smem = rows_smem_bytes(s);
         static_assert(sizeof(AOp) + sizeof(Epi) < 3500, "kernel parameter space");
-        MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_rows_kernel<AOp, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
         ProfScope ps(cat, st);
         // a second pass follows the first pass of the same layer: same images, same convention
         const bool use_pdl = prebuilt && pdl_level() >= 1 && (pdl || p > 0);
-        MFT_CHECK_CUDA(launch_kernel(umma_rows_kernel<AOp, Epi>, dim3(grid), dim3(UM_THREADS), smem, st, use_pdl,
-                                     aop, epi, (const float*)img, s));
+        if (pair_mode()) {
+            const int nst = cdiv(R, 2 * UM_ROWS);
+            const int npairs = max(1, min(nst, grid_cap() / 2));
+            // producer groups: as many as every ring the role uses is deep (a group may not run two phases ahead)
+            int pg = 4;
+            if (!AOp::kTma) pg = 2;                   // register-fed operands: 16 rows of addresses per thread would spill
+            while (pg > 1 && (pg > s.stages || (AOp::kTma && !tma_in_place<AOp>() && pg > s.raw_stages))) pg >>= 1;
+#define MFT_PAIR_LAUNCH(PGV)                                                                                         \
+    do {                                                                                                             \
+        MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_rows_pair_kernel<AOp, Epi, PGV>,                                    \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        MFT_CHECK_CUDA(launch_kernel(umma_rows_pair_kernel<AOp, Epi, PGV>, dim3(2 * npairs), dim3(UM_THREADS), smem, \
+                                     st, use_pdl, aop, epi, (const float*)img, s));                                  \
+    } while (0)
+            if (pg == 4) MFT_PAIR_LAUNCH(4);
+            else if (pg == 2) MFT_PAIR_LAUNCH(2);
+            else MFT_PAIR_LAUNCH(1);
+#undef MFT_PAIR_LAUNCH
+        } else {
+            MFT_CHECK_CUDA(cudaFuncSetAttribute(umma_rows_kernel<AOp, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+            MFT_CHECK_CUDA(launch_kernel(umma_rows_kernel<AOp, Epi>, dim3(grid), dim3(UM_THREADS), smem, st, use_pdl,
+                                         aop, epi, (const float*)img, s));
+        }
     }
     return MFT_OK;
 }

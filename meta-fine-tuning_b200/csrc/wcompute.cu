@@ -934,13 +934,14 @@ wgrad_reduce_kernel(FinalizeArgs a) {
 static inline int row_grid(int R) { return min(cdiv(R, kRowWarps), 148 * 6); }
 static inline int row_grid8(int R) { return min(cdiv(R, kRowWarps * 4), 148 * 4); }   // four rows per warp
 
-WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace) {
+WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace, int precision) {
     WcLayout L;
     L.C[0] = F; L.C[1] = 2 * nf; L.C[2] = 2 * nf; L.C[3] = nf; L.C[4] = nf;
     int Rg = N * (N + 1) / 2;
     size_t R = (size_t)B * Rg;
     Carver sv(saved);
-    for (int k = 0; k < 4; ++k) L.H[k] = sv.take<float>(R * L.C[k + 1]);
+    const size_t esz = precision == MFT_PREC_TF32 ? sizeof(__half) : sizeof(float);   // the tensor-core path keeps an fp16 tape
+    for (int k = 0; k < 4; ++k) L.H[k] = reinterpret_cast<float*>(sv.take<char>(R * L.C[k + 1] * esz));
     L.fsums = sv.take<double>(4 * kStatSlot);
     L.tscale = sv.take<float>(64);
     L.saved_bytes = sv.used();
@@ -974,7 +975,7 @@ int wcompute_fwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params*
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_fwd: bad shape B=%d N=%d F=%d nf=%d", B, N, F, nf);
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_fwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
     MFT_REQUIRE(N < 32768, "wcompute_fwd: N=%d too large", N);
-    WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
+    WcLayout L = wc_layout(B, N, F, nf, saved, workspace, precision);
     NodeMask mask;
     const int n_shared = mask_from_host(shared_nodes, B, N, mask);
     PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared, L.roww, L.rowij);
@@ -995,7 +996,7 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_fwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
     MFT_REQUIRE(N < 32768, "wcompute_fwd: N=%d too large", N);
     MFT_REQUIRE(ldx >= F, "wcompute_fwd: ldx=%d < F=%d", ldx, F);
-    WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
+    WcLayout L = wc_layout(B, N, F, nf, saved, workspace, precision);
     NodeMask mask;
     const int n_shared = mask_from_host(shared_nodes, B, N, mask);
     PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared, L.roww, L.rowij);
@@ -1065,7 +1066,7 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
                  Branches* tail, int tail_slot) {
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_bwd: bad shape");
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_bwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
-    WcLayout L = wc_layout(B, N, F, nf, saved, workspace);
+    WcLayout L = wc_layout(B, N, F, nf, saved, workspace, precision);
     NodeMask mask;
     const int n_shared = mask_from_host(shared_nodes, B, N, mask);
     PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared, L.roww, L.rowij);

@@ -44,7 +44,8 @@ size_t umma_wimg_floats(int N, int K);
 int umma_debug_wgrad(const float* P, int ldp, const float* Q, int ldq, float* dW, int ldw, int R, int Cout,
                      int Cin, cudaStream_t st);
 
-WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace);
+// precision: MFT_PREC_TF32 sizes the activation tape H_1..H_4 for fp16 elements, anything else for fp32
+WcLayout wc_layout(int B, int N, int F, int nf, void* saved, void* workspace, int precision = MFT_PREC_FP32);
 
 // wcompute_fwd_prepare: everything of the forward that depends on the parameters and the shape only
 // (statistics slots zeroed, pair tables, the four tcgen05 weight images) -- gnn_fwd issues it for layer

@@ -189,7 +189,7 @@ class _WcomputeFn(torch.autograd.Function):
         p = _lib.WcomputeParams()
         _fill_wc_params(p, params)
         adj = torch.empty(B, N, N, dtype=torch.float32, device=x.device)
-        saved = _blob(lib.mft_wcompute_saved_bytes(B, N, F, nf), x.device)
+        saved = _blob(lib.mft_wcompute_saved_bytes_for(B, N, F, nf, prec), x.device)
         ws = _blob(lib.mft_wcompute_workspace_bytes(B, N, F, nf), x.device)
         with torch.cuda.device(x.device):
             _lib.check(lib.mft_wcompute_fwd(x.data_ptr(), F, B, N, F, nf, C.byref(p), adj.data_ptr(),
@@ -283,7 +283,7 @@ class _GnnFn(torch.autograd.Function):
         p = _lib.GnnParams()
         _pack_gnn(p, params, grads=False)
         out = torch.empty(B, N, n_way, dtype=torch.float32, device=x.device)
-        saved = _blob(lib.mft_gnn_saved_bytes(B, N, F0, nf, n_way), x.device)
+        saved = _blob(lib.mft_gnn_saved_bytes_for(B, N, F0, nf, n_way, prec), x.device)
         ws = _blob(lib.mft_gnn_workspace_bytes(B, N, F0, nf, n_way), x.device)
         with torch.cuda.device(x.device):
             _lib.check(lib.mft_gnn_fwd(x.data_ptr(), B, N, F0, nf, n_way, C.byref(p), out.data_ptr(),

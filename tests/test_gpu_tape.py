@@ -74,7 +74,7 @@ def _run_kernels(p, x, d_adj, mask):
     adj = m.adjacency(xg, shared)
     saved = adj.grad_fn.saved_tensors[2]
     off = (C.c_size_t * 8)()
-    _lib.check(lib.mft_debug_wcompute_saved_offsets(bsz, n, fin, NF, off), "offsets")
+    _lib.check(lib.mft_debug_wcompute_saved_offsets(bsz, n, fin, NF, _lib.PREC_TF32, off), "offsets")
     rb, ri, rj, w, allg = KM.pair_rows(bsz, n, None if mask is None else torch.from_numpy(mask))
     rows = rb.numel()
     widths = [2 * NF, 2 * NF, NF, NF]

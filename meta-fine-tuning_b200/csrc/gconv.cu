@@ -394,7 +394,8 @@ GcLayout gc_layout(int B, int N, int F, int n_out, void* saved, void* workspace)
     size_t rows = (size_t)B * N;
     Carver sv(saved);
     L.Y = sv.take<float>(rows * n_out);
-    L.fsums = sv.take<double>(kStatSlot);
+    L.fsums = sv.take<double>(kStatSlot + 64);
+    L.sync = reinterpret_cast<int*>(L.fsums + kStatSlot);
     L.saved_bytes = sv.used();
     Carver ws(workspace);
     L.UV = ws.take<float>(rows * 2 * n_out);
@@ -416,6 +417,11 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     const bool has_bn = p->bn_g != nullptr;
     MFT_REQUIRE(has_bn || !lrelu_on, "gconv_fwd: LeakyReLU without BatchNorm is not a reference configuration");
 
+    if (gconv_fused_supported(B, N, F, n_out)) {
+        // one launch (gconv_fused.cu); statistics slot and barrier counters cleared by one memset
+        MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * (kStatSlot + 64), st));
+        return gconv_fused_fwd(adj, x, ldx, B, N, F, n_out, p, lrelu_on, out, ldo, L.Y, L.UV, L.fsums, L.sync, st);
+    }
     // V = x Wa^T -> Y ;  U = x Wb^T ;  Y += adj U   (three small batched GEMMs), then one pass adds the
     // bias and accumulates the BatchNorm1d statistics, and one applies BN + LeakyReLU.
     const bool direct = !has_bn;                     // no BN: the result goes straight to `out`

@@ -81,6 +81,7 @@ int wcompute_wgrad_layer_tf32(int k, const float* dh, const float* x, int ldx, i
 struct GcLayout {
     float* Y;            // saved: pre-BN Gconv output [B*N, n_out]
     double* fsums;       // saved: BN1d statistics [2*kMaxC]
+    int* sync;           // saved (right behind fsums: one memset clears both): barrier counters of the fused kernels
     float* UV;           // workspace fwd: x [Wa;Wb]^T  [B*N, 2 n_out]
     float* dY;           // workspace bwd: [B*N, n_out]
     float* AX;           // workspace bwd: adj x  [B*N, F]
@@ -96,6 +97,11 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
 int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
               int lrelu, const float* d_out, int ldo, float* dx, float* d_adj, const mft_gconv_grads* g,
               void* saved, void* workspace, cudaStream_t st);
+
+// gconv_fused.cu: the whole Gconv forward in one launch (spin barriers between its phases)
+int gconv_fused_supported(int B, int N, int F, int n_out);
+int gconv_fused_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
+                    int lrelu_on, float* out, int ldo, float* Y, float* V, double* fsums, int* sync, cudaStream_t st);
 
 int query_ce(const float* out, int n_way, int n_support, int n_query, float* loss, float* d_out, cudaStream_t st);
 

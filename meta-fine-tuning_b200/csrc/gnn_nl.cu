@@ -73,6 +73,9 @@ int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_g
     MFT_REQUIRE(B > 0 && N > 0 && F0 > 0 && nf >= 2 && (nf % 2) == 0 && n_way > 0, "gnn_fwd: bad shape");
     GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace, precision);
     const int rows = B * N;
+    // (the node buffer's not-yet-written columns are read -- and masked -- by the 16-byte loads of the |x_i - x_j|
+    // producers at the K tail: give them defined values)
+    MFT_CHECK_CUDA(cudaMemsetAsync(G.xcat, 0, sizeof(float) * (size_t)rows * G.ldx, st));
     MFT_CHECK_CUDA(cudaMemcpy2DAsync(G.xcat, sizeof(float) * G.ldx, x, sizeof(float) * F0, sizeof(float) * F0,
                                      rows, cudaMemcpyDeviceToDevice, st));
     // later layers see per-graph features: only layer 0 may share support pairs

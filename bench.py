@@ -365,8 +365,28 @@ def run_eval(args, world, rank, dev, lib, mft_b200):
     feats = [synthetic_features(args.shape, 10 + e, "cpu", n_query).pin_memory() for e in mine[:64]]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    # the forward of one episode as a CUDA graph (features in a static buffer, accuracy out): the eager forward is
+    # ~60 launches, which would make the sweep bound by the host's launch rate, not by the GPU
+    static_f = feats[0].to(dev)
+    use_graph = not args.no_graph
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                head.set_forward(static_f)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph), torch.no_grad():
+            static_acc = (head.set_forward(static_f).argmax(1) == y).float().mean()
+
     def episode(f):
         with torch.no_grad():
+            if use_graph:
+                static_f.copy_(f, non_blocking=True)
+                graph.replay()
+                return static_acc.clone()
             scores = head.set_forward(f.to(dev, non_blocking=True))
             return (scores.argmax(1) == y).float().mean()
 
@@ -390,6 +410,12 @@ def run_eval(args, world, rank, dev, lib, mft_b200):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     launches = lib.mft_launch_count() - l0
+    if use_graph:                                # a replay does not pass through the library's launch counter
+        with torch.no_grad():
+            c0 = lib.mft_launch_count()
+            head.set_forward(static_f)
+            torch.cuda.synchronize()
+            launches = (lib.mft_launch_count() - c0) * len(mine)
     clocks = sampler.stop()
     acc_all = parallel.gather_episode_results(acc_local, n_episodes, rank, world, device=dev)
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
@@ -407,7 +433,8 @@ def run_eval(args, world, rank, dev, lib, mft_b200):
                        "episodes": n_episodes, "parallelism": f"episode-sharded eval, episode e on rank e % {world}, "
                        "no data-path collective; one all-reduce gather of the accuracies at the end",
                        "l2": "256 MiB fill every 8 episodes", "timing": "CUDA events around the rank's share, "
-                       "host features -> H2D -> fc -> graphs -> GNN_nl -> argmax, accuracies read back once; max over ranks"},
+                       "host features -> H2D -> fc -> graphs -> GNN_nl -> argmax, accuracies read back once; max over ranks",
+                       "launch": "CUDA graph replay of the forward" if use_graph else "eager launches"},
             "clocks": clocks, "gpu_launches": int(t[1]),
             "accuracy": {"mean": mean, "ci95": ci, "note": "synthetic features, random-init weights: chance level"},
         })

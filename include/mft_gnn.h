@@ -29,6 +29,13 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* Threading / streams.  Calls are ordered on the stream passed in and never synchronise the device.  Inside a call
+ * independent kernels run on library-owned side streams (three per DEVICE, created on first use) that are forked
+ * from and joined back into the caller's stream with events before the call returns.  The side streams and their
+ * events are shared by every caller of a device: drive a device from ONE host thread and ONE caller stream at a
+ * time (the one-process-per-GPU model of this library); two calls in flight on different caller streams of the
+ * same device would re-record the same events.  mft_set_*, the grid-limit used by the backward and the profile
+ * switches are process-global for the same reason. */
 #ifdef __cplusplus
 extern "C" {
 #endif

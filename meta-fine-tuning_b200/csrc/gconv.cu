@@ -2,7 +2,8 @@
 // Replaces gmul + Gconv.forward of the reference (methods/gnn.py:16-28, 43-56).
 // The identity operator of gmul is never multiplied out, and A (x Wb^T) is
 // evaluated as written there instead of (A x) Wb^T: same result, the N x N
-// product runs on n_out (48 or n_way) columns instead of F (133..229).
+// product runs on n_out (48 or n_way) columns instead of F (133..229).  The backward
+// uses the same association (see gconv_bwd), which is why x Wb^T is part of the saved state.
 #include "common.cuh"
 #include "simt_gemm.cuh"
 #include "wcompute.cuh"
@@ -148,17 +149,6 @@ __global__ void gconv_small_grads_kernel(const double* bsums, int n_out, int has
         fc_b[c] = (float)stat_get(bsums, n_out, c, 0);
     }
 }
-
-// dx[r, f] += DU[r, f]   (the identity operator of gmul)
-__global__ void add_cols_kernel(float* __restrict__ dx, int ldx, const float* __restrict__ src, int lds, int rows,
-                                int F) {
-    int total = rows * F;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        int r = idx / F, f = idx - r * F;
-        dx[(size_t)r * ldx + f] += src[(size_t)r * lds + f];
-    }
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // Pre-head of GnnNet: fc = Linear(feat_dim -> D) + BatchNorm1d over the n_way*(n_support+n_query)
@@ -396,13 +386,13 @@ GcLayout gc_layout(int B, int N, int F, int n_out, void* saved, void* workspace)
     L.Y = sv.take<float>(rows * n_out);
     L.fsums = sv.take<double>(kStatSlot + 64);
     L.sync = reinterpret_cast<int*>(L.fsums + kStatSlot);
+    L.XWb = sv.take<float>(rows * n_out);
     L.saved_bytes = sv.used();
     Carver ws(workspace);
-    L.UV = ws.take<float>(rows * 2 * n_out);
     L.dY = ws.take<float>(rows * n_out);
-    L.AX = ws.take<float>(rows * F);
-    L.DU = ws.take<float>(rows * 2 * F);
+    L.T = ws.take<float>(rows * n_out);
     L.bsums = ws.take<double>(kStatSlot);
+    (void)F;
     L.workspace_bytes = ws.used();
     return L;
 }
@@ -420,7 +410,7 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     if (gconv_fused_supported(B, N, F, n_out)) {
         // one launch (gconv_fused.cu); statistics slot and barrier counters cleared by one memset
         MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * (kStatSlot + 64), st));
-        return gconv_fused_fwd(adj, x, ldx, B, N, F, n_out, p, lrelu_on, out, ldo, L.Y, L.UV, L.fsums, L.sync, st);
+        return gconv_fused_fwd(adj, x, ldx, B, N, F, n_out, p, lrelu_on, out, ldo, L.Y, L.XWb, L.fsums, L.sync, st);
     }
     // V = x Wa^T -> Y ;  U = x Wb^T ;  Y += adj U   (three small batched GEMMs), then one pass adds the
     // bias and accumulates the BatchNorm1d statistics, and one applies BN + LeakyReLU.
@@ -433,14 +423,14 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     {
         Branches br(st);                             // the two products with x are independent
         cudaStream_t s1 = br.fork(0);
-        { ProfScope ps(PC_GCONV_FWD, s1); MFT_CHECK_CUDA(launch_bgemm(X, Wb, L.UV, 0, n_out, 1, rows, n_out, F, 0.f, s1)); }
+        { ProfScope ps(PC_GCONV_FWD, s1); MFT_CHECK_CUDA(launch_bgemm(X, Wb, L.XWb, 0, n_out, 1, rows, n_out, F, 0.f, s1)); }
         { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wa, Y, 0, ldy, 1, rows, n_out, F, 0.f, st)); }
         br.join(0);
         MFT_REQUIRE(br.ok(), "gconv_fwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     {
         BView Am{adj, (long)N * N, N, 1};            // (m = i, k = j)
-        BView Um{L.UV, (long)N * n_out, n_out, 1};   // (k = j, n = c)
+        BView Um{L.XWb, (long)N * n_out, n_out, 1};  // (k = j, n = c)
         ProfScope ps(PC_GCONV_FWD, st);
         MFT_CHECK_CUDA(launch_bgemm(Am, Um, Y, (long)N * ldy, ldy, B, N, n_out, N, 1.f, st));
     }
@@ -470,20 +460,16 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     const int rows = B * N;
     const int has_bn = p->bn_g != nullptr;
 
-    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * kStatSlot, st));
     MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)n_out * 2 * F, st));
-    // Three chains besides the main one:
-    //   side 0:  AX = adj x (needs no gradient: starts at once) -> [after dY] small grads, d fc.weight[:, F:] = dY^T AX
-    //   side 1:  [after dY] d fc.weight[:, :F] = dY^T x ; then (after DU) d_adj = DU2 x^T
-    //   main  :  dZ -> dY -> DU = dY W  ->  dx += DU1 + adj^T DU2
-    Branches br(st);
-    cudaStream_t s0 = br.fork(0);
-    {
-        // AX = adj x   [B*N, F]
-        BView A{adj, (long)N * N, N, 1};
-        BView X{x, (long)N * ldx, ldx, 1};
-        { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA(launch_bgemm(A, X, L.AX, (long)N * F, F, B, N, F, N, 0.f, s0)); }
-    }
+    // With Y = x Wa^T + adj (x Wb^T) + b every product of the backward runs on n_out (48 or n_way) columns or
+    // over K = n_out, never on F x N:
+    //   T     = adj^T dY                         [B][N, n_out]   (K = N)
+    //   dx   += dY Wa + T Wb                     one launch, K = 2 n_out
+    //   d_adj = dY (x Wb^T)^T                    [B][N, N]       (K = n_out; x Wb^T saved by the forward)
+    //   dWa   = dY^T x,  dWb = (adj x)^T dY = T^T x
+    //   main  :  dZ -> dY -> T -> dx
+    //   side 1:  [after dY] d_adj ; dWa            side 0:  [after T] dWb ; small grads
+    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * kStatSlot, st));
     dim3 blk(kGcCols, kGcRows);
     { ProfScope ps(PC_GCONV_BWD, st); gconv_dz_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(d_out, ldo, L.Y, rows, n_out, L.fsums, p->bn_g, p->bn_b,
                                                           has_bn, lrelu_on, L.dY, L.bsums);
@@ -494,48 +480,44 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
                                                                         L.bsums);
         MFT_CHECK_LAUNCH(); }
     }
-    br.sync_to_main(0);                              // dY and the reductions exist
-    cudaStream_t s1 = br.fork(1);
-    { ProfScope ps(PC_GCONV_BWD, s0); gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, s0>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
-    MFT_CHECK_LAUNCH(); }
+    Branches br(st);
+    cudaStream_t s1 = br.fork(1);                    // dY and the reductions exist
     PlainOp dy{L.dY, n_out};
-    {
-        PlainOp qax{L.AX, F};
-        { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA((launch_gemm_tn(dy, qax, g->fc_w + F, 2 * F, n_out, F, rows, s0))); }
-    }
-    {
-        PlainOp qx{x, ldx};
-        { ProfScope ps(PC_GCONV_BWD, s1); MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, s1))); }
-    }
-
-    // DU = dY W  [B*N, 2F]: first half feeds the identity operator, second half the adjacency
-    {
-        BView Dy{L.dY, 0, n_out, 1};                 // (m = row, k = c)
-        BView Wf{p->fc_w, 0, 2 * F, 1};              // (k = c, n = f') -> fc_w[c*2F + f']
+    PlainOp qx{x, ldx};
+    // the main chain is enqueued first: the replayed graph dispatches in this order, and a side product put
+    // ahead of `dx` held it back until the side product had drained (measured: 12 us)
+    {   // T[b,j,c] = sum_i adj[b,i,j] dY[b,i,c]
+        BView At{adj, (long)N * N, 1, N};                       // (m = j, k = i) -> adj[b, i, j]
+        BView Dy{L.dY, (long)N * n_out, n_out, 1};              // (k = i, n = c)
         ProfScope ps(PC_GCONV_BWD, st);
-        MFT_CHECK_CUDA(launch_bgemm(Dy, Wf, L.DU, 0, 2 * F, 1, rows, 2 * F, n_out, 0.f, st));
+        MFT_CHECK_CUDA(launch_bgemm(At, Dy, L.T, (long)N * n_out, n_out, B, N, n_out, N, 0.f, st));
     }
-    br.sync_to_main(1);                              // side 1 continues once DU exists
-    // d_adj[b,i,j] = sum_f DU2[b,i,f] x[b,j,f]
-    {
-        BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (m=i, k=f)
-        BView Xt{x, (long)N * ldx, 1, ldx};                     // (k=f, n=j) -> x[b, j, f]
-        { ProfScope ps(PC_GCONV_BWD, s1); MFT_CHECK_CUDA(launch_bgemm(D2, Xt, d_adj, (long)N * N, N, B, N, N, F, 0.f, s1)); }
-    }
-    // dx += DU1 + adj^T DU2
-    {
-        BView At{adj, (long)N * N, 1, N};                       // (m=j, k=i) -> adj[b, i, j]
-        BView D2{L.DU + F, (long)N * 2 * F, 2 * F, 1};          // (k=i, n=f)
-        if (bgemm_takes_addend(N)) {                            // DU1 rides along as the product's addend
+    cudaStream_t s0 = br.fork(0);                    // T exists
+    {   // dx[r, f] += sum_c dY[r,c] fc_w[c, f] + sum_c T[r,c] fc_w[c, F + f]
+        BView Dy{L.dY, 0, n_out, 1};                 // (m = row, k = c)
+        BView Tt{L.T, 0, n_out, 1};
+        BView Wa{p->fc_w, 0, 2 * F, 1};              // (k = c, n = f)
+        BView Wb{p->fc_w + F, 0, 2 * F, 1};
+        if (bgemm2_supported(n_out, n_out)) {
             ProfScope ps(PC_GCONV_BWD, st);
-            MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st, L.DU, (long)N * 2 * F, 2 * F));
+            MFT_CHECK_CUDA(launch_bgemm2(Dy, Wa, n_out, Tt, Wb, n_out, dx, 0, ldx, 1, rows, F, 1.f, st));
         } else {
-            int total = rows * F;
-            { ProfScope ps(PC_GCONV_BWD, st); add_cols_kernel<<<min(cdiv(total, 256), 148 * 4), 256, 0, st>>>(dx, ldx, L.DU, 2 * F, rows, F);
-            MFT_CHECK_LAUNCH(); }
-            { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(At, D2, dx, (long)N * ldx, ldx, B, N, F, N, 1.f, st)); }
+            { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(Dy, Wa, dx, 0, ldx, 1, rows, F, n_out, 1.f, st)); }
+            { ProfScope ps(PC_GCONV_BWD, st); MFT_CHECK_CUDA(launch_bgemm(Tt, Wb, dx, 0, ldx, 1, rows, F, n_out, 1.f, st)); }
         }
     }
+    {   // d_adj[b,i,j] = sum_c dY[b,i,c] (x Wb^T)[b,j,c]
+        BView Dy{L.dY, (long)N * n_out, n_out, 1};              // (m = i, k = c)
+        BView Ut{L.XWb, (long)N * n_out, 1, n_out};             // (k = c, n = j) -> XWb[b, j, c]
+        { ProfScope ps(PC_GCONV_BWD, s1); MFT_CHECK_CUDA(launch_bgemm(Dy, Ut, d_adj, (long)N * N, N, B, N, N, n_out, 0.f, s1)); }
+        { ProfScope ps(PC_GCONV_BWD, s1); MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, s1))); }
+    }
+    {
+        PlainOp tt{L.T, n_out};
+        { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA((launch_gemm_tn(tt, qx, g->fc_w + F, 2 * F, n_out, F, rows, s0))); }
+    }
+    { ProfScope ps(PC_GCONV_BWD, s0); gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, s0>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
+    MFT_CHECK_LAUNCH(); }
     br.join(0);
     br.join(1);
     MFT_REQUIRE(br.ok(), "gconv_bwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -166,15 +166,9 @@ __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, boo
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
-bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int M, int N, int K, float beta,
-                     const float* __restrict__ addend, long sadd, int ldadd) {
-    extern __shared__ float os_smem[];
-    const int lda = K | 1;                       // odd row stride: conflict-free column walks
-    float* As = os_smem;                         // [32][lda]  (m, k)
-    float* Bs = os_smem + OS_T * lda;            // [K][32]    (k, n)
-    const int b = blockIdx.z;
-    const int m0 = blockIdx.y * OS_T, n0 = blockIdx.x * OS_T;
+// Panels of one (A, B) pair into shared memory, columns [kofs, kofs + K) of the concatenated K axis.
+__device__ __forceinline__ void os_fill(const BView& A, const BView& Bm, int b, int m0, int n0, int M, int N, int K,
+                                        int kofs, int lda, float* As, float* Bs, bool b_n_fast) {
     const int t = threadIdx.x;
     const float* Ab = A.p + (size_t)b * A.sb;
     const float* Bb = Bm.p + (size_t)b * Bm.sb;
@@ -184,28 +178,46 @@ bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc
         for (int m = wrp; m < OS_T; m += 8) {
             const bool ok = m0 + m < M;
             const float* src = Ab + (size_t)(ok ? m0 + m : 0) * A.s0;
-            for (int k = lane; k < K; k += 32) cp_async4(As + m * lda + k, src + k, ok);
+            for (int k = lane; k < K; k += 32) cp_async4(As + m * lda + kofs + k, src + k, ok);
         }
     } else {                                     // m contiguous (or general strides)
         for (int idx = t; idx < total; idx += 256) {
             const int k = idx >> 5, m = idx & 31;
             const bool ok = m0 + m < M;
-            cp_async4(As + m * lda + k, Ab + (size_t)(ok ? m0 + m : 0) * A.s0 + (size_t)k * A.s1, ok);
+            cp_async4(As + m * lda + kofs + k, Ab + (size_t)(ok ? m0 + m : 0) * A.s0 + (size_t)k * A.s1, ok);
         }
     }
-    if (Bm.s1 == 1) {                            // n contiguous
+    if (b_n_fast) {                              // n contiguous
         for (int idx = t; idx < total; idx += 256) {
             const int k = idx >> 5, n = idx & 31;
             const bool ok = n0 + n < N;
-            cp_async4(Bs + k * OS_T + n, Bb + (size_t)k * Bm.s0 + (ok ? n0 + n : 0), ok);
+            cp_async4(Bs + (kofs + k) * OS_T + n, Bb + (size_t)k * Bm.s0 + (size_t)(ok ? n0 + n : 0) * Bm.s1, ok);
         }
     } else {                                     // k contiguous (or general strides): a warp walks along a column;
         for (int n = wrp; n < OS_T; n += 8) {    // the panel is kept [n][k] (odd stride) so that neither these
             const bool ok = n0 + n < N;          // writes nor the reads below conflict on banks
             const float* src = Bb + (size_t)(ok ? n0 + n : 0) * Bm.s1;
-            for (int k = lane; k < K; k += 32) cp_async4(Bs + n * lda + k, src + (size_t)k * Bm.s0, ok);
+            for (int k = lane; k < K; k += 32) cp_async4(Bs + n * lda + kofs + k, src + (size_t)k * Bm.s0, ok);
         }
     }
+}
+
+// C = beta C + A B (+ A2 B2) (+ addend): the second pair extends the K axis (K2 = 0: none), so a sum of two
+// products costs one launch and one pass over C.
+__global__ void __launch_bounds__(256)
+bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc, int M, int N, int K, float beta,
+                     const float* __restrict__ addend, long sadd, int ldadd, BView A2, BView B2, int K2) {
+    extern __shared__ float os_smem[];
+    const int KT = K + K2;
+    const int lda = KT | 1;                      // odd row stride: conflict-free column walks
+    float* As = os_smem;                         // [32][lda]  (m, k)
+    float* Bs = os_smem + OS_T * lda;            // [KT][32]   (k, n)   or [32][lda] (n, k)
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.y * OS_T, n0 = blockIdx.x * OS_T;
+    const int t = threadIdx.x;
+    const bool b_n_fast = Bm.s1 == 1 && (K2 == 0 || B2.s1 == 1);
+    os_fill(A, Bm, b, m0, n0, M, N, K, 0, lda, As, Bs, b_n_fast);
+    if (K2 > 0) os_fill(A2, B2, b, m0, n0, M, N, K2, K, lda, As, Bs, b_n_fast);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -213,10 +225,10 @@ bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc
     const float* a0 = As + (2 * ty) * lda;
     const float* a1 = a0 + lda;
     float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
-    if (Bm.s1 == 1) {                            // B panel [k][n]
+    if (b_n_fast) {                              // B panel [k][n]
         const float* bp = Bs + 2 * tx;
 #pragma unroll 8
-        for (int k = 0; k < K; ++k) {
+        for (int k = 0; k < KT; ++k) {
             const float x0 = a0[k], x1 = a1[k];
             const float2 y = *reinterpret_cast<const float2*>(bp + k * OS_T);
             c00 = fmaf(x0, y.x, c00); c01 = fmaf(x0, y.y, c01);
@@ -226,7 +238,7 @@ bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc
         const float* b0 = Bs + (2 * tx) * lda;
         const float* b1 = b0 + lda;
 #pragma unroll 8
-        for (int k = 0; k < K; ++k) {
+        for (int k = 0; k < KT; ++k) {
             const float x0 = a0[k], x1 = a1[k];
             const float y0 = b0[k], y1 = b1[k];
             c00 = fmaf(x0, y0, c00); c01 = fmaf(x0, y1, c01);
@@ -253,25 +265,39 @@ bgemm_oneshot_kernel(BView A, BView Bm, float* __restrict__ C, long scb, int ldc
 
 bool bgemm_takes_addend(int K) { return K >= 1 && K <= OS_MAXK; }
 
+static cudaError_t launch_oneshot(BView A, BView Bm, float* C, long scb, int ldc, int batch, int M, int N, int K,
+                                  float beta, cudaStream_t st, const float* addend, long sadd, int ldadd, BView A2,
+                                  BView B2, int K2) {
+    static bool attr_set = false;
+    const size_t max_smem = (size_t)(2 * OS_T * (OS_MAXK | 1)) * sizeof(float);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(bgemm_oneshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)max_smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const size_t smem = (size_t)(2 * OS_T * ((K + K2) | 1)) * sizeof(float);
+    dim3 grid(cdiv(N, OS_T), cdiv(M, OS_T), batch);
+    bgemm_oneshot_kernel<<<grid, 256, smem, st>>>(A, Bm, C, scb, ldc, M, N, K, beta, addend, sadd, ldadd, A2, B2, K2);
+    return cudaGetLastError();
+}
+
+// C[b] = beta * C[b] + A[b] B[b] + A2[b] B2[b]: both products in one launch (K + K2 <= 512)
+cudaError_t launch_bgemm2(BView A, BView Bm, int K, BView A2, BView B2, int K2, float* C, long scb, int ldc,
+                          int batch, int M, int N, float beta, cudaStream_t st) {
+    if (batch <= 0 || M <= 0 || N <= 0) return cudaSuccess;
+    if (K < 1 || K2 < 1 || K + K2 > OS_MAXK) return cudaErrorInvalidValue;
+    return launch_oneshot(A, Bm, C, scb, ldc, batch, M, N, K, beta, st, nullptr, 0, 0, A2, B2, K2);
+}
+bool bgemm2_supported(int K, int K2) { return K >= 1 && K2 >= 1 && K + K2 <= OS_MAXK; }
+
 // C[b] = beta * C[b] + A[b] B[b] (+ addend[b], one-shot path only: see bgemm_takes_addend)
 cudaError_t launch_bgemm(BView A, BView Bm, float* C, long scb, int ldc, int batch, int M, int N, int K,
                          float beta, cudaStream_t st, const float* addend, long sadd, int ldadd) {
     if (batch <= 0 || M <= 0 || N <= 0) return cudaSuccess;
     if (addend && !bgemm_takes_addend(K)) return cudaErrorInvalidValue;
-    if (K >= 1 && K <= OS_MAXK) {
-        static bool attr_set = false;
-        const size_t max_smem = (size_t)(2 * OS_T * (OS_MAXK | 1)) * sizeof(float);
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(bgemm_oneshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)max_smem);
-            if (e != cudaSuccess) return e;
-            attr_set = true;
-        }
-        const size_t smem = (size_t)(2 * OS_T * (K | 1)) * sizeof(float);
-        dim3 grid(cdiv(N, OS_T), cdiv(M, OS_T), batch);
-        bgemm_oneshot_kernel<<<grid, 256, smem, st>>>(A, Bm, C, scb, ldc, M, N, K, beta, addend, sadd, ldadd);
-        return cudaGetLastError();
-    }
+    if (K >= 1 && K <= OS_MAXK)
+        return launch_oneshot(A, Bm, C, scb, ldc, batch, M, N, K, beta, st, addend, sadd, ldadd, BView{}, BView{}, 0);
     if (M >= 48 && N >= 40) {
         dim3 grid(cdiv(N, BG2_T), cdiv(M, BG2_T), batch);
         bgemm64_kernel<<<grid, 256, 0, st>>>(A, Bm, C, scb, ldc, M, N, K, beta);

@@ -301,5 +301,9 @@ __global__ void bgemm_kernel(BView A, BView Bm, float* __restrict__ C, long scb,
 bool bgemm_takes_addend(int K);
 cudaError_t launch_bgemm(BView A, BView Bm, float* C, long scb, int ldc, int batch, int M, int N, int K,
                          float beta, cudaStream_t st, const float* addend = nullptr, long sadd = 0, int ldadd = 0);
+// C[b] = beta * C[b] + A[b] B[b] + A2[b] B2[b] in one launch, where bgemm2_supported(K, K2)
+bool bgemm2_supported(int K, int K2);
+cudaError_t launch_bgemm2(BView A, BView Bm, int K, BView A2, BView B2, int K2, float* C, long scb, int ldc,
+                          int batch, int M, int N, float beta, cudaStream_t st);
 
 }  // namespace mft

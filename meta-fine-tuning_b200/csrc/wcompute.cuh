@@ -82,10 +82,9 @@ struct GcLayout {
     float* Y;            // saved: pre-BN Gconv output [B*N, n_out]
     double* fsums;       // saved: BN1d statistics [2*kMaxC]
     int* sync;           // saved (right behind fsums: one memset clears both): barrier counters of the fused kernels
-    float* UV;           // workspace fwd: x [Wa;Wb]^T  [B*N, 2 n_out]
+    float* XWb;          // saved: x Wb^T [B*N, n_out], the operand of the adjacency product (d_adj = dY (x Wb^T)^T)
     float* dY;           // workspace bwd: [B*N, n_out]
-    float* AX;           // workspace bwd: adj x  [B*N, F]
-    float* DU;           // workspace bwd: dY W   [B*N, 2F]
+    float* T;            // workspace bwd: adj^T dY  [B*N, n_out]
     double* bsums;       // workspace bwd: [2*kMaxC] + fc bias sums [kMaxC]
     size_t saved_bytes, workspace_bytes;
 };

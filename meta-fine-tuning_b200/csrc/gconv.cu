@@ -397,44 +397,45 @@ GcLayout gc_layout(int B, int N, int F, int n_out, void* saved, void* workspace)
     return L;
 }
 
-int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
-              int lrelu_on, float* out, int ldo, void* saved, void* workspace, cudaStream_t st) {
-    MFT_REQUIRE(B > 0 && N > 0 && F > 0 && n_out > 0, "gconv_fwd: bad shape");
-    MFT_REQUIRE(n_out <= kMaxC, "gconv_fwd: n_out=%d exceeds %d", n_out, kMaxC);
-    MFT_REQUIRE(ldx >= F && ldo >= n_out, "gconv_fwd: bad leading dimensions");
-    GcLayout L = gc_layout(B, N, F, n_out, saved, workspace);
+// Everything of the forward that needs no adjacency: x Wa^T -> Y (or `out` for the BN-less last layer),
+// x Wb^T -> XWb, statistics slot cleared.  gnn_fwd runs it on a side stream beside the score / softmax kernels of
+// the Wcompute that produces this layer's adjacency.
+int gconv_fwd_products(const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
+                       float* out, int ldo, void* saved, cudaStream_t st) {
+    GcLayout L = gc_layout(B, N, F, n_out, saved, nullptr);
     const int rows = B * N;
     const bool has_bn = p->bn_g != nullptr;
-    MFT_REQUIRE(has_bn || !lrelu_on, "gconv_fwd: LeakyReLU without BatchNorm is not a reference configuration");
-
-    if (gconv_fused_supported(B, N, F, n_out)) {
-        // one launch (gconv_fused.cu); statistics slot and barrier counters cleared by one memset
-        MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * (kStatSlot + 64), st));
-        return gconv_fused_fwd(adj, x, ldx, B, N, F, n_out, p, lrelu_on, out, ldo, L.Y, L.XWb, L.fsums, L.sync, st);
+    BView X{x, 0, ldx, 1};                           // (m = row, k = f)
+    if (has_bn) {
+        MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * kStatSlot, st));
+        // both products in one launch: "batch" h selects the half of fc.weight and the output buffer
+        BView W{p->fc_w, (long)F, 1, 2 * F};         // (k = f, n = c) -> fc_w[c*2F + h*F + f]
+        ProfScope ps(PC_GCONV_FWD, st);
+        MFT_CHECK_CUDA(launch_bgemm(X, W, L.Y, (long)(L.XWb - L.Y), n_out, 2, rows, n_out, F, 0.f, st));
+    } else {
+        BView Wa{p->fc_w, 0, 1, 2 * F};
+        BView Wb{p->fc_w + F, 0, 1, 2 * F};
+        { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wa, out, 0, ldo, 1, rows, n_out, F, 0.f, st)); }
+        { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wb, L.XWb, 0, n_out, 1, rows, n_out, F, 0.f, st)); }
     }
-    // V = x Wa^T -> Y ;  U = x Wb^T ;  Y += adj U   (three small batched GEMMs), then one pass adds the
-    // bias and accumulates the BatchNorm1d statistics, and one applies BN + LeakyReLU.
+    return MFT_OK;
+}
+
+// Y += adj (x Wb^T); one pass adds the bias and accumulates the BatchNorm1d statistics, one applies BN + LeakyReLU.
+int gconv_fwd_finish(const float* adj, int B, int N, int F, int n_out, const mft_gconv_params* p, int lrelu_on,
+                     float* out, int ldo, void* saved, cudaStream_t st) {
+    GcLayout L = gc_layout(B, N, F, n_out, saved, nullptr);
+    const int rows = B * N;
+    const bool has_bn = p->bn_g != nullptr;
     const bool direct = !has_bn;                     // no BN: the result goes straight to `out`
     float* Y = direct ? out : L.Y;
     const int ldy = direct ? ldo : n_out;
-    BView X{x, 0, ldx, 1};                           // (m = row, k = f)
-    BView Wa{p->fc_w, 0, 1, 2 * F};                  // (k = f, n = c) -> fc_w[c*2F + f]
-    BView Wb{p->fc_w + F, 0, 1, 2 * F};
-    {
-        Branches br(st);                             // the two products with x are independent
-        cudaStream_t s1 = br.fork(0);
-        { ProfScope ps(PC_GCONV_FWD, s1); MFT_CHECK_CUDA(launch_bgemm(X, Wb, L.XWb, 0, n_out, 1, rows, n_out, F, 0.f, s1)); }
-        { ProfScope ps(PC_GCONV_FWD, st); MFT_CHECK_CUDA(launch_bgemm(X, Wa, Y, 0, ldy, 1, rows, n_out, F, 0.f, st)); }
-        br.join(0);
-        MFT_REQUIRE(br.ok(), "gconv_fwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
     {
         BView Am{adj, (long)N * N, N, 1};            // (m = i, k = j)
         BView Um{L.XWb, (long)N * n_out, n_out, 1};  // (k = j, n = c)
         ProfScope ps(PC_GCONV_FWD, st);
         MFT_CHECK_CUDA(launch_bgemm(Am, Um, Y, (long)N * ldy, ldy, B, N, n_out, N, 1.f, st));
     }
-    if (has_bn) MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * kStatSlot, st));
     {
         ProfScope ps(PC_GCONV_FWD, st);
         gconv_bias_stats_kernel<<<cdiv(rows, kGcRows), dim3(kGcCols, kGcRows), 0, st>>>(Y, ldy, p->fc_b, rows, n_out,
@@ -449,6 +450,29 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
         MFT_CHECK_LAUNCH();
     }
     return MFT_OK;
+}
+
+int gconv_fwd_check(int B, int N, int F, int n_out, int ldx, int ldo, const mft_gconv_params* p, int lrelu_on) {
+    MFT_REQUIRE(B > 0 && N > 0 && F > 0 && n_out > 0, "gconv_fwd: bad shape");
+    MFT_REQUIRE(n_out <= kMaxC, "gconv_fwd: n_out=%d exceeds %d", n_out, kMaxC);
+    MFT_REQUIRE(ldx >= F && ldo >= n_out, "gconv_fwd: bad leading dimensions");
+    MFT_REQUIRE(p->bn_g != nullptr || !lrelu_on, "gconv_fwd: LeakyReLU without BatchNorm is not a reference configuration");
+    return MFT_OK;
+}
+
+int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
+              int lrelu_on, float* out, int ldo, void* saved, void* workspace, cudaStream_t st) {
+    int rc = gconv_fwd_check(B, N, F, n_out, ldx, ldo, p, lrelu_on);
+    if (rc != MFT_OK) return rc;
+    if (gconv_fused_supported(B, N, F, n_out)) {
+        // one launch (gconv_fused.cu); statistics slot and barrier counters cleared by one memset
+        GcLayout L = gc_layout(B, N, F, n_out, saved, workspace);
+        MFT_CHECK_CUDA(cudaMemsetAsync(L.fsums, 0, sizeof(double) * (kStatSlot + 64), st));
+        return gconv_fused_fwd(adj, x, ldx, B, N, F, n_out, p, lrelu_on, out, ldo, L.Y, L.XWb, L.fsums, L.sync, st);
+    }
+    rc = gconv_fwd_products(x, ldx, B, N, F, n_out, p, out, ldo, saved, st);
+    if (rc != MFT_OK) return rc;
+    return gconv_fwd_finish(adj, B, N, F, n_out, p, lrelu_on, out, ldo, saved, st);
 }
 
 int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,

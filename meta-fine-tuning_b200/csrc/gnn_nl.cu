@@ -68,6 +68,15 @@ size_t gnn_workspace_bytes(int B, int N, int F0, int nf, int n_way) {
     return gnn_layout(B, N, F0, nf, n_way, nullptr, nullptr).workspace_bytes;
 }
 
+static bool gconv_hoist() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MFT_GCONV_HOIST");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+
 int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_gnn_params* p, float* out,
             void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st) {
     MFT_REQUIRE(B > 0 && N > 0 && F0 > 0 && nf >= 2 && (nf % 2) == 0 && n_way > 0, "gnn_fwd: bad shape");
@@ -87,24 +96,40 @@ int gnn_fwd(const float* x, int B, int N, int F0, int nf, int n_way, const mft_g
     if (rc != MFT_OK) return rc;
     Branches br(st);
     for (int l = 0; l < G.L; ++l) {
+        const bool last = (l == G.L - 1);
+        float* dst = last ? out : G.xcat + G.F[l];
+        int ldo = last ? n_way : G.ldx;
+        // The Gconv's two products with x need no adjacency: they run on side stream 3, forked inside wcompute_fwd
+        // behind the fourth conv layer, i.e. beside the score / softmax kernels (not for the one-launch Gconv).
+        const bool hoist = gconv_hoist() && !gconv_fused_supported(B, N, G.F[l], G.nout[l]);
         {
             ProfScope span(PC_SPAN_WC_FWD, st, false);
             rc = wcompute_fwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.wc_saved[l], G.wc_ws,
-                              precision, l == 0 ? shared_nodes : nullptr, st, true);
+                              precision, l == 0 ? shared_nodes : nullptr, st, true, hoist ? &br : nullptr, 3);
         }
         if (rc != MFT_OK) return rc;
-        const bool last = (l == G.L - 1);
+        if (hoist) {
+            rc = gconv_fwd_check(B, N, G.F[l], G.nout[l], G.ldx, ldo, &p->l[l], last ? 0 : 1);
+            if (rc == MFT_OK)
+                rc = gconv_fwd_products(G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], dst, ldo, G.gc_saved[l],
+                                        br.stream(3));
+            if (rc != MFT_OK) return rc;
+        }
         if (!last) {
             // tables and weight images of the next Wcompute (parameters only) beside this layer's Gconv
             rc = prepare(l + 1, br.fork(2));
             if (rc != MFT_OK) return rc;
         }
-        float* dst = last ? out : G.xcat + G.F[l];
-        int ldo = last ? n_way : G.ldx;
         {
             ProfScope span(PC_SPAN_GC_FWD, st, false);
-            rc = gconv_fwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, dst, ldo,
-                           G.gc_saved[l], G.gc_ws, st);
+            if (hoist) {
+                br.join(3);
+                rc = gconv_fwd_finish(G.adj[l], B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, dst, ldo,
+                                      G.gc_saved[l], st);
+            } else {
+                rc = gconv_fwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, dst, ldo,
+                               G.gc_saved[l], G.gc_ws, st);
+            }
             if (rc != MFT_OK) return rc;
             br.join(2);
         }

@@ -160,6 +160,11 @@ cudaStream_t Branches::fork(int i) {
     return p->s[i];
 }
 
+cudaStream_t Branches::stream(int i) const {
+    SidePool* p = static_cast<SidePool*>(pool_);
+    return p ? p->s[i] : main_;
+}
+
 void Branches::join(int i) {
     SidePool* p = static_cast<SidePool*>(pool_);
     if (!p || !forked_[i]) return;

@@ -47,7 +47,7 @@ struct ProfScope {
 // ---------------------------------------------------------------------------------------------
 namespace mft {
 
-constexpr int kSideStreams = 3;   // 0, 1: inside one Wcompute / Gconv call; 2: gnn_fwd / gnn_bwd across calls
+constexpr int kSideStreams = 4;   // 0, 1: inside one Wcompute / Gconv call; 2, 3: gnn_fwd / gnn_bwd across calls
 
 class Branches {
 public:
@@ -55,6 +55,8 @@ public:
     bool ok() const { return ok_; }
     // side stream i, ordered after everything enqueued on the main stream so far
     cudaStream_t fork(int i);
+    // side stream i as it is (forked or not)
+    cudaStream_t stream(int i) const;
     // make side stream i wait for the main stream's work enqueued so far
     void sync_to_main(int i);
     // main stream waits for side stream i

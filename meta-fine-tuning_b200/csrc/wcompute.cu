@@ -991,7 +991,7 @@ int wcompute_fwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params*
 
 int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p, float* adj,
                  void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st,
-                 bool prepared) {
+                 bool prepared, Branches* mid, int mid_slot) {
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_fwd: bad shape B=%d N=%d F=%d nf=%d", B, N, F, nf);
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_fwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
     MFT_REQUIRE(N < 32768, "wcompute_fwd: N=%d too large", N);
@@ -1025,6 +1025,7 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
             }
         }
     }
+    if (mid) mid->fork(mid_slot);
     {
         ProfScope ps(PC_SCORE, st);
 #define MFT_SCORE(HALF, SHARED)                                                                                   \

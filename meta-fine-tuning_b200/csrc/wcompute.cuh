@@ -54,7 +54,9 @@ int wcompute_fwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params*
                          int precision, const unsigned char* shared_nodes, cudaStream_t st);
 int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p, float* adj,
                  void* saved, void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st,
-                 bool prepared = false);
+                 bool prepared = false, class Branches* mid = nullptr, int mid_slot = 0);
+// mid: side stream `mid_slot` of *mid is forked once the four conv layers are enqueued, i.e. beside the score and
+// softmax kernels, which leave most of the chip idle (gnn_fwd puts the next Gconv's x W products there).
 // tail_st: stream for the kernels that only finish parameter gradients (finalize_grads, wgrad_reduce);
 // when it differs from st the caller has ordered it after st's work so far and joins it before the
 // workspace is reused (gnn_bwd runs them under the next layer's Gconv backward).
@@ -93,6 +95,12 @@ GcLayout gc_layout(int B, int N, int F, int n_out, void* saved, void* workspace)
 
 int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
               int lrelu, float* out, int ldo, void* saved, void* workspace, cudaStream_t st);
+// the two halves of gconv_fwd (not for the one-launch variant): what needs no adjacency, and the rest
+int gconv_fwd_check(int B, int N, int F, int n_out, int ldx, int ldo, const mft_gconv_params* p, int lrelu);
+int gconv_fwd_products(const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
+                       float* out, int ldo, void* saved, cudaStream_t st);
+int gconv_fwd_finish(const float* adj, int B, int N, int F, int n_out, const mft_gconv_params* p, int lrelu,
+                     float* out, int ldo, void* saved, cudaStream_t st);
 int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
               int lrelu, const float* d_out, int ldo, float* dx, float* d_adj, const mft_gconv_grads* g,
               void* saved, void* workspace, cudaStream_t st);

@@ -1135,11 +1135,16 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     // buffers rotate so that dgrad_{k-1} never writes what wgrad_k is still reading; wgrads alternate between
     // two side streams and dgrad_{k-2} joins the one wgrad_k ran on.  MFT_BWD_SPLIT=0 restores the serial order.
     static const int split_env = [] { const char* e = getenv("MFT_BWD_SPLIT"); return e ? atoi(e) : 1; }();
-    const bool split = precision == MFT_PREC_TF32 && split_env != 0 && g.R >= 16 * 128 * 4;
-    // SMs of the wgrad kernels (the dgrad chain gets the rest): half by default, MFT_BWD_SPLIT=<count> overrides
-    // (measured on B200, 5w20s / 5w50c: 40 % of the SMs for the wgrads is the optimum -- the dgrad chain is the
-    // critical path, the wgrads only have to keep up: profiles/r02_summary.md)
-    const int wg_sms = split_env >= 8 ? min(split_env, umma_num_sms() - 8) : (umma_num_sms() * 2) / 5;
+    static const int small_env = [] { const char* e = getenv("MFT_BWD_SPLIT_SMALL"); return e ? atoi(e) : 1; }();
+    const int sms = umma_num_sms();
+    const int tiles = (g.R + 127) / 128;             // CTAs a dgrad launch can use
+    const bool one_wave = small_env != 0 && tiles <= sms - 40;
+    const bool split = precision == MFT_PREC_TF32 && split_env != 0 && (g.R >= 16 * 128 * 4 || one_wave);
+    // SMs of the wgrad kernels (the dgrad chain gets the rest): MFT_BWD_SPLIT=<count> overrides.  Many tiles
+    // (measured on B200, 5w20s / 5w50c): 40 % of the SMs for the wgrads is the optimum -- the dgrad chain is the
+    // critical path, the wgrads only have to keep up (profiles/r02_summary.md).  A dgrad launch that fits in one wave
+    // (5w5s: 58 tiles; the shared-support layer_w0 of 5w20s: 104) keeps one SM per tile and the wgrads get the rest.
+    const int wg_sms = split_env >= 8 ? min(split_env, sms - 8) : (one_wave ? sms - tiles : (sms * 2) / 5);
     ProfScope* region = precision == MFT_PREC_TF32 ? new ProfScope(PC_BWD_REGION, st, false) : nullptr;
     Branches wb(st);
     float* bufs[3] = {L.dyA, L.dyB, L.dyC};

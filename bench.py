@@ -67,6 +67,24 @@ def gemm_traffic(shape, share, prec):
     return None
 
 
+def hbm_view(shape, share, prec, ms_per_step, hbm_gbs):
+    """The step seen from the memory side: DRAM bytes of one step (committed `ncu` capture, every kernel profiled
+    alone) over the measured step time, against the measured copy bandwidth.  None without a matching capture."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")))
+    except (OSError, ValueError):
+        return None
+    step = rec.get("step")
+    if not step or rec.get("config") != {"shape": shape, "share_support": bool(share), "precision": prec}:
+        return None
+    total = step["dram_read_bytes"] + step["dram_write_bytes"]
+    gbs = total / (ms_per_step / 1e3) / 1e9
+    return {"dram_bytes_per_step": total, "achieved_gbs_on_step": gbs, "hbm_peak_gbs": hbm_gbs,
+            "frac_of_hbm_peak_on_step": gbs / hbm_gbs if hbm_gbs else None,
+            "note": "upper bound (cold-L2, serialised capture); the step is bound by neither roof alone: see "
+                    "DESIGN.md 4.4"}
+
+
 def shape_dims(shape, n_query=None):
     n_way, n_shot, nq, compress = SHAPES[shape]
     k = round(n_shot / 2) if compress else n_shot
@@ -712,6 +730,7 @@ def run_ours(args):
                 "bound": "tensor", "achieved": achieved, "peak": tf32["burst"], "unit": "TFLOP/s",
                 "frac": (achieved / tf32["burst"]) if achieved else None,
                 "traffic": gemm_traffic(args.shape, not args.no_share, prec),
+                "hbm_view": hbm_view(args.shape, not args.no_share, prec, ms_per_step, peaks.get("hbm_gbs")),
                 "kernel": "edge-MLP GEMM launches (4 fwd + 4 dgrad + 4 wgrad per Wcompute, x3); time = forward launch "
                           "durations + span of each Wcompute's overlapped wgrad/dgrad region",
                 "gemm_ms_per_step": gemm_ms,

@@ -1,7 +1,9 @@
 """Turn an `ncu --page raw --csv` export (with dram__bytes_read.sum / dram__bytes_write.sum) into
 profiles/<name>_gemm_traffic.json: average DRAM bytes per edge-MLP GEMM launch (the kernels
 bench.py's `roofline` object describes) plus a per-kernel table for profiles/r01_summary.md.
-usage: python tools/ncu_traffic.py raw.csv out.json"""
+Also the whole capture's DRAM bytes ("step": the capture is one eager step of the head) for the HBM view of the
+step in bench.py's `roofline.hbm_view`.
+usage: python tools/ncu_traffic.py raw.csv out.json [shape share_support(0|1) precision]"""
 import collections
 import csv
 import json
@@ -41,6 +43,17 @@ def main():
                            "dram_write_MB": round(v[2] / v[0] / 1e6, 2), "avg_us": round(v[3] / v[0], 1)}
                        for k, v in sorted(per.items(), key=lambda kv: -kv[1][3])},
     }
+    out["step"] = {
+        "launches": sum(v[0] for v in per.values()),
+        "dram_read_bytes": sum(v[1] for v in per.values()),
+        "dram_write_bytes": sum(v[2] for v in per.values()),
+        "kernel_time_us_serialised": sum(v[3] for v in per.values()),
+        "what": "every library kernel of ONE eager step, each launch profiled alone with a cold L2: an upper bound of "
+                "the replayed step's DRAM reads (concurrent wgrad / dgrad launches share dy and H through the L2); "
+                "write-backs that leave the L2 after a kernel ended are not attributed",
+    }
+    if len(sys.argv) > 5:
+        out["config"] = {"shape": sys.argv[3], "share_support": bool(int(sys.argv[4])), "precision": sys.argv[5]}
     json.dump(out, open(sys.argv[2], "w"), indent=1)
     print(json.dumps({k: out[k] for k in ("bytes_per_launch", "launches")}))
 

@@ -38,20 +38,31 @@ def test_wcompute_module_alone(prec, tol):
     mft_b200.set_precision("auto")
 
 
-def test_gconv_module_alone_forward_backward():
+@pytest.mark.parametrize("fin,nout,bsz,n,bn_bool", [(37, 12, 3, 9, True), (133, 48, 16, 30, True), (229, 48, 4, 105, True),
+                                                    (229, 5, 4, 105, False), (70, 33, 2, 41, True), (181, 5, 3, 30, False)])
+def test_gconv_module_alone_forward_backward(fin, nout, bsz, n, bn_bool):
+    """Gconv alone, incl. the real widths and the BN-less last layer: output, input / adjacency gradients and every
+    parameter gradient against the float64 oracle (the backward runs on n_out-wide products and needs the x Wb^T
+    the forward saved; a non-multiple-of-32 everything exercises the tile edges of the dual-K product)."""
     import mft_b200
-    fin, nout, bsz, n = 37, 12, 3, 9
     g = torch.Generator().manual_seed(3)
     adj = torch.softmax(torch.randn(bsz, n, n, generator=g, dtype=torch.float64), dim=2)
     eye = torch.eye(n, dtype=torch.float64).expand(bsz, n, n)
     W = torch.stack([eye, adj], dim=3)
     x = torch.randn(bsz, n, fin, generator=g, dtype=torch.float64)
-    m = mft_b200.Gconv(fin, nout, 2).cuda()
-    p = {"l.fc.weight": m.fc.weight.detach().double().cpu(), "l.fc.bias": m.fc.bias.detach().double().cpu(),
-         "l.bn.weight": m.bn.weight.detach().double().cpu(), "l.bn.bias": m.bn.bias.detach().double().cpu()}
+    m = mft_b200.Gconv(fin, nout, 2, bn_bool=bn_bool).cuda()
+    with torch.no_grad():
+        if bn_bool:
+            m.bn.weight.uniform_(0.5, 1.5)
+            m.bn.bias.uniform_(-0.5, 0.5)
+    p = {"l.fc.weight": m.fc.weight.detach().double().cpu().requires_grad_(True),
+         "l.fc.bias": m.fc.bias.detach().double().cpu().requires_grad_(True)}
+    if bn_bool:
+        p["l.bn.weight"] = m.bn.weight.detach().double().cpu().requires_grad_(True)
+        p["l.bn.bias"] = m.bn.bias.detach().double().cpu().requires_grad_(True)
     xr = x.clone().requires_grad_(True)
     Wr = W.clone().requires_grad_(True)
-    ref = O.gconv(Wr, xr, p, "l.")
+    ref = O.gconv(Wr, xr, p, "l.", bn_bool=bn_bool)
     proj = torch.randn(ref.shape, generator=g, dtype=torch.float64)
     (ref * proj).sum().backward()
     xg = x.float().cuda().requires_grad_(True)
@@ -62,6 +73,13 @@ def test_gconv_module_alone_forward_backward():
     assert U.rel(out.detach().cpu().numpy(), ref.detach().numpy()) < 5e-6
     assert U.rel(xg.grad.cpu().numpy(), xr.grad.numpy()) < 5e-5
     assert U.rel(Wg.grad[..., 1].cpu().numpy(), Wr.grad[..., 1].numpy()) < 5e-5
+    assert U.rel(m.fc.weight.grad.cpu().numpy(), p["l.fc.weight"].grad.numpy()) < 5e-5
+    if bn_bool:
+        assert U.rel(m.bn.weight.grad.cpu().numpy(), p["l.bn.weight"].grad.numpy()) < 5e-5
+        assert U.rel(m.bn.bias.grad.cpu().numpy(), p["l.bn.bias"].grad.numpy()) < 5e-5
+        assert float(m.fc.bias.grad.abs().max()) == 0.0      # BatchNorm1d removes the mean
+    else:
+        assert U.rel(m.fc.bias.grad.cpu().numpy(), p["l.fc.bias"].grad.numpy()) < 5e-5
 
 
 def test_inference_modes_and_copies_agree():
@@ -279,7 +297,7 @@ def test_fused_query_cross_entropy_equals_torch(n_support, n_query):
     loss_b = torch.nn.functional.cross_entropy(E.select_scores(b, n_way, n_support, n_query),
                                                E.query_labels(n_way, n_query).cuda())
     (loss_b * 1.7).backward()
-    assert abs(float(loss_a) - float(loss_b)) < 2e-6 * max(1.0, abs(float(loss_b)))
+    assert abs(float(loss_a.detach()) - float(loss_b.detach())) < 2e-6 * max(1.0, abs(float(loss_b.detach())))
     assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-8)
     sup = torch.ones(n, dtype=torch.bool)
     sup[n_support::n_support + 1] = False

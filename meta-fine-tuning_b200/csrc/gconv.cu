@@ -477,7 +477,7 @@ int gconv_fwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
 
 int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
               int lrelu_on, const float* d_out, int ldo, float* dx, float* d_adj, const mft_gconv_grads* g,
-              void* saved, void* workspace, cudaStream_t st) {
+              void* saved, void* workspace, cudaStream_t st, Branches* late, int late_slot) {
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && n_out > 0, "gconv_bwd: bad shape");
     MFT_REQUIRE(n_out <= kMaxC, "gconv_bwd: n_out=%d exceeds %d", n_out, kMaxC);
     GcLayout L = gc_layout(B, N, F, n_out, saved, workspace);
@@ -492,7 +492,7 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     //   d_adj = dY (x Wb^T)^T                    [B][N, N]       (K = n_out; x Wb^T saved by the forward)
     //   dWa   = dY^T x,  dWb = (adj x)^T dY = T^T x
     //   main  :  dZ -> dY -> T -> dx
-    //   side 1:  [after dY] d_adj ; dWa            side 0:  [after T] dWb ; small grads
+    //   side 1:  [after dY] d_adj ; small grads    late (or side 0 / 1): [after T] dWb ; dWa
     MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * kStatSlot, st));
     dim3 blk(kGcCols, kGcRows);
     { ProfScope ps(PC_GCONV_BWD, st); gconv_dz_kernel<<<cdiv(rows, kGcRows), blk, 0, st>>>(d_out, ldo, L.Y, rows, n_out, L.fsums, p->bn_g, p->bn_b,
@@ -516,7 +516,8 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
         ProfScope ps(PC_GCONV_BWD, st);
         MFT_CHECK_CUDA(launch_bgemm(At, Dy, L.T, (long)N * n_out, n_out, B, N, n_out, N, 0.f, st));
     }
-    cudaStream_t s0 = br.fork(0);                    // T exists
+    // the two weight-gradient products: nothing downstream of this call reads them
+    cudaStream_t sw_a = late ? late->fork(late_slot) : br.fork(0);       // T and dY exist
     {   // dx[r, f] += sum_c dY[r,c] fc_w[c, f] + sum_c T[r,c] fc_w[c, F + f]
         BView Dy{L.dY, 0, n_out, 1};                 // (m = row, k = c)
         BView Tt{L.T, 0, n_out, 1};
@@ -534,14 +535,15 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
         BView Dy{L.dY, (long)N * n_out, n_out, 1};              // (m = i, k = c)
         BView Ut{L.XWb, (long)N * n_out, 1, n_out};             // (k = c, n = j) -> XWb[b, j, c]
         { ProfScope ps(PC_GCONV_BWD, s1); MFT_CHECK_CUDA(launch_bgemm(Dy, Ut, d_adj, (long)N * N, N, B, N, N, n_out, 0.f, s1)); }
-        { ProfScope ps(PC_GCONV_BWD, s1); MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, s1))); }
     }
+    { ProfScope ps(PC_GCONV_BWD, s1); gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, s1>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
+    MFT_CHECK_LAUNCH(); }
     {
         PlainOp tt{L.T, n_out};
-        { ProfScope ps(PC_GCONV_BWD, s0); MFT_CHECK_CUDA((launch_gemm_tn(tt, qx, g->fc_w + F, 2 * F, n_out, F, rows, s0))); }
+        cudaStream_t sw_b = late ? sw_a : s1;                             // without a late stream: one product per side stream
+        { ProfScope ps(PC_GCONV_BWD, sw_a); MFT_CHECK_CUDA((launch_gemm_tn(tt, qx, g->fc_w + F, 2 * F, n_out, F, rows, sw_a))); }
+        { ProfScope ps(PC_GCONV_BWD, sw_b); MFT_CHECK_CUDA((launch_gemm_tn(dy, qx, g->fc_w, 2 * F, n_out, F, rows, sw_b))); }
     }
-    { ProfScope ps(PC_GCONV_BWD, s0); gconv_small_grads_kernel<<<cdiv(n_out, 128), 128, 0, s0>>>(L.bsums, n_out, has_bn, g->fc_b, g->bn_g, g->bn_b);
-    MFT_CHECK_LAUNCH(); }
     br.join(0);
     br.join(1);
     MFT_REQUIRE(br.ok(), "gconv_bwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -145,7 +145,10 @@ int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const m
     GnnLayout G = gnn_layout(B, N, F0, nf, n_way, saved, workspace, precision);
     const int rows = B * N;
     MFT_CHECK_CUDA(cudaMemsetAsync(G.dxcat, 0, sizeof(float) * (size_t)rows * G.ldx, st));
-    Branches tail(st);   // slot 2: parameter-gradient finalisation of layer l beside the Gconv backward of layer l-1
+    // slot 2: parameter-gradient finalisation of layer l beside the Gconv backward of layer l-1
+    // slot 3: the Gconv's fc.weight gradient products beside the Wcompute backward of the same layer
+    // slot 4: tables and dgrad weight images of Wcompute l (parameters only) beside the Gconv backward of layer l
+    Branches tail(st);
     for (int l = G.L - 1; l >= 0; --l) {
         const bool last = (l == G.L - 1);
         // upstream of this Gconv: d_out for the last one, else the columns it produced in xcat
@@ -153,23 +156,29 @@ int gnn_bwd(const float* d_out, int B, int N, int F0, int nf, int n_way, const m
         const float* up = last ? d_out : G.dxcat + G.F[l];
         int ldu = last ? n_way : G.ldx;
         int rc;
+        const unsigned char* sh = l == 0 ? shared_nodes : nullptr;
+        rc = wcompute_bwd_prepare(B, N, G.F[l], nf, &p->w[l], G.wc_saved[l], G.wc_ws, precision, sh, tail.fork(4));
+        if (rc != MFT_OK) return rc;
         {
             ProfScope span(PC_SPAN_GC_BWD, st, false);
+            tail.join(3);      // the Gconv workspace (dY, T) is about to be rewritten
             rc = gconv_bwd(G.adj[l], G.xcat, G.ldx, B, N, G.F[l], G.nout[l], &p->l[l], last ? 0 : 1, up, ldu,
-                           G.dxcat, G.d_adj, &g->l[l], G.gc_saved[l], G.gc_ws, st);
+                           G.dxcat, G.d_adj, &g->l[l], G.gc_saved[l], G.gc_ws, st, &tail, 3);
             if (rc != MFT_OK) return rc;
             tail.join(2);      // the Wcompute workspace (partial dW copies, reductions) is about to be reused
+            tail.join(4);
         }
         {
             ProfScope span(PC_SPAN_WC_BWD, st, false);
             rc = wcompute_bwd(G.xcat, G.ldx, B, N, G.F[l], nf, &p->w[l], G.adj[l], G.d_adj, G.dxcat, &g->w[l],
-                              G.wc_saved[l], G.wc_ws, precision, l == 0 ? shared_nodes : nullptr, st, &tail, 2);
+                              G.wc_saved[l], G.wc_ws, precision, sh, st, &tail, 2, true);
         }
         if (rc != MFT_OK) return rc;
     }
     MFT_CHECK_CUDA(cudaMemcpy2DAsync(dx, sizeof(float) * F0, G.dxcat, sizeof(float) * G.ldx, sizeof(float) * F0,
                                      rows, cudaMemcpyDeviceToDevice, st));
     tail.join(2);
+    tail.join(3);
     MFT_REQUIRE(tail.ok(), "gnn_bwd: stream fork/join failed: %s", cudaGetErrorString(cudaGetLastError()));
     return MFT_OK;
 }

@@ -47,7 +47,7 @@ struct ProfScope {
 // ---------------------------------------------------------------------------------------------
 namespace mft {
 
-constexpr int kSideStreams = 4;   // 0, 1: inside one Wcompute / Gconv call; 2, 3: gnn_fwd / gnn_bwd across calls
+constexpr int kSideStreams = 5;   // 0, 1: inside one Wcompute / Gconv call; 2, 3, 4: gnn_fwd / gnn_bwd across calls
 
 class Branches {
 public:

@@ -1061,10 +1061,28 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     return MFT_OK;
 }
 
+// Parameter-only part of the backward: pair tables and (tensor-core path) the four dgrad weight images.  Touches
+// the tables and the image region of the workspace only (not the reductions / partial copies a previous layer's
+// gradient finalisation may still be reading).
+int wcompute_bwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params* p, void* saved, void* workspace,
+                         int precision, const unsigned char* shared_nodes, cudaStream_t st) {
+    WcLayout L = wc_layout(B, N, F, nf, saved, workspace, precision);
+    NodeMask mask;
+    const int n_shared = mask_from_host(shared_nodes, B, N, mask);
+    PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared, L.roww, L.rowij);
+    {
+        ProfScope ps(PC_PREP, st);
+        tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, st>>>(L.tri, L.inv, L.roww, L.rowij, B, N, g.Rg, g.Rs, n_shared, mask);
+        MFT_CHECK_LAUNCH();
+    }
+    if (precision == MFT_PREC_TF32) return wcompute_bwd_prepare_tf32(p, L, F, nf, st);   // four images, one launch
+    return MFT_OK;
+}
+
 int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
                  const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* gr, void* saved,
                  void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st,
-                 Branches* tail, int tail_slot) {
+                 Branches* tail, int tail_slot, bool prepared) {
     MFT_REQUIRE(B > 0 && N > 0 && F > 0 && nf > 0, "wcompute_bwd: bad shape");
     MFT_REQUIRE(2 * nf <= kMaxC, "wcompute_bwd: nf=%d exceeds the supported maximum %d", nf, kMaxC / 2);
     WcLayout L = wc_layout(B, N, F, nf, saved, workspace, precision);
@@ -1080,16 +1098,11 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     }
     {
         // the pair tables and (tensor-core path) the four dgrad weight images do not depend on the
-        // upstream gradient: build them on a side branch while the softmax backward runs
+        // upstream gradient: build them on a side branch while the softmax backward runs -- unless the caller
+        // has already had them built (wcompute_bwd_prepare; gnn_bwd does it beside the Gconv backward)
         Branches br(st);
-        cudaStream_t s0 = br.fork(0);
-        {
-            ProfScope ps(PC_PREP, s0);
-            tri_table_kernel<<<cdiv(g.Rg, 256), 256, 0, s0>>>(L.tri, L.inv, L.roww, L.rowij, B, N, g.Rg, g.Rs, n_shared, mask);
-            MFT_CHECK_LAUNCH();
-        }
-        if (precision == MFT_PREC_TF32) {
-            int rc = wcompute_bwd_prepare_tf32(p, L, F, nf, s0);   // all four dgrad weight images, one launch
+        if (!prepared) {
+            int rc = wcompute_bwd_prepare(B, N, F, nf, p, saved, workspace, precision, shared_nodes, br.fork(0));
             if (rc != MFT_OK) return rc;
         }
         {

@@ -63,7 +63,11 @@ int wcompute_fwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
 int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft_wcompute_params* p,
                  const float* adj, const float* d_adj, float* dx, const mft_wcompute_grads* gr, void* saved,
                  void* workspace, int precision, const unsigned char* shared_nodes, cudaStream_t st,
-                 class Branches* tail = nullptr, int tail_slot = 0);
+                 class Branches* tail = nullptr, int tail_slot = 0, bool prepared = false);
+// prepared: wcompute_bwd_prepare has run (and been joined) for this layer since the workspace's tables / images
+// were last overwritten.
+int wcompute_bwd_prepare(int B, int N, int F, int nf, const mft_wcompute_params* p, void* saved, void* workspace,
+                         int precision, const unsigned char* shared_nodes, cudaStream_t st);
 
 // tcgen05 (MFT_PREC_TF32) replacements for the four forward layer GEMMs and for the
 // dgrad + wgrad pair of one backward layer; same buffers in and out as the fp32 path.
@@ -101,9 +105,11 @@ int gconv_fwd_products(const float* x, int ldx, int B, int N, int F, int n_out, 
                        float* out, int ldo, void* saved, cudaStream_t st);
 int gconv_fwd_finish(const float* adj, int B, int N, int F, int n_out, const mft_gconv_params* p, int lrelu,
                      float* out, int ldo, void* saved, cudaStream_t st);
+// late / late_slot: side stream of the caller's Branches for the two fc.weight gradient products, which nothing
+// downstream of the call needs; the caller joins it before the Gconv workspace is reused (null: joined inside).
 int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, int n_out, const mft_gconv_params* p,
               int lrelu, const float* d_out, int ldo, float* dx, float* d_adj, const mft_gconv_grads* g,
-              void* saved, void* workspace, cudaStream_t st);
+              void* saved, void* workspace, cudaStream_t st, class Branches* late = nullptr, int late_slot = 0);
 
 // gconv_fused.cu: the whole Gconv forward in one launch (spin barriers between its phases)
 int gconv_fused_supported(int B, int N, int F, int n_out);

@@ -20,7 +20,7 @@ struct PlainOp {
     __device__ __forceinline__ float at(int r, int k, const float*) const { return p[(size_t)r * ld + k]; }
 };
 
-constexpr int kGcRows = 4;    // rows (nodes) per CTA in the per-node kernels
+constexpr int kGcRows = 4;    // rows (nodes) per CTA in the per-node kernels (8 / 16 measured: within noise)
 constexpr int kGcCols = 64;   // threads along the output channel
 
 // Y[r, c] += bias[c]; optional BatchNorm1d batch statistics (sum y, sum y^2) over the B*N rows.
@@ -484,7 +484,8 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     const int rows = B * N;
     const int has_bn = p->bn_g != nullptr;
 
-    MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)n_out * 2 * F, st));
+    // (d fc.weight is accumulated by split-K atomics: cleared on the stream its products run on)
+    if (!late) MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)n_out * 2 * F, st));
     // With Y = x Wa^T + adj (x Wb^T) + b every product of the backward runs on n_out (48 or n_way) columns or
     // over K = n_out, never on F x N:
     //   T     = adj^T dY                         [B][N, n_out]   (K = N)
@@ -518,6 +519,7 @@ int gconv_bwd(const float* adj, const float* x, int ldx, int B, int N, int F, in
     }
     // the two weight-gradient products: nothing downstream of this call reads them
     cudaStream_t sw_a = late ? late->fork(late_slot) : br.fork(0);       // T and dY exist
+    if (late) MFT_CHECK_CUDA(cudaMemsetAsync(g->fc_w, 0, sizeof(float) * (size_t)n_out * 2 * F, sw_a));
     {   // dx[r, f] += sum_c dY[r,c] fc_w[c, f] + sum_c T[r,c] fc_w[c, F + f]
         BView Dy{L.dY, 0, n_out, 1};                 // (m = row, k = c)
         BView Tt{L.T, 0, n_out, 1};

@@ -1090,7 +1090,6 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
     const int n_shared = mask_from_host(shared_nodes, B, N, mask);
     PairGeom g = make_geom(B, N, L.tri, L.inv, n_shared, L.roww, L.rowij);
 
-    MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * kStatSlot, st));
     int wg_copies[4] = {0, 0, 0, 0};
     if (precision != MFT_PREC_TF32) {
         for (int k = 0; k < 4; ++k)
@@ -1101,8 +1100,11 @@ int wcompute_bwd(const float* x, int ldx, int B, int N, int F, int nf, const mft
         // upstream gradient: build them on a side branch while the softmax backward runs -- unless the caller
         // has already had them built (wcompute_bwd_prepare; gnn_bwd does it beside the Gconv backward)
         Branches br(st);
+        cudaStream_t s0 = br.fork(0);
+        // (the reductions of the backward are first touched by the dy4 kernel: cleared beside the softmax backward)
+        MFT_CHECK_CUDA(cudaMemsetAsync(L.bsums, 0, sizeof(double) * 5 * kStatSlot, s0));
         if (!prepared) {
-            int rc = wcompute_bwd_prepare(B, N, F, nf, p, saved, workspace, precision, shared_nodes, br.fork(0));
+            int rc = wcompute_bwd_prepare(B, N, F, nf, p, saved, workspace, precision, shared_nodes, s0);
             if (rc != MFT_OK) return rc;
         }
         {

@@ -496,6 +496,14 @@ dy4_vec_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C,
 // owns the 4-channel groups (l & 7) + 8q.  Compared with one warp per row this divides the per-row
 // overhead (row decode, reduction shuffles, address arithmetic, scatter) by four, which is what
 // bounds these kernels once the loads are vectorised (ncu: issue-bound at ~1 TB/s).
+// Row quads a warp keeps in flight (measured on B200 with tools/ab_build2.sh, 5w20s step): score8 1 / 2 / 3 the
+// same; dy8 1: 1.2735 ms, 2: 1.2773, 3: 1.2855 (spills) -- its three reductions leave few registers for loads.
+#ifndef MFT_SCORE_RU
+#define MFT_SCORE_RU 2
+#endif
+#ifndef MFT_DY_RU
+#define MFT_DY_RU 1
+#endif
 template <int NGL>
 struct Lane8Consts {
     float4 sc[NGL], sh[NGL], wl[NGL];
@@ -542,7 +550,7 @@ score8_kernel(const void* __restrict__ H4, int C, const double* sums, const floa
     Lane8Consts<NGL> k;
     lane8_consts<NGL>(k, aux, wls, C, sl);
     const float bias = last_b[0];
-    constexpr int RU = 2;                          // row quads in flight per warp
+    constexpr int RU = MFT_SCORE_RU;               // row quads in flight per warp
     const int stride = gridDim.x * kRowWarps * 4;  // rows per grid sweep
     for (int rb = (blockIdx.x * kRowWarps + warp) * 4; rb < g.R; rb += RU * stride) {   // warp-uniform trip count
         const int r0 = rb + rg;
@@ -600,7 +608,7 @@ dy8_kernel(const float* __restrict__ dS, const void* __restrict__ H4, int C, con
     float4 p0[NGL], p1[NGL], p2[NGL];
 #pragma unroll
     for (int q = 0; q < NGL; ++q) p0[q] = p1[q] = p2[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    constexpr int RU = 2;
+    constexpr int RU = MFT_DY_RU;
     const int stride = gridDim.x * kRowWarps * 4;
     for (int rb = (blockIdx.x * kRowWarps + warp) * 4; rb < g.R; rb += RU * stride) {   // warp-uniform trip count
         const int r0 = rb + rg;

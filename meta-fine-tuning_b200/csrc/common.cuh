@@ -196,9 +196,14 @@ __device__ __forceinline__ float dlrelu(float y) { return y > 0.f ? 1.f : kSlope
 // Batch statistics of one BN layer live in a "slot": kStatCopies copies of [2][C] doubles
 // (which = 0: sum w*h or sum dy, which = 1: sum w*h^2 or sum dy*hhat).  CTAs accumulate with fp64
 // atomics into copy (blockIdx.x % kStatCopies): same-address atomics serialise in L2 (~200 cycles
-// each, measured: 148 CTAs on one copy cost 17 us per layer), sixteen copies cut that to ~10 per
-// address.  Consumers add the copies up (stat_get) and turn them into mean / rstd themselves.
-constexpr int kStatCopies = 16;
+// each, measured: 148 CTAs on one copy cost 17 us per layer), a few copies remove that.  Consumers add
+// the copies up (stat_get) and turn them into mean / rstd themselves -- in EVERY kernel's prologue, on the critical
+// path of every launch, which is why more is not better (5w20s step on B200, tools/ab_build2.sh: 2 / 4 / 6 copies
+// 1.251 ms, 8: 1.255, 16: 1.272, 32: 1.321).
+#ifndef MFT_STAT_COPIES
+#define MFT_STAT_COPIES 4
+#endif
+constexpr int kStatCopies = MFT_STAT_COPIES;
 constexpr int kStatCopyStride = 2 * kMaxC;
 constexpr int kStatSlot = kStatCopies * kStatCopyStride;   // doubles per slot
 

@@ -7,7 +7,7 @@
 //
 //   phase 1   [U | V] = x_slab [Wa | Wb]^T                  (32 x 2 n_out outputs, K = F through shared memory)
 //             V goes to global memory; a per-GRAPH counter tells when all slabs of the graph have written theirs
-//   phase 2   Y = U + A_slab V_graph + b ;  per-column sum / sum of squares -> fp64 atomics (16 copies)
+//   phase 2   Y = U + A_slab V_graph + b ;  per-column sum / sum of squares -> fp64 atomics (kStatCopies copies)
 //             a GRID-wide counter tells when every CTA has contributed
 //   phase 3   out = LeakyReLU(BN(Y)) with the batch statistics over all B*N rows (skipped without BatchNorm)
 //
@@ -177,7 +177,7 @@ gconv_fused_fwd_kernel(const GconvFusedArgs a) {
         }
         return;
     }
-    // column statistics: 8 row groups -> shared memory -> one fp64 atomic per column per CTA (16 copies)
+    // column statistics: 8 row groups -> shared memory -> one fp64 atomic per column per CTA (kStatCopies copies)
     __syncthreads();                                           // vs / as no longer needed: reuse the union region
     float* red = un;                                           // [8][2][GF_MAX_OUT]
     if (c0) { red[(ty * 2 + 0) * GF_MAX_OUT + tx] = p0[0]; red[(ty * 2 + 1) * GF_MAX_OUT + tx] = p1[0]; }
